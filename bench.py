@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- fwd+bwd Mpix/s of the differentiable gaussian rasterizer (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                     (the path's CPU implementation, timed alone)
+
+A *step* is one pass of the hot path over one batch of synthetic input: every rank renders its
+`--views-per-rank` camera views of the SAME replicated gaussians forward + backward (L1 loss against a
+synthetic target image), gradients accumulate in one flat bucket, and ONE NCCL all-reduce sums the bucket
+over ranks (view-parallel, weak scaling: views per rank fixed).  Workload = BASELINE.json configs[2]
+(1 M random gaussians, 1920x1080, SH degree 3); with 8 views per rank, N=8 is configs[4] (64 views).
+
+`value`   : inputs (cameras, target images) resident in HBM; device-timed (CUDA events), max over ranks.
+`e2e`     : same step through the public API with HOST inputs: each view's camera matrices and target
+            image are copied from pinned host memory inside the timed region and the step's loss is read
+            back to the host (the host<->device crossings of the reference's loop: train.py:119,148).
+            The gaussians are the model state and stay resident, as they do in the reference.
+`roofline`: dominant kernel (render_bwd) -- algorithmic bytes / CUDA-event time on its launch stream.
+`cpu_baseline` / `--impl reference`: the CPU restatement of the path (oracle/gs_oracle.c, OpenMP over all
+            host cores).  The reference's own rasterizer sources are absent from /root/reference
+            (SURVEY.md section 0), so there is no oracle/_ref and kind is "port".
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "gaussian-splatting_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "fwd+bwd Mpix/s @1M gaussians 1080p"
+UNIT = "Mpix/s"
+LOG_SCALE_MEAN = -5.3   # mean reference tiles-touched per visible gaussian ~= 7 (SURVEY.md 8d asks 4-8)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--views-per-rank", type=int, default=8)
+    ap.add_argument("--gaussians", type=int, default=1_000_000)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--sh-degree", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
+    return ap.parse_args()
+
+
+class BenchCamera:
+    """The attributes render() reads from scene.cameras.Camera (/root/reference/scene/cameras.py:19-89)."""
+
+    def __init__(self, width, height, fovx, R, T, device):
+        from oracle import torch_oracle as TO  # camera formulae only (cameras.py:80-89), no compute
+        self.image_width, self.image_height = width, height
+        self.FoVx = fovx
+        self.FoVy = 2.0 * math.atan(math.tan(fovx / 2) * height / width)
+        wvt, full, center = TO.camera_matrices(R, T, self.FoVx, self.FoVy)
+        self.host = dict(wvt=wvt.contiguous().pin_memory() if device != "cpu" else wvt,
+                         full=full.contiguous().pin_memory() if device != "cpu" else full,
+                         center=center.contiguous().pin_memory() if device != "cpu" else center)
+        self.world_view_transform = wvt.to(device)
+        self.full_proj_transform = full.to(device)
+        self.camera_center = center.to(device)
+        self.image_name = "synthetic"
+
+    def upload(self, device):
+        """e2e leg: per-view camera tensors come from pinned host memory."""
+        self.world_view_transform = self.host["wvt"].to(device, non_blocking=True)
+        self.full_proj_transform = self.host["full"].to(device, non_blocking=True)
+        self.camera_center = self.host["center"].to(device, non_blocking=True)
+        return 4 * (16 + 16 + 3)
+
+
+def view_pose(global_index: int, radius: float):
+    """Cameras on a sphere of radius 3R looking at the origin; golden-angle spiral."""
+    from oracle import torch_oracle as TO
+    k = global_index
+    phi = k * 2.399963229728653
+    y = 0.35 * math.sin(0.61803398875 * k * 2 * math.pi)
+    r = math.sqrt(max(0.0, 1 - y * y))
+    eye = (radius * r * math.sin(phi), radius * y, -radius * r * math.cos(phi))
+    return TO.look_at_camera(eye)
+
+
+class BenchGaussians:
+    """Duck-typed stand-in for scene.GaussianModel: activated tensors as leaves (the rasterizer's inputs)."""
+
+    def __init__(self, scene, sh_degree, device):
+        import torch
+        self.active_sh_degree = sh_degree
+        self.max_sh_degree = int(round(math.sqrt(scene["shs"].shape[1]))) - 1
+        mk = lambda t: t.to(device).contiguous().requires_grad_(True)
+        self._xyz, self._shs, self._opacity = mk(scene["means3D"]), mk(scene["shs"]), mk(scene["opacities"])
+        self._scaling, self._rotation = mk(scene["scales"]), mk(scene["rotations"])
+
+    def parameters(self):
+        return [self._xyz, self._shs, self._opacity, self._scaling, self._rotation]
+
+    get_xyz = property(lambda s: s._xyz)
+    get_features = property(lambda s: s._shs)
+    get_opacity = property(lambda s: s._opacity)
+    get_scaling = property(lambda s: s._scaling)
+    get_rotation = property(lambda s: s._rotation)
+
+
+class Pipe:
+    debug = False
+    antialiasing = False
+    compute_cov3D_python = False
+    convert_SHs_python = False
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_pass(scene, cam_settings, repeats):
+    """One full-frame forward+backward of the CPU oracle per repeat; returns (seconds per pass, threads)."""
+    import numpy as np
+    from oracle.c_oracle import COracle, threads
+    H, W = cam_settings.image_height, cam_settings.image_width
+    rng = np.random.default_rng(0)
+    dL = rng.standard_normal((3, H, W)).astype(np.float32)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        co = COracle(scene["means3D"], scene["shs"], None, scene["opacities"], scene["scales"], scene["rotations"],
+                     None, cam_settings)
+        co.backward(dL, None)
+        co.close()
+        times.append(time.perf_counter() - t0)
+    return times, threads()
+
+
+def oracle_settings(cam: BenchCamera, sh_degree: int):
+    import torch
+    from oracle import torch_oracle as TO
+    return TO.OracleSettings(image_height=cam.image_height, image_width=cam.image_width,
+                             tanfovx=math.tan(cam.FoVx * 0.5), tanfovy=math.tan(cam.FoVy * 0.5),
+                             bg=torch.zeros(3), scale_modifier=1.0, viewmatrix=cam.world_view_transform.cpu(),
+                             projmatrix=cam.full_proj_transform.cpu(), sh_degree=sh_degree,
+                             campos=cam.camera_center.cpu(), prefiltered=False, debug=False, antialiasing=False)
+
+
+def workload_config(a, world):
+    return {"workload": f"{a.gaussians} random gaussians, {a.width}x{a.height}, SH degree {a.sh_degree}, fwd+bwd "
+                        f"(BASELINE.json configs[2]); {a.views_per_rank} views per rank",
+            "gaussians": a.gaussians, "image": [a.width, a.height], "sh_degree": a.sh_degree,
+            "views_per_rank": a.views_per_rank, "views_total": a.views_per_rank * world,
+            "parallelism": f"view-parallel x{world}, gaussians replicated, one all-reduce of 59 floats/gaussian",
+            "l2": "inputs_exceed_l2 (236 MB parameters + 8 distinct views per step; no explicit flush)",
+            "scene": f"xyz~U([-1,1]^3), log-scale~N({LOG_SCALE_MEAN},0.5), opacity=sigmoid(U(-2,4)), cameras on sphere r=3, seed 0"}
+
+
+def run_reference(a):
+    """--impl reference: the path's CPU implementation on the host cores, one view per step (bounded sample)."""
+    import torch
+    from oracle import torch_oracle as TO
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene = TO.make_scene(a.gaussians, seed=0, log_scale_mean=LOG_SCALE_MEAN)
+    R, T = view_pose(0, 3.0)
+    cam = BenchCamera(a.width, a.height, math.radians(60.0), R, T, "cpu")
+    cs = oracle_settings(cam, a.sh_degree)
+    times, nthreads = cpu_reference_pass(scene, cs, a.warmup + a.steps)
+    timed = times[a.warmup:]
+    total = sum(timed)
+    mpix = a.width * a.height / 1e6
+    value = mpix * len(timed) / total
+    sample = "1 full view (forward+backward) per step"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, max(1, a.gpus)),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "CPU port of the path (oracle/gs_oracle.c, OpenMP); the reference's CUDA rasterizer sources "
+                    "are absent from /root/reference so its own implementation cannot be built or timed"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    import torch
+    import torch.distributed as dist
+    from oracle import torch_oracle as TO   # scene + camera generators (shared with the tests); no compute
+    import diff_gaussian_rasterization as dgr
+    from gaussian_renderer import GradientBucket, render
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the rasterizer has no CPU path (use --impl reference for the CPU port)")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != a.gpus and rank == 0:
+        print(f"# note: --gpus {a.gpus} but WORLD_SIZE {world}; using {world}", file=sys.stderr)
+
+    torch.manual_seed(0)
+    scene = TO.make_scene(a.gaussians, seed=0, log_scale_mean=LOG_SCALE_MEAN)
+    pc = BenchGaussians(scene, a.sh_degree, dev)
+    bucket = GradientBucket(pc.parameters())
+    pipe = Pipe()
+    bg = torch.zeros(3, device=dev)
+    V, H, W = a.views_per_rank, a.height, a.width
+    cams = [BenchCamera(W, H, math.radians(60.0), *view_pose(rank * V + i, 3.0), dev) for i in range(V)]
+    gen = torch.Generator().manual_seed(1234 + rank)
+    gt_host = [torch.rand(3, H, W, generator=gen).pin_memory() for _ in range(V)]
+    gt_dev = [g.to(dev) for g in gt_host]
+    mpix_step = V * world * H * W / 1e6
+
+    def step(host_inputs: bool):
+        bucket.zero_()
+        total = torch.zeros((), device=dev)
+        for i, cam in enumerate(cams):
+            if host_inputs:
+                cam.upload(dev)
+                gt = gt_host[i].to(dev, non_blocking=True)
+            else:
+                gt = gt_dev[i]
+            pkg = render(cam, pc, pipe, bg)
+            loss = (pkg["render"] - gt).abs().mean()
+            loss.backward()
+            total += loss.detach()
+        bucket.all_reduce()
+        if host_inputs:
+            return float(total.item())   # device -> host read of the step's result
+        return None
+
+    def timed(host_inputs: bool, steps: int):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(host_inputs)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident leg ----
+    for _ in range(max(a.warmup, 3)):
+        step(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dgr.set_option("time_kernels", 1)
+    dgr.kernel_time("", reset=True)
+    dgr.reset_launch_count()
+    ms_total = timed(False, a.steps)
+    launches = dgr.launch_count()
+    bwd_ms, bwd_n = dgr.kernel_time("render_bwd")
+    fwd_ms, fwd_n = dgr.kernel_time("render_fwd", reset=True)
+    dgr.set_option("time_kernels", 0)
+    clocks = sampler.stop() if rank == 0 else None
+    value = mpix_step * a.steps / (ms_total / 1e3)
+
+    # ---- end-to-end leg (host inputs) ----
+    for _ in range(max(a.warmup, 3)):
+        step(True)
+    ms_e2e = timed(True, a.steps)
+    e2e_value = mpix_step * a.steps / (ms_e2e / 1e3)
+    h2d = V * (3 * H * W * 4 + 4 * 35)
+    d2h = 4
+
+    # ---- instance statistics + per-kernel breakdown of one view (outside the timed regions) ----
+    with torch.no_grad():
+        rs = dgr.GaussianRasterizationSettings(H, W, math.tan(cams[0].FoVx * 0.5), math.tan(cams[0].FoVy * 0.5), bg, 1.0,
+                                               cams[0].world_view_transform, cams[0].full_proj_transform, a.sh_degree,
+                                               cams[0].camera_center, False, False, False)
+        _, radii, _, pack = dgr._forward_impl(pc._xyz.detach(), pc._shs.detach(), None, pc._opacity.detach().reshape(-1),
+                                              pc._scaling.detach(), pc._rotation.detach(), None, rs)
+        sv = dgr.state_views(pack, H, W)
+        D = int(pack["num_rendered"])
+        lens = (sv["ranges"][:, 1] - sv["ranges"][:, 0]).float()
+        nc = sv["n_contrib"]
+        gy, gx = (H + 15) // 16, (W + 15) // 16
+        pad = torch.zeros(gy * 16, gx * 16, dtype=nc.dtype, device=dev)
+        pad[:H, :W] = nc
+        tile_max = pad.view(gy, 16, gx, 16).permute(0, 2, 1, 3).reshape(gy * gx, 256).max(dim=1).values
+        D_visited = int(tile_max.sum().item())
+        stats = {"P_visible": int((radii > 0).sum().item()), "D": D, "D_visited_bwd": D_visited,
+                 "tile_list_mean": float(lens.mean().item()), "tile_list_max": int(lens.max().item()),
+                 "n_contrib_mean": float(nc.float().mean().item())}
+    dgr.set_option("time_kernels", 2)
+    dgr.kernel_time("", reset=True)
+    for _ in range(2):
+        step(False)
+    torch.cuda.synchronize()
+    breakdown = {}
+    for name in ("preprocess_fwd", "sort_hist", "sort_rowscan", "sort_scatter", "scan_reduce", "scan_partials",
+                 "scan_apply", "emit", "tile_ranges", "render_fwd", "render_bwd", "preprocess_bwd"):
+        t, n = dgr.kernel_time(name)
+        breakdown[name] = round(t / (2 * V), 4)
+    dgr.kernel_time("", reset=True)
+    dgr.set_option("time_kernels", 0)
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (render_bwd); byte counts per DESIGN.md ----
+    npix = H * W
+    bytes_bwd = D_visited * (4 + 48 + 40) + npix * 24
+    bytes_fwd = D_visited * (4 + 48) + npix * 24
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("render_bwd_dram_bytes_per_launch")
+    except Exception:
+        pass
+    bwd_avg_ms = bwd_ms / max(1, bwd_n)
+    fwd_avg_ms = fwd_ms / max(1, fwd_n)
+    achieved = bytes_bwd / (bwd_avg_ms * 1e-3) / 1e9 if bwd_avg_ms > 0 else 0.0
+    roofline = {"kernel": "render_bwd", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
+                "algorithmic_bytes_per_launch": bytes_bwd, "avg_launch_ms": bwd_avg_ms, "launches_timed": bwd_n,
+                "render_fwd": {"avg_launch_ms": fwd_avg_ms, "algorithmic_bytes_per_launch": bytes_fwd,
+                               "achieved": bytes_fwd / (fwd_avg_ms * 1e-3) / 1e9 if fwd_avg_ms > 0 else 0.0,
+                               "frac": (bytes_fwd / (fwd_avg_ms * 1e-3) / 1e9 / peak) if fwd_avg_ms > 0 else 0.0}}
+
+    cpu = None
+    if not a.no_cpu_baseline and world == 1:
+        cs = oracle_settings(cams[0], a.sh_degree)
+        t0 = time.perf_counter()
+        times, nthreads = cpu_reference_pass(scene, cs, 1)
+        reps = int(max(0, min(3, (a.cpu_baseline_seconds - (time.perf_counter() - t0)) // max(times[0], 1e-3))))
+        if reps > 0:
+            more, _ = cpu_reference_pass(scene, cs, reps)
+            times += more
+        cpu = {"value": (H * W / 1e6) * len(times) / sum(times), "unit": UNIT, "cores": nthreads, "kind": "port",
+               "sample": f"{len(times)} full view(s) of the same workload, forward+backward, oracle/gs_oracle.c"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(a, world), "roofline": roofline,
+            "cpu_baseline": cpu, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": launches, "clocks": clocks, "scene_stats": stats, "kernel_ms_per_view": breakdown}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

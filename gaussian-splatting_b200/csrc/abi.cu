@@ -1,0 +1,376 @@
+// abi.cu -- extern "C" entry points of libgs_b200.so (include/gs_b200.h) and the host-side
+// orchestration of the forward / backward kernel sequences.
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace gsb {
+
+static thread_local char g_err[512] = "";
+int64_t g_launch_count = 0;
+
+int g_time_kernels = 0;
+
+// ---- kernel timing records ----
+struct TimerRec { char name[32]; cudaEvent_t e0, e1; };
+static std::vector<TimerRec *> g_timer_recs;
+
+void *timer_begin(const char *name, cudaStream_t stream) {
+    if (g_time_kernels == 1 && strncmp(name, "render_", 7) != 0) return nullptr;
+    TimerRec *r = new TimerRec();
+    strncpy(r->name, name, sizeof(r->name) - 1);
+    r->name[sizeof(r->name) - 1] = 0;
+    if (cudaEventCreate(&r->e0) != cudaSuccess || cudaEventCreate(&r->e1) != cudaSuccess) { delete r; return nullptr; }
+    cudaEventRecord(r->e0, stream);
+    return r;
+}
+
+void timer_end(void *token, cudaStream_t stream) {
+    TimerRec *r = static_cast<TimerRec *>(token);
+    cudaEventRecord(r->e1, stream);
+    g_timer_recs.push_back(r);
+}
+
+static int opt_cull = 1;
+static int opt_fwd_variant = 0;
+static int opt_bwd_variant = 0;
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char *what, bool debug, cudaStream_t stream) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && debug) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+        set_error("kernel %s failed: %s", what, cudaGetErrorString(e));
+        return GSB_ERR_CUDA;
+    }
+    return GSB_OK;
+}
+
+// pinned read-back slot for the instance count, one per device, created on first use
+static unsigned long long *pinned_slot() {
+    static unsigned long long *slots[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!slots[dev]) {
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, 64, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+        slots[dev] = static_cast<unsigned long long *>(p);
+    }
+    return slots[dev];
+}
+
+static int bits_for(uint32_t max_value) {
+    int b = 1;
+    while (b < 32 && (max_value >> b) != 0u) ++b;
+    return b;
+}
+
+static int make_cam(const GsbSettings *s, CamArgs &c) {
+    if (!s->bg || !s->viewmatrix || !s->projmatrix || !s->campos) {
+        set_error("settings: bg / viewmatrix / projmatrix / campos must be device pointers");
+        return GSB_ERR_ARGUMENT;
+    }
+    if (s->image_width <= 0 || s->image_height <= 0 || s->image_width > 16 * 65535 || s->image_height > 16 * 65535) {
+        set_error("settings: bad image size %d x %d", s->image_width, s->image_height);
+        return GSB_ERR_ARGUMENT;
+    }
+    if (s->sh_degree < 0 || s->sh_degree > 3) {
+        set_error("settings: sh_degree %d outside 0..3", s->sh_degree);
+        return GSB_ERR_ARGUMENT;
+    }
+    c.view = s->viewmatrix; c.proj = s->projmatrix; c.campos = s->campos; c.bg = s->bg;
+    c.tanfovx = s->tanfovx; c.tanfovy = s->tanfovy;
+    c.W = s->image_width; c.H = s->image_height;
+    c.focal_x = c.W / (2.0f * s->tanfovx);
+    c.focal_y = c.H / (2.0f * s->tanfovy);
+    c.scale_modifier = s->scale_modifier;
+    c.gx = (c.W + TILE - 1) / TILE; c.gy = (c.H + TILE - 1) / TILE;
+    c.sh_degree = s->sh_degree; c.sh_coeffs = s->sh_coeffs; c.antialiasing = s->antialiasing;
+    return GSB_OK;
+}
+
+static int check_inputs(const GsbSettings *s, const GsbInputs *in) {
+    if (in->P < 0) { set_error("inputs: P < 0"); return GSB_ERR_ARGUMENT; }
+    if (in->P > 0 && (!in->means3D || !in->opacities)) { set_error("inputs: means3D / opacities missing"); return GSB_ERR_ARGUMENT; }
+    if (in->P > 0 && ((in->shs != nullptr) == (in->colors_precomp != nullptr))) {
+        set_error("inputs: provide exactly one of shs / colors_precomp");
+        return GSB_ERR_ARGUMENT;
+    }
+    const bool sr = in->scales != nullptr && in->rotations != nullptr;
+    if (in->P > 0 && (sr == (in->cov3D_precomp != nullptr))) {
+        set_error("inputs: provide exactly one of (scales, rotations) / cov3D_precomp");
+        return GSB_ERR_ARGUMENT;
+    }
+    if (in->shs && s->sh_coeffs < (s->sh_degree + 1) * (s->sh_degree + 1)) {
+        set_error("inputs: shs has %d coefficients, degree %d needs %d", s->sh_coeffs, s->sh_degree,
+                  (s->sh_degree + 1) * (s->sh_degree + 1));
+        return GSB_ERR_ARGUMENT;
+    }
+    return GSB_OK;
+}
+
+static void *do_alloc(gsb_alloc_fn alloc, void *ctx, int which, size_t bytes) {
+    void *p = alloc(ctx, which, bytes < 256 ? 256 : bytes);
+    if (!p) set_error("allocator returned NULL for buffer %d (%zu bytes)", which, bytes);
+    return p;
+}
+
+struct ImageView { float *final_T; uint32_t *n_contrib; };
+static size_t carve_image(void *base, size_t npix, ImageView &v) {
+    Carver c(base);
+    v.final_T = c.take<float>(npix);
+    v.n_contrib = c.take<uint32_t>(npix);
+    return c.bytes();
+}
+struct BinningView { uint32_t *point_list; uint2 *ranges; };
+static size_t carve_binning(void *base, int64_t D, int num_tiles, BinningView &v) {
+    Carver c(base);
+    v.point_list = c.take<uint32_t>((size_t)(D > 0 ? D : 1));
+    v.ranges = c.take<uint2>((size_t)num_tiles);
+    return c.bytes();
+}
+
+}  // namespace gsb
+
+using namespace gsb;
+
+extern "C" {
+
+const char *gsb_last_error(void) { return g_err; }
+int32_t gsb_abi_version(void) { return GSB_ABI_VERSION; }
+int64_t gsb_launch_count(void) { return g_launch_count; }
+void gsb_reset_launch_count(void) { g_launch_count = 0; }
+
+int32_t gsb_set_option(const char *name, int32_t value) {
+    if (!name) return 1;
+    if (!strcmp(name, "cull")) { opt_cull = value; return 0; }
+    if (!strcmp(name, "time_kernels")) { g_time_kernels = value; return 0; }
+    if (!strcmp(name, "render_fwd_variant")) { opt_fwd_variant = value; return 0; }
+    if (!strcmp(name, "render_bwd_variant")) { opt_bwd_variant = value; return 0; }
+    return 1;
+}
+
+int32_t gsb_kernel_time(const char *name, double *total_ms, int64_t *launches, int32_t reset) {
+    // waits for the recorded events; name == NULL or "" sums every kernel
+    double ms = 0.0;
+    int64_t n = 0;
+    for (TimerRec *r : g_timer_recs) {
+        if (name && name[0] && strcmp(name, r->name) != 0) continue;
+        float t = 0.f;
+        if (cudaEventSynchronize(r->e1) == cudaSuccess && cudaEventElapsedTime(&t, r->e0, r->e1) == cudaSuccess) {
+            ms += t;
+            ++n;
+        }
+    }
+    if (reset) {
+        for (TimerRec *r : g_timer_recs) { cudaEventDestroy(r->e0); cudaEventDestroy(r->e1); delete r; }
+        g_timer_recs.clear();
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = n;
+    return GSB_OK;
+}
+
+int32_t gsb_forward(const GsbSettings *s, const GsbInputs *in, float *out_color, int32_t *out_radii,
+                    float *out_invdepth, gsb_alloc_fn alloc, void *alloc_ctx, GsbState *st, void *cuda_stream) {
+    if (!s || !in || !out_color || !out_radii || !out_invdepth || !alloc || !st) {
+        set_error("gsb_forward: NULL argument");
+        return GSB_ERR_ARGUMENT;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    const bool debug = s->debug != 0;
+    CamArgs cam;
+    int rc = make_cam(s, cam);
+    if (rc) return rc;
+    rc = check_inputs(s, in);
+    if (rc) return rc;
+    const int P = in->P;
+    const int num_tiles = cam.gx * cam.gy;
+    const size_t npix = (size_t)cam.W * cam.H;
+    memset(st, 0, sizeof(*st));
+    st->P = P; st->num_tiles = num_tiles; st->num_visible = -1;
+
+    // ---- per-gaussian state ----
+    const size_t Pn = (size_t)(P > 0 ? P : 1);
+    st->geom_bytes = align_up(Pn * SPLAT_F4 * sizeof(float4), 256);
+    st->geom = do_alloc(alloc, alloc_ctx, GSB_BUF_GEOM, st->geom_bytes);
+    if (!st->geom) return GSB_ERR_ALLOC;
+    float4 *splat = static_cast<float4 *>(st->geom);
+
+    Carver c0(nullptr);
+    auto carve0 = [&](Carver &c, uint32_t *&key, uint32_t *&idx, uint32_t *&key_alt, uint32_t *&idx_alt, uint32_t *&tiles,
+                      uint2 *&rect, uint32_t *&offsets, uint32_t *&partials, unsigned long long *&total, char *&sortscr) {
+        key = c.take<uint32_t>(Pn); idx = c.take<uint32_t>(Pn); key_alt = c.take<uint32_t>(Pn); idx_alt = c.take<uint32_t>(Pn);
+        tiles = c.take<uint32_t>(Pn); rect = c.take<uint2>(Pn); offsets = c.take<uint32_t>(Pn);
+        partials = c.take<uint32_t>(scan_partials_count(P)); total = c.take<unsigned long long>(4);
+        sortscr = c.take<char>(sort_scratch_bytes(P));
+    };
+    uint32_t *key, *idx, *key_alt, *idx_alt, *tiles, *offsets, *partials; uint2 *rect; unsigned long long *total; char *sortscr;
+    carve0(c0, key, idx, key_alt, idx_alt, tiles, rect, offsets, partials, total, sortscr);
+    void *scr0 = do_alloc(alloc, alloc_ctx, GSB_BUF_SCRATCH0, c0.bytes());
+    if (!scr0) return GSB_ERR_ALLOC;
+    Carver c0r(scr0);
+    carve0(c0r, key, idx, key_alt, idx_alt, tiles, rect, offsets, partials, total, sortscr);
+
+    int64_t D = 0;
+    if (P > 0) {
+        PreFwdArgs pa;
+        pa.P = P; pa.means = in->means3D; pa.shs = in->shs; pa.colors = in->colors_precomp; pa.opac = in->opacities;
+        pa.scales = in->scales; pa.rots = in->rotations; pa.cov_pre = in->cov3D_precomp;
+        pa.splat = splat; pa.depth_key = key; pa.depth_idx = idx; pa.tiles = tiles; pa.rect = rect; pa.radii = out_radii;
+        pa.cull = opt_cull;
+        rc = launch_preprocess_fwd(cam, pa, debug, stream);
+        if (rc) return rc;
+        // gaussians by depth (culled ones carry key 0xffffffff and sort to the end)
+        rc = sort_pairs(key, idx, key_alt, idx_alt, P, 0, 32, sortscr, debug, stream);
+        if (rc) return rc;
+        BinArgs ba;
+        ba.P = P; ba.num_tiles = num_tiles; ba.gx = cam.gx; ba.order = idx; ba.tiles = tiles; ba.rect = rect; ba.splat = splat;
+        ba.offsets = offsets; ba.partials = partials; ba.total = total;
+        rc = launch_tile_scan(ba, debug, stream);
+        if (rc) return rc;
+        // the one host synchronisation of the forward pass: the instance count sizes the next buffers
+        unsigned long long *h = pinned_slot();
+        if (!h) { set_error("pinned read-back slot unavailable"); return GSB_ERR_CUDA; }
+        GSB_CUDA(cudaMemcpyAsync(h, total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        GSB_CUDA(cudaStreamSynchronize(stream));
+        if (*h >= (1ull << 31)) {
+            set_error("instance count %llu exceeds 2^31", *h);
+            return GSB_ERR_OVERFLOW;
+        }
+        D = (int64_t)*h;
+
+        BinningView bv;
+        st->binning_bytes = carve_binning(nullptr, D, num_tiles, bv);
+        st->binning = do_alloc(alloc, alloc_ctx, GSB_BUF_BINNING, st->binning_bytes);
+        if (!st->binning) return GSB_ERR_ALLOC;
+        carve_binning(st->binning, D, num_tiles, bv);
+
+        if (D > 0) {
+            const size_t Dn = (size_t)D;
+            Carver c1(nullptr);
+            c1.take<uint32_t>(Dn); c1.take<uint32_t>(Dn); c1.take<uint32_t>(Dn); c1.take<char>(sort_scratch_bytes(D));
+            void *scr1 = do_alloc(alloc, alloc_ctx, GSB_BUF_SCRATCH1, c1.bytes());
+            if (!scr1) return GSB_ERR_ALLOC;
+            Carver c1r(scr1);
+            uint32_t *inst_tile = c1r.take<uint32_t>(Dn), *inst_tile_alt = c1r.take<uint32_t>(Dn), *inst_gauss_alt = c1r.take<uint32_t>(Dn);
+            char *sortscr1 = c1r.take<char>(sort_scratch_bytes(D));
+            rc = launch_emit(ba, inst_tile, bv.point_list, debug, stream);
+            if (rc) return rc;
+            rc = sort_pairs(inst_tile, bv.point_list, inst_tile_alt, inst_gauss_alt, D, 0, bits_for((uint32_t)num_tiles), sortscr1, debug, stream);
+            if (rc) return rc;
+            rc = launch_tile_ranges(inst_tile, D, num_tiles, bv.ranges, debug, stream);
+            if (rc) return rc;
+        } else {
+            rc = launch_tile_ranges(nullptr, 0, num_tiles, bv.ranges, debug, stream);
+            if (rc) return rc;
+        }
+    } else {
+        BinningView bv;
+        st->binning_bytes = carve_binning(nullptr, 0, num_tiles, bv);
+        st->binning = do_alloc(alloc, alloc_ctx, GSB_BUF_BINNING, st->binning_bytes);
+        if (!st->binning) return GSB_ERR_ALLOC;
+        carve_binning(st->binning, 0, num_tiles, bv);
+        rc = launch_tile_ranges(nullptr, 0, num_tiles, bv.ranges, debug, stream);
+        if (rc) return rc;
+    }
+    st->num_rendered = D;
+
+    // ---- per-pixel state + blend ----
+    ImageView iv;
+    st->image_bytes = carve_image(nullptr, npix, iv);
+    st->image = do_alloc(alloc, alloc_ctx, GSB_BUF_IMAGE, st->image_bytes);
+    if (!st->image) return GSB_ERR_ALLOC;
+    carve_image(st->image, npix, iv);
+    BinningView bv;
+    carve_binning(st->binning, D, num_tiles, bv);
+    RenderFwdArgs ra;
+    ra.W = cam.W; ra.H = cam.H; ra.gx = cam.gx; ra.gy = cam.gy; ra.ranges = bv.ranges; ra.point_list = bv.point_list;
+    ra.splat = splat; ra.bg = s->bg; ra.out_color = out_color; ra.out_invdepth = out_invdepth; ra.final_T = iv.final_T;
+    ra.n_contrib = iv.n_contrib;
+    return launch_render_fwd(ra, opt_fwd_variant, debug, stream);
+}
+
+int32_t gsb_backward(const GsbSettings *s, const GsbInputs *in, const GsbState *st, const float *dL_dcolor,
+                     const float *dL_dinvdepth, const GsbGrads *grads, int32_t accumulate, gsb_alloc_fn alloc,
+                     void *alloc_ctx, void *cuda_stream) {
+    if (!s || !in || !st || !dL_dcolor || !grads || !alloc) {
+        set_error("gsb_backward: NULL argument");
+        return GSB_ERR_ARGUMENT;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    const bool debug = s->debug != 0;
+    CamArgs cam;
+    int rc = make_cam(s, cam);
+    if (rc) return rc;
+    rc = check_inputs(s, in);
+    if (rc) return rc;
+    const int P = in->P;
+    if (P != st->P || st->num_tiles != cam.gx * cam.gy || !st->geom || !st->binning || !st->image) {
+        set_error("gsb_backward: state does not match the inputs (P %d vs %d)", P, st->P);
+        return GSB_ERR_ARGUMENT;
+    }
+    if (P == 0) return GSB_OK;
+    const size_t npix = (size_t)cam.W * cam.H;
+    const size_t dacc_bytes = align_up((size_t)P * DACC_STRIDE * sizeof(float), 256);
+    float *dacc = static_cast<float *>(do_alloc(alloc, alloc_ctx, GSB_BUF_SCRATCH0, dacc_bytes));
+    if (!dacc) return GSB_ERR_ALLOC;
+    GSB_CUDA(cudaMemsetAsync(dacc, 0, dacc_bytes, stream));
+
+    ImageView iv;
+    carve_image(st->image, npix, iv);
+    BinningView bv;
+    carve_binning(st->binning, st->num_rendered, st->num_tiles, bv);
+    const float4 *splat = static_cast<const float4 *>(st->geom);
+
+    if (st->num_rendered > 0) {
+        RenderBwdArgs ra;
+        ra.W = cam.W; ra.H = cam.H; ra.gx = cam.gx; ra.gy = cam.gy; ra.ranges = bv.ranges; ra.point_list = bv.point_list;
+        ra.splat = splat; ra.bg = s->bg; ra.final_T = iv.final_T; ra.n_contrib = iv.n_contrib; ra.dL_dcolor = dL_dcolor;
+        ra.dL_dinvdepth = dL_dinvdepth; ra.dacc = dacc;
+        rc = launch_render_bwd(ra, opt_bwd_variant, debug, stream);
+        if (rc) return rc;
+    }
+    PreBwdArgs pa;
+    pa.P = P; pa.means = in->means3D; pa.shs = in->shs; pa.opac = in->opacities; pa.scales = in->scales; pa.rots = in->rotations;
+    pa.cov_pre = in->cov3D_precomp; pa.splat = splat; pa.dacc = dacc; pa.g = *grads;
+    return launch_preprocess_bwd(cam, pa, accumulate != 0, debug, stream);
+}
+
+int32_t gsb_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+                         uint8_t *present, void *cuda_stream) {
+    (void)projmatrix;
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) {
+        set_error("gsb_mark_visible: bad argument");
+        return GSB_ERR_ARGUMENT;
+    }
+    return launch_mark_visible(P, means3D, viewmatrix, present, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int32_t gsb_sort_pairs(uint32_t *keys, uint32_t *vals, int64_t n, int32_t begin_bit, int32_t end_bit,
+                       gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream) {
+    if (n < 0 || (n > 0 && (!keys || !vals)) || !alloc || begin_bit < 0 || end_bit > 32 || begin_bit > end_bit) {
+        set_error("gsb_sort_pairs: bad argument");
+        return GSB_ERR_ARGUMENT;
+    }
+    if (n == 0) return GSB_OK;
+    Carver c(nullptr);
+    c.take<uint32_t>((size_t)n); c.take<uint32_t>((size_t)n); c.take<char>(sort_scratch_bytes(n));
+    void *scr = do_alloc(alloc, alloc_ctx, GSB_BUF_SCRATCH0, c.bytes());
+    if (!scr) return GSB_ERR_ALLOC;
+    Carver cr(scr);
+    uint32_t *ka = cr.take<uint32_t>((size_t)n), *va = cr.take<uint32_t>((size_t)n);
+    char *ss = cr.take<char>(sort_scratch_bytes(n));
+    return sort_pairs(keys, vals, ka, va, n, begin_bit, end_bit, ss, false, static_cast<cudaStream_t>(cuda_stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+// common.cuh -- shared definitions for the sm_100a rasterizer kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gs_b200.h"
+
+namespace gsb {
+
+// ---- splatting constants (same set as oracle/torch_oracle.py UNVERIFIED_VS_REFERENCE) ----
+constexpr int TILE = 16;
+constexpr int TILE_PIX = TILE * TILE;
+constexpr float NEAR_CULL = 0.2f;
+constexpr float FRUSTUM_CLAMP = 1.3f;
+constexpr float DILATION = 0.3f;
+constexpr float AA_FLOOR = 0.000025f;
+constexpr float ALPHA_MIN = 1.0f / 255.0f;
+constexpr float ALPHA_MAX = 0.99f;
+constexpr float T_STOP = 0.0001f;
+constexpr float W_EPS = 0.0000001f;
+
+// SH constants: /root/reference/utils/sh_utils.py:26-54
+constexpr float SH_C0 = 0.28209479177387814f;
+constexpr float SH_C1 = 0.4886025119029199f;
+__device__ constexpr float SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                       -1.0925484305920792f, 0.5462742152960396f};
+__device__ constexpr float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                       0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                       -0.5900435899266435f};
+
+// ---- per-gaussian forward record gathered by the blend kernels: 3 x float4 = 48 B ----
+//   q0 = { x, y, conic.A, conic.B }      pixel-space mean, inverse dilated 2D covariance
+//   q1 = { conic.C, opacity, r, g }      opacity already multiplied by the AA factor
+//   q2 = { b, 1/depth, depth, bits }     bits: low 3 = SH clamp flags
+constexpr int SPLAT_F4 = 3;
+
+// ---- host-side plumbing -------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern int64_t g_launch_count;
+int check_launch(const char *what, bool debug, cudaStream_t stream);
+
+// per-kernel CUDA-event timing on the launching stream (option "time_kernels": 1 = blend kernels only,
+// 2 = every kernel); read back with gsb_kernel_time()
+extern int g_time_kernels;
+void *timer_begin(const char *name, cudaStream_t stream);
+void timer_end(void *token, cudaStream_t stream);
+
+#define GSB_LAUNCH(name, debug, stream, kernel, grid, block, smem, ...)                         \
+    do {                                                                                        \
+        void *_tok = gsb::g_time_kernels ? gsb::timer_begin(name, (stream)) : nullptr;          \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                             \
+        if (_tok) gsb::timer_end(_tok, (stream));                                               \
+        ++gsb::g_launch_count;                                                                  \
+        int _e = gsb::check_launch(name, (debug), (stream));                                    \
+        if (_e) return _e;                                                                      \
+    } while (0)
+
+#define GSB_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _err = (expr);                                                              \
+        if (_err != cudaSuccess) {                                                              \
+            gsb::set_error("%s failed: %s", #expr, cudaGetErrorString(_err));                   \
+            return GSB_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// bump carver over one allocation
+struct Carver {
+    char *base;
+    size_t off;
+    explicit Carver(void *p) : base(static_cast<char *>(p)), off(0) {}
+    template <typename T>
+    T *take(size_t count) {
+        off = align_up(off, 256);
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+    size_t bytes() const { return align_up(off, 256); }
+};
+
+// ---- radix sort / scan (radix_sort.cu) ----------------------------------------------------
+size_t sort_scratch_bytes(int64_t n);
+// Stable LSD sort of pairs on bits [begin_bit, end_bit).  Result is left in (keys, vals);
+// (keys_alt, vals_alt) are ping-pong buffers of the same size; scratch >= sort_scratch_bytes(n).
+int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n,
+               int begin_bit, int end_bit, void *scratch, bool debug, cudaStream_t stream);
+size_t scan_scratch_bytes(int64_t n);
+
+}  // namespace gsb

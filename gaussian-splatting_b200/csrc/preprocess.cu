@@ -1,0 +1,388 @@
+// preprocess.cu -- per-gaussian kernels: forward projection (K1), backward chain rule (K8) and the
+// frustum-only visibility test (K9).  One thread per gaussian, 256-thread blocks.
+//
+// Replaces preprocessCUDA / BACKWARD::preprocessCUDA / checkFrustum of the reference's
+// cuda_rasterizer/{forward,backward,auxiliary}.* (named in BASELINE.json north_star; the files are
+// absent from /root/reference).  The cited in-tree formulae:
+//   SH -> RGB ........ /root/reference/utils/sh_utils.py:57-112, gaussian_renderer/__init__.py:76-80
+//   Sigma = L L^T .... /root/reference/utils/general_utils.py:78-110, scene/gaussian_model.py:33-37
+//   matrices ......... /root/reference/scene/cameras.py:86-89 (transposed, row-vector convention)
+#include "geom.cuh"
+#include "kernels.cuh"
+
+namespace gsb {
+
+constexpr int PRE_THREADS = 256;
+
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_fwd_kernel(const CamArgs ca, const PreFwdArgs a) {
+    __shared__ CamParams cam;
+    load_cam(ca, cam);
+    __syncthreads();
+    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
+    if (i >= a.P) return;
+
+    // defaults for a culled gaussian
+    uint32_t key = 0xffffffffu, ntiles = 0;
+    int radius_out = 0;
+    float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0, q2 = q0;
+    uint2 rect = make_uint2(0u, 0u);
+    bool write_all = false;
+
+    const float px = a.means[3 * i], py = a.means[3 * i + 1], pz = a.means[3 * i + 2];
+    const float *v = cam.view, *pm = cam.proj;
+    const float tz = v[2] * px + v[6] * py + v[10] * pz + v[14];
+    if (tz > NEAR_CULL) {
+        const float hx = pm[0] * px + pm[4] * py + pm[8] * pz + pm[12];
+        const float hy = pm[1] * px + pm[5] * py + pm[9] * pz + pm[13];
+        const float hw = pm[3] * px + pm[7] * py + pm[11] * pz + pm[15];
+        const float pw = 1.0f / (hw + W_EPS);
+        const float ndcx = hx * pw, ndcy = hy * pw;
+
+        float c6[6];
+        if (a.cov_pre) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) c6[k] = a.cov_pre[6 * (size_t)i + k];
+        } else {
+            const float4 q = reinterpret_cast<const float4 *>(a.rots)[i];
+            cov3d_from_scale_rot(a.scales[3 * i], a.scales[3 * i + 1], a.scales[3 * i + 2], cam.scale_modifier, q, c6);
+        }
+        Cov2D cv;
+        cov2d(cam, px, py, pz, c6, cv);
+        const float det0 = cv.a * cv.c - cv.b * cv.b;
+        const float ca_ = cv.a + DILATION, cc_ = cv.c + DILATION, cb_ = cv.b;
+        const float det = ca_ * cc_ - cb_ * cb_;
+        float hscale = 1.0f;
+        if (cam.antialiasing) hscale = sqrtf(fmaxf(AA_FLOOR, det0 / det));
+        if (det != 0.0f) {
+            const float det_inv = 1.0f / det;
+            const float mid = 0.5f * (ca_ + cc_);
+            const float root = sqrtf(fmaxf(0.1f, mid * mid - det));
+            const float lam = fmaxf(mid + root, mid - root);
+            const float radius = ceilf(3.0f * sqrtf(lam));
+            const float sx = ((ndcx + 1.0f) * cam.W - 1.0f) * 0.5f;
+            const float sy = ((ndcy + 1.0f) * cam.H - 1.0f) * 0.5f;
+            int x0 = (int)((sx - radius) / TILE), y0 = (int)((sy - radius) / TILE);
+            int x1 = (int)((sx + radius + TILE - 1) / TILE), y1 = (int)((sy + radius + TILE - 1) / TILE);
+            x0 = min(cam.gx, max(0, x0)); x1 = min(cam.gx, max(0, x1));
+            y0 = min(cam.gy, max(0, y0)); y1 = min(cam.gy, max(0, y1));
+            if ((x1 - x0) * (y1 - y0) != 0) {
+                float r = 0.f, g = 0.f, b = 0.f;
+                uint32_t bits = 8u;  // bit 3: visible
+                if (a.colors) {
+                    r = a.colors[3 * (size_t)i]; g = a.colors[3 * (size_t)i + 1]; b = a.colors[3 * (size_t)i + 2];
+                } else {
+                    const float dx = px - cam.campos[0], dy = py - cam.campos[1], dz = pz - cam.campos[2];
+                    const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+                    float bas[16];
+                    sh_basis(cam.sh_degree, dx * inv, dy * inv, dz * inv, bas);
+                    const int nb = (cam.sh_degree + 1) * (cam.sh_degree + 1);
+                    const float *sh = a.shs + (size_t)i * cam.sh_coeffs * 3;
+                    for (int k = 0; k < nb; ++k) {
+                        r += bas[k] * sh[3 * k]; g += bas[k] * sh[3 * k + 1]; b += bas[k] * sh[3 * k + 2];
+                    }
+                    r += 0.5f; g += 0.5f; b += 0.5f;
+                    if (r < 0.f) { bits |= 1u; r = 0.f; }
+                    if (g < 0.f) { bits |= 2u; g = 0.f; }
+                    if (b < 0.f) { bits |= 4u; b = 0.f; }
+                }
+                const float opacity = a.opac[i] * hscale;
+                const float A = cc_ * det_inv, B = -cb_ * det_inv, C = ca_ * det_inv;
+                CullGeom cg;
+                cg.cx = sx; cg.cy = sy; cg.A = A; cg.B = B; cg.C = C;
+                cg.rx0 = x0; cg.ry0 = y0; cg.rx1 = x1; cg.ry1 = y1;
+                if (a.cull) {
+                    cg.lim = cull_limit(opacity);
+                    ntiles = cull_count(cg);
+                } else {
+                    cg.lim = 3.0e38f;
+                    ntiles = (uint32_t)((x1 - x0) * (y1 - y0));
+                }
+                q0 = make_float4(sx, sy, A, B);
+                q1 = make_float4(C, opacity, r, g);
+                q2 = make_float4(b, 1.0f / tz, cg.lim, __uint_as_float(bits));
+                rect = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)y0 | ((uint32_t)y1 << 16));
+                key = __float_as_uint(tz);
+                radius_out = (int)radius;
+                write_all = true;
+            }
+        }
+    }
+    float4 *rec = a.splat + (size_t)i * SPLAT_F4;
+    if (write_all) { rec[0] = q0; rec[1] = q1; }
+    rec[2] = q2;
+    a.depth_key[i] = key;
+    a.depth_idx[i] = (uint32_t)i;
+    a.tiles[i] = ntiles;
+    a.rect[i] = rect;
+    a.radii[i] = radius_out;
+}
+
+// d basis / d(x,y,z)
+__device__ __forceinline__ void sh_basis_grad(const int deg, const float x, const float y, const float z, float bx[16],
+                                              float by[16], float bz[16]) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) bx[k] = by[k] = bz[k] = 0.0f;
+    if (deg < 1) return;
+    by[1] = -SH_C1; bz[2] = SH_C1; bx[3] = -SH_C1;
+    if (deg < 2) return;
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    bx[4] = SH_C2[0] * y; by[4] = SH_C2[0] * x;
+    by[5] = SH_C2[1] * z; bz[5] = SH_C2[1] * y;
+    bx[6] = SH_C2[2] * -2.0f * x; by[6] = SH_C2[2] * -2.0f * y; bz[6] = SH_C2[2] * 4.0f * z;
+    bx[7] = SH_C2[3] * z; bz[7] = SH_C2[3] * x;
+    bx[8] = SH_C2[4] * 2.0f * x; by[8] = SH_C2[4] * -2.0f * y;
+    if (deg < 3) return;
+    bx[9] = SH_C3[0] * 6.0f * xy; by[9] = SH_C3[0] * (3.0f * xx - 3.0f * yy);
+    bx[10] = SH_C3[1] * yz; by[10] = SH_C3[1] * xz; bz[10] = SH_C3[1] * xy;
+    bx[11] = SH_C3[2] * -2.0f * xy; by[11] = SH_C3[2] * (4.0f * zz - xx - 3.0f * yy); bz[11] = SH_C3[2] * 8.0f * yz;
+    bx[12] = SH_C3[3] * -6.0f * xz; by[12] = SH_C3[3] * -6.0f * yz;
+    bz[12] = SH_C3[3] * (6.0f * zz - 3.0f * xx - 3.0f * yy);
+    bx[13] = SH_C3[4] * (4.0f * zz - 3.0f * xx - yy); by[13] = SH_C3[4] * -2.0f * xy; bz[13] = SH_C3[4] * 8.0f * xz;
+    bx[14] = SH_C3[5] * 2.0f * xz; by[14] = SH_C3[5] * -2.0f * yz; bz[14] = SH_C3[5] * (xx - yy);
+    bx[15] = SH_C3[6] * (3.0f * xx - 3.0f * yy); by[15] = SH_C3[6] * -6.0f * xy;
+}
+
+template <bool ACC>
+__device__ __forceinline__ void put(float *p, const float v) {
+    if (ACC) *p += v; else *p = v;
+}
+
+// K8: per-gaussian chain rule from (mean2D, conic, opacity, rgb, inverse depth) gradients to the inputs.
+template <bool ACC>
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_bwd_kernel(const CamArgs ca, const PreBwdArgs a) {
+    __shared__ CamParams cam;
+    load_cam(ca, cam);
+    __syncthreads();
+    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
+    if (i >= a.P) return;
+    const int M = cam.sh_coeffs;
+
+    const float4 q2 = a.splat[(size_t)i * SPLAT_F4 + 2];
+    const uint32_t bits = __float_as_uint(q2.w);
+    const bool visible = (bits & 8u) != 0u;
+
+    float gm[3] = {0.f, 0.f, 0.f};
+    float g_m2[2] = {0.f, 0.f};
+    float g_op = 0.f;
+    float g_rgb[3] = {0.f, 0.f, 0.f};
+    float g_sc[3] = {0.f, 0.f, 0.f};
+    float g_rot[4] = {0.f, 0.f, 0.f, 0.f};
+    float dS[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float d_rgb_sh[3] = {0.f, 0.f, 0.f};
+    float bas[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) bas[k] = 0.f;
+    const int nb = (cam.sh_degree + 1) * (cam.sh_degree + 1);
+
+    if (visible) {
+        const float *acc = a.dacc + (size_t)i * DACC_STRIDE;
+        const float d_m2x = acc[0], d_m2y = acc[1];
+        const float dA = acc[2], dB = acc[3], dC = acc[4];
+        const float d_w = acc[5];
+        const float d_rgb[3] = {acc[6], acc[7], acc[8]};
+        const float d_invd = acc[9];
+        g_m2[0] = d_m2x; g_m2[1] = d_m2y;
+        const float px = a.means[3 * i], py = a.means[3 * i + 1], pz = a.means[3 * i + 2];
+
+        // colour
+        if (a.shs) {
+            const float dx = px - cam.campos[0], dy = py - cam.campos[1], dz = pz - cam.campos[2];
+            const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            const float ux = dx * inv, uy = dy * inv, uz = dz * inv;
+            float bx[16], by[16], bz[16];
+            sh_basis(cam.sh_degree, ux, uy, uz, bas);
+            sh_basis_grad(cam.sh_degree, ux, uy, uz, bx, by, bz);
+            d_rgb_sh[0] = (bits & 1u) ? 0.f : d_rgb[0];
+            d_rgb_sh[1] = (bits & 2u) ? 0.f : d_rgb[1];
+            d_rgb_sh[2] = (bits & 4u) ? 0.f : d_rgb[2];
+            const float *sh = a.shs + (size_t)i * M * 3;
+            float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+            for (int k = 1; k < nb; ++k) {
+                const float s = sh[3 * k] * d_rgb_sh[0] + sh[3 * k + 1] * d_rgb_sh[1] + sh[3 * k + 2] * d_rgb_sh[2];
+                ddx += bx[k] * s; ddy += by[k] * s; ddz += bz[k] * s;
+            }
+            const float dot = ux * ddx + uy * ddy + uz * ddz;
+            gm[0] += (ddx - ux * dot) * inv; gm[1] += (ddy - uy * dot) * inv; gm[2] += (ddz - uz * dot) * inv;
+        } else {
+            g_rgb[0] = d_rgb[0]; g_rgb[1] = d_rgb[1]; g_rgb[2] = d_rgb[2];
+        }
+
+        // conic -> dilated 2D covariance
+        float c6[6];
+        float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+        float sc[3] = {0.f, 0.f, 0.f};
+        if (a.cov_pre) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) c6[k] = a.cov_pre[6 * (size_t)i + k];
+        } else {
+            q = reinterpret_cast<const float4 *>(a.rots)[i];
+            sc[0] = a.scales[3 * i]; sc[1] = a.scales[3 * i + 1]; sc[2] = a.scales[3 * i + 2];
+            cov3d_from_scale_rot(sc[0], sc[1], sc[2], cam.scale_modifier, q, c6);
+        }
+        Cov2D cv;
+        cov2d(cam, px, py, pz, c6, cv);
+        const float a0 = cv.a, b = cv.b, c0 = cv.c;
+        const float a_ = a0 + DILATION, c_ = c0 + DILATION;
+        const float det = a_ * c_ - b * b;
+        const float dinv2 = 1.0f / (det * det + 0.0000001f);
+        float dL_da = dinv2 * (-c_ * c_ * dA + b * c_ * dB - b * b * dC);
+        float dL_dc = dinv2 * (-b * b * dA + a_ * b * dB - a_ * a_ * dC);
+        float dL_db = dinv2 * (2.f * b * c_ * dA - (det + 2.f * b * b) * dB + 2.f * a_ * b * dC);
+        g_op = d_w;
+        if (cam.antialiasing) {
+            const float det0 = a0 * c0 - b * b;
+            const float ratio = det0 / det;
+            const float hs = sqrtf(fmaxf(AA_FLOOR, ratio));
+            g_op = d_w * hs;
+            if (ratio > AA_FLOOR) {
+                const float d_ratio = d_w * a.opac[i] / (2.0f * hs);
+                dL_da += d_ratio * (c0 / det - det0 * c_ / (det * det));
+                dL_dc += d_ratio * (a0 / det - det0 * a_ / (det * det));
+                dL_db += d_ratio * (-2.f * b / det + det0 * 2.f * b / (det * det));
+            }
+        }
+
+        // 2D covariance -> Sigma and M = J R
+        const float *M0 = cv.M0, *M1 = cv.M1;
+        dS[0] = M0[0] * M0[0] * dL_da + M0[0] * M1[0] * dL_db + M1[0] * M1[0] * dL_dc;
+        dS[3] = M0[1] * M0[1] * dL_da + M0[1] * M1[1] * dL_db + M1[1] * M1[1] * dL_dc;
+        dS[5] = M0[2] * M0[2] * dL_da + M0[2] * M1[2] * dL_db + M1[2] * M1[2] * dL_dc;
+        dS[1] = 2.f * M0[0] * M0[1] * dL_da + (M0[0] * M1[1] + M0[1] * M1[0]) * dL_db + 2.f * M1[0] * M1[1] * dL_dc;
+        dS[2] = 2.f * M0[0] * M0[2] * dL_da + (M0[0] * M1[2] + M0[2] * M1[0]) * dL_db + 2.f * M1[0] * M1[2] * dL_dc;
+        dS[4] = 2.f * M0[1] * M0[2] * dL_da + (M0[1] * M1[2] + M0[2] * M1[1]) * dL_db + 2.f * M1[1] * M1[2] * dL_dc;
+        const float S0[3] = {c6[0], c6[1], c6[2]}, S1[3] = {c6[1], c6[3], c6[4]}, S2[3] = {c6[2], c6[4], c6[5]};
+        const float SM0[3] = {S0[0] * M0[0] + S0[1] * M0[1] + S0[2] * M0[2], S1[0] * M0[0] + S1[1] * M0[1] + S1[2] * M0[2],
+                              S2[0] * M0[0] + S2[1] * M0[1] + S2[2] * M0[2]};
+        const float SM1[3] = {S0[0] * M1[0] + S0[1] * M1[1] + S0[2] * M1[2], S1[0] * M1[0] + S1[1] * M1[1] + S1[2] * M1[2],
+                              S2[0] * M1[0] + S2[1] * M1[1] + S2[2] * M1[2]};
+        float dJ00 = 0.f, dJ02 = 0.f, dJ11 = 0.f, dJ12 = 0.f;
+        const float *v = cam.view;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float dM0 = 2.f * dL_da * SM0[c] + dL_db * SM1[c];
+            const float dM1 = 2.f * dL_dc * SM1[c] + dL_db * SM0[c];
+            dJ00 += dM0 * v[4 * c + 0]; dJ02 += dM0 * v[4 * c + 2];
+            dJ11 += dM1 * v[4 * c + 1]; dJ12 += dM1 * v[4 * c + 2];
+        }
+        const float tz = cv.tz, tz2 = 1.0f / (tz * tz), tz3 = tz2 / tz;
+        const float fx = cam.focal_x, fy = cam.focal_y;
+        const float dtx = cv.cx ? 0.0f : -fx * tz2 * dJ02;
+        const float dty = cv.cy ? 0.0f : -fy * tz2 * dJ12;
+        float dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + 2.f * fx * cv.tx * tz3 * dJ02 + 2.f * fy * cv.ty * tz3 * dJ12;
+        dtz -= d_invd * tz2;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gm[c] += dtx * v[4 * c + 0] + dty * v[4 * c + 1] + dtz * v[4 * c + 2];
+
+        // NDC 2D mean -> 3D mean
+        {
+            const float *pm = cam.proj;
+            const float hx = pm[0] * px + pm[4] * py + pm[8] * pz + pm[12];
+            const float hy = pm[1] * px + pm[5] * py + pm[9] * pz + pm[13];
+            const float hw = pm[3] * px + pm[7] * py + pm[11] * pz + pm[15];
+            const float pw = 1.0f / (hw + W_EPS);
+            const float mul1 = hx * pw * pw, mul2 = hy * pw * pw;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                gm[c] += (pm[4 * c + 0] * pw - pm[4 * c + 3] * mul1) * d_m2x + (pm[4 * c + 1] * pw - pm[4 * c + 3] * mul2) * d_m2y;
+        }
+
+        // Sigma -> scale, rotation
+        if (!a.cov_pre) {
+            float R[9];
+            quat_to_R(q, R);
+            const float mod = cam.scale_modifier;
+            const float sp[3] = {mod * sc[0], mod * sc[1], mod * sc[2]};
+            const float Gm[9] = {dS[0], 0.5f * dS[1], 0.5f * dS[2], 0.5f * dS[1], dS[3], 0.5f * dS[4],
+                                 0.5f * dS[2], 0.5f * dS[4], dS[5]};
+            float dR[9];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float ds = 0.f;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float dl = 2.f * (Gm[3 * r] * R[k] + Gm[3 * r + 1] * R[3 + k] + Gm[3 * r + 2] * R[6 + k]) * sp[k];
+                    ds += dl * R[3 * r + k];
+                    dR[3 * r + k] = dl * sp[k];
+                }
+                g_sc[k] = mod * ds;
+            }
+            const float r = q.x, x = q.y, y = q.z, z = q.w;
+            g_rot[0] = 2.f * (-z * dR[1] + y * dR[2] + z * dR[3] - x * dR[5] - y * dR[6] + x * dR[7]);
+            g_rot[1] = 2.f * (y * dR[1] + z * dR[2] + y * dR[3] - 2.f * x * dR[4] - r * dR[5] + z * dR[6] + r * dR[7] - 2.f * x * dR[8]);
+            g_rot[2] = 2.f * (-2.f * y * dR[0] + x * dR[1] + r * dR[2] + x * dR[3] + z * dR[5] - r * dR[6] + z * dR[7] - 2.f * y * dR[8]);
+            g_rot[3] = 2.f * (-2.f * z * dR[0] - r * dR[1] + x * dR[2] + r * dR[3] - 2.f * z * dR[4] + y * dR[5] + x * dR[6] + y * dR[7]);
+        }
+    }
+
+    if (a.g.dL_dmeans3D) {
+        put<ACC>(a.g.dL_dmeans3D + 3 * (size_t)i, gm[0]); put<ACC>(a.g.dL_dmeans3D + 3 * (size_t)i + 1, gm[1]);
+        put<ACC>(a.g.dL_dmeans3D + 3 * (size_t)i + 2, gm[2]);
+    }
+    if (a.g.dL_dmeans2D) {
+        put<ACC>(a.g.dL_dmeans2D + 3 * (size_t)i, g_m2[0]); put<ACC>(a.g.dL_dmeans2D + 3 * (size_t)i + 1, g_m2[1]);
+        put<ACC>(a.g.dL_dmeans2D + 3 * (size_t)i + 2, 0.f);
+    }
+    if (a.g.dL_dopacities) put<ACC>(a.g.dL_dopacities + i, g_op);
+    if (a.g.dL_dcolors) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) put<ACC>(a.g.dL_dcolors + 3 * (size_t)i + c, g_rgb[c]);
+    }
+    if (a.g.dL_dshs && a.shs) {
+        float *o = a.g.dL_dshs + (size_t)i * M * 3;
+        for (int k = 0; k < M; ++k) {
+            const float bk = (k < nb && k < 16) ? bas[k] : 0.f;
+            put<ACC>(o + 3 * k, bk * d_rgb_sh[0]); put<ACC>(o + 3 * k + 1, bk * d_rgb_sh[1]);
+            put<ACC>(o + 3 * k + 2, bk * d_rgb_sh[2]);
+        }
+    }
+    if (a.cov_pre) {
+        if (a.g.dL_dcov3D) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) put<ACC>(a.g.dL_dcov3D + 6 * (size_t)i + k, dS[k]);
+        }
+    } else {
+        if (a.g.dL_dscales) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) put<ACC>(a.g.dL_dscales + 3 * (size_t)i + k, g_sc[k]);
+        }
+        if (a.g.dL_drotations) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) put<ACC>(a.g.dL_drotations + 4 * (size_t)i + k, g_rot[k]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PRE_THREADS)
+mark_visible_kernel(const int P, const float *__restrict__ means, const float *__restrict__ view, uint8_t *present) {
+    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
+    if (i >= P) return;
+    const float tz = __ldg(view + 2) * means[3 * i] + __ldg(view + 6) * means[3 * i + 1] + __ldg(view + 10) * means[3 * i + 2] + __ldg(view + 14);
+    present[i] = tz > NEAR_CULL ? 1 : 0;
+}
+
+int launch_preprocess_fwd(const CamArgs &ca, const PreFwdArgs &a, bool debug, cudaStream_t stream) {
+    if (a.P <= 0) return GSB_OK;
+    GSB_LAUNCH("preprocess_fwd", debug, stream, preprocess_fwd_kernel, (int)ceil_div(a.P, PRE_THREADS), PRE_THREADS, 0, ca, a);
+    return GSB_OK;
+}
+
+int launch_preprocess_bwd(const CamArgs &ca, const PreBwdArgs &a, bool accumulate, bool debug, cudaStream_t stream) {
+    if (a.P <= 0) return GSB_OK;
+    const int grid = (int)ceil_div(a.P, PRE_THREADS);
+    if (accumulate) {
+        GSB_LAUNCH("preprocess_bwd", debug, stream, preprocess_bwd_kernel<true>, grid, PRE_THREADS, 0, ca, a);
+    } else {
+        GSB_LAUNCH("preprocess_bwd", debug, stream, preprocess_bwd_kernel<false>, grid, PRE_THREADS, 0, ca, a);
+    }
+    return GSB_OK;
+}
+
+int launch_mark_visible(int P, const float *means, const float *view, uint8_t *present, cudaStream_t stream) {
+    if (P <= 0) return GSB_OK;
+    GSB_LAUNCH("mark_visible", false, stream, mark_visible_kernel, (int)ceil_div(P, PRE_THREADS), PRE_THREADS, 0, P, means, view, present);
+    return GSB_OK;
+}
+
+}  // namespace gsb

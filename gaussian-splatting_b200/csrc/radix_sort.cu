@@ -1,0 +1,185 @@
+// radix_sort.cu -- stable LSD radix sort of (u32 key, u32 value) pairs, 8 bits per pass.
+//
+// Replaces the reference's cub::DeviceRadixSort::SortPairs call (named in BASELINE.json
+// north_star; the call site lives in the absent cuda_rasterizer/rasterizer_impl.cu).
+//
+// The reference sorts D 64-bit keys (tile << 32 | depth) in one 6-pass sort.  Here the same
+// order is produced by two much smaller sorts (DESIGN.md "binning"):
+//   1. gaussians by depth bits      (P pairs, 4 passes)
+//   2. instances by tile id, STABLE (D pairs, ceil(log2(tiles)/8) = 2 passes)
+// because instances are emitted in depth order and a stable sort keeps that order per tile.
+//
+// Per pass: digit histogram per block -> per-digit row scan -> stable scatter.
+// Traffic per pass: 2 key reads + 1 value read + 1 key write + 1 value write = 20 B / pair.
+#include "common.cuh"
+
+namespace gsb {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_IPT = 16;
+constexpr int SORT_KPB = SORT_THREADS * SORT_IPT;  // keys per block
+
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_hist_kernel(const uint32_t *__restrict__ keys, uint32_t *__restrict__ table, int64_t n, int nblocks,
+                 int shift, uint32_t mask) {
+    __shared__ uint32_t hist[RADIX];
+    const int tid = threadIdx.x;
+    hist[tid] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * SORT_KPB;
+#pragma unroll 4
+    for (int i = 0; i < SORT_IPT; ++i) {
+        int64_t idx = base + (int64_t)i * SORT_THREADS + tid;
+        if (idx < n) atomicAdd(&hist[(keys[idx] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    table[(int64_t)tid * nblocks + blockIdx.x] = hist[tid];
+}
+
+// one block per digit: in-row exclusive scan over the blocks, row total -> totals[digit]
+__global__ void __launch_bounds__(256)
+sort_rowscan_kernel(uint32_t *__restrict__ table, uint32_t *__restrict__ totals, int nblocks) {
+    __shared__ uint32_t warp_sums[8];
+    __shared__ uint32_t carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    uint32_t *row = table + (int64_t)blockIdx.x * nblocks;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 256) {
+        int i = base + tid;
+        uint32_t v = i < nblocks ? row[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[w] = incl;
+        __syncthreads();
+        uint32_t wprefix = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint32_t s = warp_sums[k];
+            if (k < w) wprefix += s;
+            total += s;
+        }
+        const uint32_t carry = carry_s;
+        if (i < nblocks) row[i] = carry + wprefix + incl - v;
+        __syncthreads();
+        if (tid == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+    if (tid == 0) totals[blockIdx.x] = carry_s;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                    const uint32_t *__restrict__ table, const uint32_t *__restrict__ totals, int64_t n,
+                    int nblocks, int shift, uint32_t mask) {
+    __shared__ uint32_t warp_cnt[SORT_THREADS / 32][RADIX];
+    __shared__ uint32_t warp_sums[8];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < SORT_THREADS / 32; ++k) warp_cnt[k][tid] = 0;
+
+    // exclusive scan of the 256 digit totals -> global base of digit `tid`
+    const uint32_t tot = totals[tid];
+    uint32_t incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    uint32_t digit_base = incl - tot;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k < w) digit_base += warp_sums[k];
+
+    // stable ranks: block order = (warp, round, lane)
+    const int64_t seg = (int64_t)blockIdx.x * SORT_KPB + (int64_t)w * (32 * SORT_IPT);
+    uint32_t key[SORT_IPT];
+    uint32_t rank[SORT_IPT];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; ++r) {
+        const int64_t idx = seg + r * 32 + lane;
+        const bool valid = idx < n;
+        key[r] = valid ? keys_in[idx] : 0xffffffffu;
+        const uint32_t d = valid ? ((key[r] >> shift) & mask) : (uint32_t)RADIX;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader && valid) {
+            base = warp_cnt[w][d];
+            warp_cnt[w][d] = base + __popc(peers);
+        }
+        base = __shfl_sync(0xffffffffu, base, leader);
+        rank[r] = base + __popc(peers & lt_mask);
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        uint32_t run = digit_base + table[(int64_t)tid * nblocks + blockIdx.x];
+#pragma unroll
+        for (int k = 0; k < SORT_THREADS / 32; ++k) {
+            uint32_t c = warp_cnt[k][tid];
+            warp_cnt[k][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; ++r) {
+        const int64_t idx = seg + r * 32 + lane;
+        if (idx < n) {
+            const uint32_t d = (key[r] >> shift) & mask;
+            const uint32_t pos = warp_cnt[w][d] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = vals_in[idx];
+        }
+    }
+}
+
+size_t sort_scratch_bytes(int64_t n) {
+    int64_t nblocks = ceil_div(n > 0 ? n : 1, SORT_KPB);
+    return align_up((size_t)RADIX * nblocks * sizeof(uint32_t), 256) + align_up(RADIX * sizeof(uint32_t), 256);
+}
+
+int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n,
+               int begin_bit, int end_bit, void *scratch, bool debug, cudaStream_t stream) {
+    if (n <= 0 || end_bit <= begin_bit) return GSB_OK;
+    if (n >= (int64_t)1 << 32) {
+        set_error("sort_pairs: n=%lld does not fit 32-bit positions", (long long)n);
+        return GSB_ERR_OVERFLOW;
+    }
+    const int nblocks = (int)ceil_div(n, SORT_KPB);
+    uint32_t *table = static_cast<uint32_t *>(scratch);
+    uint32_t *totals = reinterpret_cast<uint32_t *>(static_cast<char *>(scratch) +
+                                                    align_up((size_t)RADIX * nblocks * sizeof(uint32_t), 256));
+    uint32_t *kin = keys, *vin = vals, *kout = keys_alt, *vout = vals_alt;
+    int passes = 0;
+    for (int bit = begin_bit; bit < end_bit; bit += RADIX_BITS) {
+        const int bits = (end_bit - bit) < RADIX_BITS ? (end_bit - bit) : RADIX_BITS;
+        const uint32_t mask = (1u << bits) - 1u;
+        GSB_LAUNCH("sort_hist", debug, stream, sort_hist_kernel, nblocks, SORT_THREADS, 0, kin, table, n, nblocks,
+                   bit, mask);
+        GSB_LAUNCH("sort_rowscan", debug, stream, sort_rowscan_kernel, RADIX, 256, 0, table, totals, nblocks);
+        GSB_LAUNCH("sort_scatter", debug, stream, sort_scatter_kernel, nblocks, SORT_THREADS, 0, kin, vin, kout,
+                   vout, table, totals, n, nblocks, bit, mask);
+        uint32_t *t = kin; kin = kout; kout = t;
+        t = vin; vin = vout; vout = t;
+        ++passes;
+    }
+    if (passes & 1) {  // result sits in the alt buffers
+        GSB_CUDA(cudaMemcpyAsync(keys, keys_alt, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+        GSB_CUDA(cudaMemcpyAsync(vals, vals_alt, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+    }
+    return GSB_OK;
+}
+
+}  // namespace gsb

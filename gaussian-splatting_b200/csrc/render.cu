@@ -1,0 +1,200 @@
+// render.cu -- per-tile blend kernels: forward front-to-back alpha blend (K6) and backward
+// back-to-front gradient accumulation (K7).
+//
+// Replaces FORWARD::renderCUDA / BACKWARD::renderCUDA of the reference's
+// cuda_rasterizer/{forward,backward}.cu (named in BASELINE.json north_star; absent from
+// /root/reference).  Blend rules restated in oracle/gs_oracle.c.
+//
+// Data movement: a tile's sorted gaussian ids are contiguous in point_list; the 48-byte splat
+// records they point to are gathered from the L2-resident record table (P * 48 B) into shared
+// memory 256 at a time.  One 16x16 tile per CTA; a warp owns an 8x4 pixel patch so that a gaussian
+// which misses the patch is skipped by the whole warp.
+#include "kernels.cuh"
+
+namespace gsb {
+
+constexpr int RB = 256;  // gaussians staged per round
+
+__device__ __forceinline__ void pixel_of_thread(const int tile_x, const int tile_y, int &px, int &py) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    px = tile_x * TILE + (w & 1) * 8 + (l & 7);
+    py = tile_y * TILE + (w >> 1) * 4 + (l >> 3);
+}
+
+__global__ void __launch_bounds__(256)
+render_fwd_kernel(const RenderFwdArgs a) {
+    __shared__ float4 s0[RB], s1[RB], s2[RB];
+    const int tile = blockIdx.x;
+    const int tile_x = tile % a.gx, tile_y = tile / a.gx;
+    int px, py;
+    pixel_of_thread(tile_x, tile_y, px, py);
+    const bool inside = px < a.W && py < a.H;
+    const float fx = (float)px, fy = (float)py;
+    const uint2 range = a.ranges[tile];
+    const int todo = (int)(range.y - range.x);
+    const int rounds = (todo + RB - 1) / RB;
+
+    bool done = !inside;
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
+    uint32_t contributor = 0, last = 0;
+
+    for (int rd = 0; rd < rounds; ++rd) {
+        if (__syncthreads_count(done) == 256) break;
+        const int idx = rd * RB + threadIdx.x;
+        if (idx < todo) {
+            const uint32_t g = a.point_list[range.x + idx];
+            const float4 *rec = a.splat + (size_t)g * SPLAT_F4;
+            s0[threadIdx.x] = __ldg(rec);
+            s1[threadIdx.x] = __ldg(rec + 1);
+            s2[threadIdx.x] = __ldg(rec + 2);
+        }
+        __syncthreads();
+        const int n = min(RB, todo - rd * RB);
+        for (int j = 0; !done && j < n; ++j) {
+            ++contributor;
+            const float4 q0 = s0[j];
+            const float4 q1 = s1[j];
+            const float dx = q0.x - fx, dy = q0.y - fy;
+            const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
+            if (power > 0.0f) continue;
+            const float alpha = fminf(ALPHA_MAX, q1.y * __expf(power));
+            if (alpha < ALPHA_MIN) continue;
+            const float test_T = T * (1.0f - alpha);
+            if (test_T < T_STOP) { done = true; continue; }
+            const float4 q2 = s2[j];
+            const float w = alpha * T;
+            C0 += q1.z * w; C1 += q1.w * w; C2 += q2.x * w;
+            Dp += q2.y * w;
+            T = test_T;
+            last = contributor;
+        }
+    }
+    if (inside) {
+        const size_t pid = (size_t)py * a.W + px, HW = (size_t)a.W * a.H;
+        a.final_T[pid] = T;
+        a.n_contrib[pid] = last;
+        a.out_color[pid] = C0 + T * __ldg(a.bg);
+        a.out_color[HW + pid] = C1 + T * __ldg(a.bg + 1);
+        a.out_color[2 * HW + pid] = C2 + T * __ldg(a.bg + 2);
+        a.out_invdepth[pid] = Dp;
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// v0: per-pixel threads, butterfly warp reduction of the 10 per-gaussian gradient terms, one lane adds.
+__global__ void __launch_bounds__(256)
+render_bwd_kernel(const RenderBwdArgs a) {
+    __shared__ float4 s0[RB], s1[RB], s2[RB];
+    __shared__ uint32_t sid[RB];
+    __shared__ uint32_t s_max;
+    const int tile = blockIdx.x;
+    const int tile_x = tile % a.gx, tile_y = tile / a.gx;
+    int px, py;
+    pixel_of_thread(tile_x, tile_y, px, py);
+    const bool inside = px < a.W && py < a.H;
+    const float fx = (float)px, fy = (float)py;
+    const uint2 range = a.ranges[tile];
+    const size_t pid = (size_t)py * a.W + px, HW = (size_t)a.W * a.H;
+
+    const float T_final = inside ? a.final_T[pid] : 0.f;
+    const uint32_t last = inside ? a.n_contrib[pid] : 0u;
+    float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f, dLd = 0.f;
+    if (inside) {
+        dLp0 = a.dL_dcolor[pid]; dLp1 = a.dL_dcolor[HW + pid]; dLp2 = a.dL_dcolor[2 * HW + pid];
+        if (a.dL_dinvdepth) dLd = a.dL_dinvdepth[pid];
+    }
+    const float bg_dot = __ldg(a.bg) * dLp0 + __ldg(a.bg + 1) * dLp1 + __ldg(a.bg + 2) * dLp2;
+    const float ddx = 0.5f * a.W, ddy = 0.5f * a.H;
+
+    // the deepest position any pixel of the tile reached
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, last);
+    if ((threadIdx.x & 31) == 0) atomicMax(&s_max, wmax);
+    __syncthreads();
+    const int todo = (int)s_max;  // positions todo .. 1 (1-based) are visited back to front
+    const int rounds = (todo + RB - 1) / RB;
+
+    float T = T_final;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accd = 0.f;
+    float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, ld = 0.f, last_alpha = 0.f;
+
+    for (int rd = 0; rd < rounds; ++rd) {
+        __syncthreads();
+        const int k = rd * RB + threadIdx.x;  // k-th from the back
+        if (k < todo) {
+            const uint32_t g = a.point_list[range.x + (todo - 1 - k)];
+            const float4 *rec = a.splat + (size_t)g * SPLAT_F4;
+            sid[threadIdx.x] = g;
+            s0[threadIdx.x] = __ldg(rec);
+            s1[threadIdx.x] = __ldg(rec + 1);
+            s2[threadIdx.x] = __ldg(rec + 2);
+        }
+        __syncthreads();
+        const int n = min(RB, todo - rd * RB);
+        for (int j = 0; j < n; ++j) {
+            const uint32_t pos = (uint32_t)(todo - (rd * RB + j));  // 1-based position in the tile list
+            const float4 q0 = s0[j];
+            const float4 q1 = s1[j];
+            const float dx = q0.x - fx, dy = q0.y - fy;
+            const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
+            const float G = __expf(power);
+            const float alpha = fminf(ALPHA_MAX, q1.y * G);
+            const bool valid = (pos <= last) && (power <= 0.0f) && (alpha >= ALPHA_MIN);
+            if (!__any_sync(0xffffffffu, valid)) continue;
+            float g_mx = 0.f, g_my = 0.f, g_A = 0.f, g_B = 0.f, g_C = 0.f, g_o = 0.f, g_r = 0.f, g_g = 0.f, g_b = 0.f, g_d = 0.f;
+            if (valid) {
+                const float4 q2 = s2[j];
+                T = T / (1.0f - alpha);
+                const float w = alpha * T;
+                acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = q1.z;
+                acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = q1.w;
+                acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = q2.x;
+                accd = last_alpha * ld + (1.f - last_alpha) * accd; ld = q2.y;
+                float dL_dalpha = (q1.z - acc0) * dLp0 + (q1.w - acc1) * dLp1 + (q2.x - acc2) * dLp2 + (q2.y - accd) * dLd;
+                g_r = w * dLp0; g_g = w * dLp1; g_b = w * dLp2; g_d = w * dLd;
+                dL_dalpha *= T;
+                last_alpha = alpha;
+                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                const float dL_dpow = q1.y * G * dL_dalpha;
+                g_mx = dL_dpow * (-q0.z * dx - q0.w * dy) * ddx;
+                g_my = dL_dpow * (-q1.x * dy - q0.w * dx) * ddy;
+                g_A = dL_dpow * (-0.5f * dx * dx);
+                g_B = dL_dpow * (-dx * dy);
+                g_C = dL_dpow * (-0.5f * dy * dy);
+                g_o = G * dL_dalpha;
+            }
+            g_mx = warp_sum(g_mx); g_my = warp_sum(g_my); g_A = warp_sum(g_A); g_B = warp_sum(g_B); g_C = warp_sum(g_C);
+            g_o = warp_sum(g_o); g_r = warp_sum(g_r); g_g = warp_sum(g_g); g_b = warp_sum(g_b); g_d = warp_sum(g_d);
+            if ((threadIdx.x & 31) == 0) {
+                float *d = a.dacc + (size_t)sid[j] * DACC_STRIDE;
+                atomicAdd(d + 0, g_mx); atomicAdd(d + 1, g_my); atomicAdd(d + 2, g_A); atomicAdd(d + 3, g_B);
+                atomicAdd(d + 4, g_C); atomicAdd(d + 5, g_o); atomicAdd(d + 6, g_r); atomicAdd(d + 7, g_g);
+                atomicAdd(d + 8, g_b); atomicAdd(d + 9, g_d);
+            }
+        }
+    }
+}
+
+int launch_render_fwd(const RenderFwdArgs &a, int variant, bool debug, cudaStream_t stream) {
+    (void)variant;
+    const int tiles = a.gx * a.gy;
+    if (tiles <= 0) return GSB_OK;
+    GSB_LAUNCH("render_fwd", debug, stream, render_fwd_kernel, tiles, 256, 0, a);
+    return GSB_OK;
+}
+
+int launch_render_bwd(const RenderBwdArgs &a, int variant, bool debug, cudaStream_t stream) {
+    (void)variant;
+    const int tiles = a.gx * a.gy;
+    if (tiles <= 0) return GSB_OK;
+    GSB_LAUNCH("render_bwd", debug, stream, render_bwd_kernel, tiles, 256, 0, a);
+    return GSB_OK;
+}
+
+}  // namespace gsb

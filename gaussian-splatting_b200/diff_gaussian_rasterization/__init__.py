@@ -1,0 +1,354 @@
+"""Drop-in ``diff_gaussian_rasterization`` package backed by libgs_b200.so (sm_100a CUDA, C ABI).
+
+Mirrors the surface the reference imports at /root/reference/gaussian_renderer/__init__.py:14
+(``GaussianRasterizationSettings``, ``GaussianRasterizer``) and calls at :36-52 / :91-110, plus the
+``rasterize_gaussians`` autograd.Function named in BASELINE.json north_star.  ``SparseGaussianAdam``
+is deliberately NOT exported: its presence would flip ``separate_sh`` in train.py:38,111.
+
+There is no CPU path and no fallback: importing this package without the built library raises.
+Host code is plumbing only -- tensors in, raw device pointers across the C ABI (include/gs_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import CFUNCTYPE, POINTER, Structure, byref, c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians"]
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(os.path.dirname(_PKG_DIR), "libgs_b200.so")
+
+
+# ---------------------------------------------------------------------------------------------
+# C ABI mirror (include/gs_b200.h)
+# ---------------------------------------------------------------------------------------------
+class _Settings(Structure):
+    _fields_ = [("image_height", c_int32), ("image_width", c_int32), ("tanfovx", c_float), ("tanfovy", c_float),
+                ("bg", c_void_p), ("scale_modifier", c_float), ("viewmatrix", c_void_p), ("projmatrix", c_void_p),
+                ("sh_degree", c_int32), ("campos", c_void_p), ("prefiltered", c_int32), ("debug", c_int32),
+                ("antialiasing", c_int32), ("sh_coeffs", c_int32)]
+
+
+class _Inputs(Structure):
+    _fields_ = [("P", c_int32), ("means3D", c_void_p), ("shs", c_void_p), ("colors_precomp", c_void_p),
+                ("opacities", c_void_p), ("scales", c_void_p), ("rotations", c_void_p), ("cov3D_precomp", c_void_p)]
+
+
+class _State(Structure):
+    _fields_ = [("P", c_int32), ("num_tiles", c_int32), ("num_rendered", c_int64), ("num_visible", c_int64),
+                ("geom", c_void_p), ("geom_bytes", c_size_t), ("binning", c_void_p), ("binning_bytes", c_size_t),
+                ("image", c_void_p), ("image_bytes", c_size_t)]
+
+
+class _Grads(Structure):
+    _fields_ = [("dL_dmeans3D", c_void_p), ("dL_dmeans2D", c_void_p), ("dL_dshs", c_void_p), ("dL_dcolors", c_void_p),
+                ("dL_dopacities", c_void_p), ("dL_dscales", c_void_p), ("dL_drotations", c_void_p),
+                ("dL_dcov3D", c_void_p)]
+
+
+_ALLOC_FN = CFUNCTYPE(c_void_p, c_void_p, c_int32, c_size_t)
+BUF_GEOM, BUF_BINNING, BUF_IMAGE = 0, 1, 2
+
+
+def _load():
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"(or `make -C gaussian-splatting_b200/csrc`).  There is no CPU fallback.")
+    lib = ctypes.CDLL(_LIB_PATH)
+    lib.gsb_forward.restype = c_int32
+    lib.gsb_forward.argtypes = [POINTER(_Settings), POINTER(_Inputs), c_void_p, c_void_p, c_void_p, _ALLOC_FN,
+                                c_void_p, POINTER(_State), c_void_p]
+    lib.gsb_backward.restype = c_int32
+    lib.gsb_backward.argtypes = [POINTER(_Settings), POINTER(_Inputs), POINTER(_State), c_void_p, c_void_p,
+                                 POINTER(_Grads), c_int32, _ALLOC_FN, c_void_p, c_void_p]
+    lib.gsb_mark_visible.restype = c_int32
+    lib.gsb_mark_visible.argtypes = [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.gsb_sort_pairs.restype = c_int32
+    lib.gsb_sort_pairs.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, _ALLOC_FN, c_void_p, c_void_p]
+    lib.gsb_last_error.restype = c_char_p
+    lib.gsb_abi_version.restype = c_int32
+    lib.gsb_launch_count.restype = c_int64
+    lib.gsb_reset_launch_count.restype = None
+    lib.gsb_kernel_time.restype = c_int32
+    lib.gsb_kernel_time.argtypes = [c_char_p, POINTER(ctypes.c_double), POINTER(c_int64), c_int32]
+    lib.gsb_set_option.restype = c_int32
+    lib.gsb_set_option.argtypes = [c_char_p, c_int32]
+    if lib.gsb_abi_version() != 1:
+        raise ImportError(f"{_LIB_PATH}: ABI version {lib.gsb_abi_version()} != 1")
+    return lib
+
+
+_C = _load()
+
+
+def launch_count() -> int:
+    """Kernels launched by libgs_b200.so in this process since the last reset."""
+    return int(_C.gsb_launch_count())
+
+
+def reset_launch_count() -> None:
+    _C.gsb_reset_launch_count()
+
+
+def set_option(name: str, value: int) -> None:
+    if _C.gsb_set_option(name.encode(), int(value)) != 0:
+        raise KeyError(name)
+
+
+def kernel_time(name: str = "", reset: bool = False):
+    """(total_ms, launches) of kernel `name` ("" = all) timed with CUDA events on the launching stream while
+    option time_kernels was on."""
+    ms, n = ctypes.c_double(0.0), c_int64(0)
+    _C.gsb_kernel_time(name.encode(), byref(ms), byref(n), int(reset))
+    return float(ms.value), int(n.value)
+
+
+def state_views(pack: dict, height: int, width: int):
+    """Typed views over the forward state buffers (layout: csrc/abi.cu carve_image / carve_binning); for tests
+    and the benchmark's instance statistics."""
+    npix = height * width
+    al = lambda v: (v + 255) // 256 * 256
+    img, binning, D = pack["image"], pack["binning"], pack["num_rendered"]
+    final_T = img[:npix * 4].view(torch.float32).view(height, width)
+    n_contrib = img[al(npix * 4):al(npix * 4) + npix * 4].view(torch.int32).view(height, width)
+    pl_bytes = max(D, 1) * 4
+    point_list = binning[:D * 4].view(torch.int32)
+    num_tiles = int(pack["state"].num_tiles)
+    ranges = binning[al(pl_bytes):al(pl_bytes) + num_tiles * 8].view(torch.int32).view(num_tiles, 2)
+    return dict(final_T=final_T, n_contrib=n_contrib, point_list=point_list, ranges=ranges)
+
+
+class _Arena:
+    """Hands torch-owned device memory to the library (torch caching allocator)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+        self.error = None
+        self.cb = _ALLOC_FN(self._alloc)
+
+    def _alloc(self, _ctx, which, nbytes):
+        try:
+            t = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            self.bufs[int(which)] = t
+            return t.data_ptr()
+        except Exception as e:  # never let an exception cross the C ABI
+            self.error = e
+            return None
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None or t.numel() == 0:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _check(rc: int, arena: Optional[_Arena] = None):
+    if rc != 0:
+        msg = _C.gsb_last_error().decode(errors="replace")
+        if arena is not None and arena.error is not None:
+            raise RuntimeError(f"libgs_b200: {msg}") from arena.error
+        raise RuntimeError(f"libgs_b200 error {rc}: {msg}")
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+    antialiasing: bool
+
+
+def _c_settings(rs: GaussianRasterizationSettings, sh_coeffs: int, keep: list) -> _Settings:
+    dev_t = [_f32c(rs.bg), _f32c(rs.viewmatrix), _f32c(rs.projmatrix), _f32c(rs.campos)]
+    keep.extend(dev_t)
+    s = _Settings()
+    s.image_height = int(rs.image_height)
+    s.image_width = int(rs.image_width)
+    s.tanfovx = float(rs.tanfovx)
+    s.tanfovy = float(rs.tanfovy)
+    s.bg = _ptr(dev_t[0])
+    s.scale_modifier = float(rs.scale_modifier)
+    s.viewmatrix = _ptr(dev_t[1])
+    s.projmatrix = _ptr(dev_t[2])
+    s.sh_degree = int(rs.sh_degree)
+    s.campos = _ptr(dev_t[3])
+    s.prefiltered = int(bool(rs.prefiltered))
+    s.debug = int(bool(rs.debug))
+    s.antialiasing = int(bool(rs.antialiasing))
+    s.sh_coeffs = int(sh_coeffs)
+    return s
+
+
+def _c_inputs(P, means3D, sh, colors, opac, scales, rots, cov) -> _Inputs:
+    i = _Inputs()
+    i.P = int(P)
+    i.means3D, i.shs, i.colors_precomp, i.opacities = _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opac)
+    i.scales, i.rotations, i.cov3D_precomp = _ptr(scales), _ptr(rots), _ptr(cov)
+    return i
+
+
+def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs):
+    """Returns (color, radii, invdepth, ctx_pack).  All tensor arguments already float32-contiguous or None."""
+    if not means3D.is_cuda:
+        raise RuntimeError("diff_gaussian_rasterization (B200): tensors must live on a CUDA device; there is no CPU path")
+    dev = means3D.device
+    P = int(means3D.shape[0])
+    H, W = int(rs.image_height), int(rs.image_width)
+    M = int(sh.shape[1]) if sh is not None else 0
+    with torch.cuda.device(dev):
+        keep = []
+        cs = _c_settings(rs, M, keep)
+        ci = _c_inputs(P, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
+        color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        invdepth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+        arena = _Arena(dev)
+        st = _State()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = _C.gsb_forward(byref(cs), byref(ci), color.data_ptr(), radii.data_ptr(), invdepth.data_ptr(), arena.cb,
+                            None, byref(st), stream)
+        _check(rc, arena)
+    pack = dict(state=st, geom=arena.bufs.get(BUF_GEOM), binning=arena.bufs.get(BUF_BINNING),
+                image=arena.bufs.get(BUF_IMAGE), num_rendered=int(st.num_rendered), sh_coeffs=M)
+    return color, radii, invdepth, pack
+
+
+def _backward_impl(pack, rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                   grad_color, grad_invdepth, grads: dict, accumulate: bool):
+    dev = means3D.device
+    P = int(means3D.shape[0])
+    with torch.cuda.device(dev):
+        keep = []
+        cs = _c_settings(rs, pack["sh_coeffs"], keep)
+        ci = _c_inputs(P, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
+        g = _Grads()
+        g.dL_dmeans3D, g.dL_dmeans2D = _ptr(grads.get("means3D")), _ptr(grads.get("means2D"))
+        g.dL_dshs, g.dL_dcolors = _ptr(grads.get("shs")), _ptr(grads.get("colors_precomp"))
+        g.dL_dopacities = _ptr(grads.get("opacities"))
+        g.dL_dscales, g.dL_drotations = _ptr(grads.get("scales")), _ptr(grads.get("rotations"))
+        g.dL_dcov3D = _ptr(grads.get("cov3D_precomp"))
+        arena = _Arena(dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = _C.gsb_backward(byref(cs), byref(ci), byref(pack["state"]), grad_color.data_ptr(), _ptr(grad_invdepth),
+                             byref(g), int(bool(accumulate)), arena.cb, None, stream)
+        _check(rc, arena)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        args = [_f32c(means3D), _f32c(sh), _f32c(colors_precomp), _f32c(opacities), _f32c(scales), _f32c(rotations),
+                _f32c(cov3Ds_precomp)]
+        if args[0] is None:  # P == 0
+            args[0] = means3D.float().contiguous()
+        try:
+            color, radii, invdepth, pack = _forward_impl(*args, raster_settings)
+        except Exception:
+            if raster_settings.debug:
+                torch.save([a.detach().cpu() if a is not None else None for a in args], "snapshot_fw.dump")
+                print("\nAn error occured in forward. Writing snapshot_fw.dump for debugging.")
+            raise
+        ctx.raster_settings = raster_settings
+        ctx.pack = pack
+        ctx.shapes = dict(means2D=None if means2D is None else tuple(means2D.shape), opacities=tuple(opacities.shape),
+                          sh=None if sh is None else tuple(sh.shape))
+        ctx.save_for_backward(*[a if a is not None else torch.empty(0) for a in args])
+        ctx.mark_non_differentiable(radii)
+        return color, radii, invdepth
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii, grad_out_depth):
+        rs = ctx.raster_settings
+        saved = [t if t.numel() > 0 else None for t in ctx.saved_tensors]
+        means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp = saved
+        if means3D is None:
+            means3D = ctx.saved_tensors[0]
+        dev = means3D.device
+        P = int(means3D.shape[0])
+        new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        grads = dict(means3D=new(P, 3), means2D=new(P, 3), opacities=new(P))
+        if sh is not None:
+            grads["shs"] = new(*sh.shape)
+        if colors_precomp is not None:
+            grads["colors_precomp"] = new(P, 3)
+        if cov3Ds_precomp is not None:
+            grads["cov3D_precomp"] = new(P, 6)
+        else:
+            grads["scales"] = new(P, 3)
+            grads["rotations"] = new(P, 4)
+        gc = _f32c(grad_out_color)
+        if gc is None:
+            gc = torch.zeros((3, int(rs.image_height), int(rs.image_width)), dtype=torch.float32, device=dev)
+        gd = _f32c(grad_out_depth)
+        try:
+            _backward_impl(ctx.pack, rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                           gc, gd, grads, accumulate=False)
+        except Exception:
+            if rs.debug:
+                torch.save([t.detach().cpu() for t in ctx.saved_tensors] + [gc.cpu()], "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+            raise
+        g_op = grads["opacities"].reshape(ctx.shapes["opacities"])
+        return (grads["means3D"], grads["means2D"] if ctx.shapes["means2D"] is not None else None, grads.get("shs"),
+                grads.get("colors_precomp"), g_op, grads.get("scales"), grads.get("rotations"),
+                grads.get("cov3D_precomp"), None)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions: torch.Tensor) -> torch.Tensor:
+        """Frustum test only; bool [P]."""
+        with torch.no_grad():
+            rs = self.raster_settings
+            pos = _f32c(positions)
+            P = int(positions.shape[0])
+            present = torch.zeros((P,), dtype=torch.uint8, device=positions.device)
+            if P > 0:
+                view, proj = _f32c(rs.viewmatrix), _f32c(rs.projmatrix)
+                with torch.cuda.device(positions.device):
+                    rc = _C.gsb_mark_visible(P, pos.data_ptr(), view.data_ptr(), proj.data_ptr(), present.data_ptr(),
+                                             torch.cuda.current_stream(positions.device).cuda_stream)
+                _check(rc)
+            return present.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        rs = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                   rs)

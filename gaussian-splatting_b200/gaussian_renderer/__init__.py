@@ -1,0 +1,160 @@
+"""Render glue for the B200 rasterizer: ``render()`` with the reference's signature and return dict
+(/root/reference/gaussian_renderer/__init__.py:18-128) plus the view-batch path BASELINE.json's
+north_star adds ("gaussian_renderer/__init__.py gains a view-batch path"):
+
+* ``render_views`` -- several cameras against the same (replicated) gaussians in one call;
+* ``GradientBucket`` -- one flat buffer holding every per-gaussian gradient, so that the data-parallel
+  step is a SINGLE all-reduce over NVLink (views shard across ranks, gaussians are replicated;
+  SURVEY.md section 8e).  The reference has no distributed path at all.
+
+The reference's own file stays usable unchanged: it only needs ``diff_gaussian_rasterization`` on the
+path.  This module exists for the view-batch path and for callers that have no
+``scene.GaussianModel`` (it duck-types ``pc``).
+"""
+from __future__ import annotations
+
+import math
+from typing import Iterable, List, Optional, Sequence
+
+import torch
+
+from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+
+__all__ = ["render", "render_views", "GradientBucket", "shard_views"]
+
+
+def _eval_sh(deg, sh, dirs):
+    # torch-side SH only for pipe.convert_SHs_python; formula /root/reference/utils/sh_utils.py:57-112
+    C0, C1 = 0.28209479177387814, 0.4886025119029199
+    C2 = [1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396]
+    C3 = [-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+          1.445305721320277, -0.5900435899266435]
+    result = C0 * sh[..., 0]
+    if deg > 0:
+        x, y, z = dirs[..., 0:1], dirs[..., 1:2], dirs[..., 2:3]
+        result = result - C1 * y * sh[..., 1] + C1 * z * sh[..., 2] - C1 * x * sh[..., 3]
+        if deg > 1:
+            xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+            result = (result + C2[0] * xy * sh[..., 4] + C2[1] * yz * sh[..., 5] + C2[2] * (2.0 * zz - xx - yy) * sh[..., 6]
+                      + C2[3] * xz * sh[..., 7] + C2[4] * (xx - yy) * sh[..., 8])
+            if deg > 2:
+                result = (result + C3[0] * y * (3 * xx - yy) * sh[..., 9] + C3[1] * xy * z * sh[..., 10]
+                          + C3[2] * y * (4 * zz - xx - yy) * sh[..., 11] + C3[3] * z * (2 * zz - 3 * xx - 3 * yy) * sh[..., 12]
+                          + C3[4] * x * (4 * zz - xx - yy) * sh[..., 13] + C3[5] * z * (xx - yy) * sh[..., 14]
+                          + C3[6] * x * (xx - 3 * yy) * sh[..., 15])
+    return result
+
+
+def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, separate_sh=False,
+           override_color=None, use_trained_exp=False):
+    """Same contract as the reference's render(): returns
+    {"render", "viewspace_points", "visibility_filter", "radii", "depth"}."""
+    xyz = pc.get_xyz
+    screenspace_points = torch.zeros_like(xyz, dtype=xyz.dtype, requires_grad=True, device=xyz.device) + 0
+    try:
+        screenspace_points.retain_grad()
+    except Exception:
+        pass
+    raster_settings = GaussianRasterizationSettings(
+        image_height=int(viewpoint_camera.image_height), image_width=int(viewpoint_camera.image_width),
+        tanfovx=math.tan(viewpoint_camera.FoVx * 0.5), tanfovy=math.tan(viewpoint_camera.FoVy * 0.5),
+        bg=bg_color, scale_modifier=scaling_modifier, viewmatrix=viewpoint_camera.world_view_transform,
+        projmatrix=viewpoint_camera.full_proj_transform, sh_degree=pc.active_sh_degree,
+        campos=viewpoint_camera.camera_center, prefiltered=False, debug=bool(getattr(pipe, "debug", False)),
+        antialiasing=bool(getattr(pipe, "antialiasing", False)))
+    rasterizer = GaussianRasterizer(raster_settings=raster_settings)
+
+    scales = rotations = cov3D_precomp = None
+    if getattr(pipe, "compute_cov3D_python", False):
+        cov3D_precomp = pc.get_covariance(scaling_modifier)
+    else:
+        scales, rotations = pc.get_scaling, pc.get_rotation
+
+    shs = colors_precomp = None
+    if override_color is None:
+        if getattr(pipe, "convert_SHs_python", False):
+            feats = pc.get_features
+            shs_view = feats.transpose(1, 2).view(-1, 3, (pc.max_sh_degree + 1) ** 2)
+            dir_pp = xyz - viewpoint_camera.camera_center.repeat(feats.shape[0], 1)
+            dir_pp = dir_pp / dir_pp.norm(dim=1, keepdim=True)
+            colors_precomp = torch.clamp_min(_eval_sh(pc.active_sh_degree, shs_view, dir_pp) + 0.5, 0.0)
+        elif separate_sh:
+            # the B200 rasterizer takes one [P,K,3] tensor; the split layout of the accel branch is re-joined here
+            shs = torch.cat((pc.get_features_dc, pc.get_features_rest), dim=1)
+        else:
+            shs = pc.get_features
+    else:
+        colors_precomp = override_color
+
+    rendered_image, radii, depth_image = rasterizer(
+        means3D=xyz, means2D=screenspace_points, shs=shs, colors_precomp=colors_precomp, opacities=pc.get_opacity,
+        scales=scales, rotations=rotations, cov3D_precomp=cov3D_precomp)
+
+    if use_trained_exp:
+        exposure = pc.get_exposure_from_name(viewpoint_camera.image_name)
+        rendered_image = torch.matmul(rendered_image.permute(1, 2, 0), exposure[:3, :3]).permute(2, 0, 1) \
+            + exposure[:3, 3, None, None]
+    rendered_image = rendered_image.clamp(0, 1)
+    return {"render": rendered_image, "viewspace_points": screenspace_points,
+            "visibility_filter": (radii > 0).nonzero(), "radii": radii, "depth": depth_image}
+
+
+def render_views(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch.Tensor, **kw) -> List[dict]:
+    """View-batch path: the same gaussians rendered from several cameras.  Each entry is a render() dict and
+    stays connected to autograd, so ``sum(losses).backward()`` accumulates every view's per-gaussian gradient
+    into the parameters' ``.grad`` (which GradientBucket maps onto one flat buffer)."""
+    return [render(cam, pc, pipe, bg_color, **kw) for cam in viewpoint_cameras]
+
+
+def shard_views(views: Sequence, rank: int, world_size: int) -> list:
+    """Round-robin view partition over ranks."""
+    return [v for i, v in enumerate(views) if i % world_size == rank]
+
+
+class GradientBucket:
+    """Maps the ``.grad`` of every gaussian parameter onto views of ONE flat float32 buffer, so the
+    data-parallel reduction is a single ``all_reduce`` (59 floats per gaussian at SH degree 3:
+    xyz 3, f_dc 3, f_rest 45, opacity 1, scaling 3, rotation 4; parameter groups at
+    /root/reference/scene/gaussian_model.py:183-190), followed by the per-view densification
+    statistics the training loop needs identical on every rank."""
+
+    def __init__(self, params: Iterable[torch.Tensor]):
+        self.params = [p for p in params]
+        if not self.params:
+            raise ValueError("GradientBucket needs at least one parameter")
+        dev, total = self.params[0].device, sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError("GradientBucket: float32 parameters on one device only")
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def all_reduce(self, group=None, average: bool = False):
+        """One collective for all per-gaussian gradients.  No-op for world size 1."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return self.flat
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            self.flat.div_(dist.get_world_size(group))
+        return self.flat
+
+    @staticmethod
+    def reduce_densification_stats(grad_norm_accum: torch.Tensor, denom: torch.Tensor, max_radii2D: torch.Tensor,
+                                   group=None):
+        """Per-view statistics feeding densify/prune (gaussian_model.py:471-473, train.py:166) must agree on
+        all ranks: sum for the accumulated gradient norm and its count, max for the radii."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        packed = torch.cat([grad_norm_accum.reshape(-1), denom.reshape(-1).to(grad_norm_accum.dtype)])
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        n = grad_norm_accum.numel()
+        grad_norm_accum.copy_(packed[:n].view_as(grad_norm_accum))
+        denom.copy_(packed[n:].view_as(denom).to(denom.dtype))
+        dist.all_reduce(max_radii2D, op=dist.ReduceOp.MAX, group=group)

@@ -1,0 +1,156 @@
+/*
+ * gs_b200.h -- C ABI of libgs_b200.so, the B200 (sm_100a) differentiable 3D-Gaussian-splatting
+ * rasterizer.  Plain C: raw device pointers, explicit sizes, explicit stream, int error codes.
+ * No torch types, no exceptions, no hidden global state except a per-device pinned 16-byte
+ * read-back slot and the launch counter.
+ *
+ * What each entry point replaces in the reference (graphdeco-inria/gaussian-splatting):
+ * the reference reaches this path ONLY through the python package imported at
+ *   /root/reference/gaussian_renderer/__init__.py:14
+ *       from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+ * constructed at :36-52 and called at :91-110.  The package's native side
+ * (submodules/diff-gaussian-rasterization @ 59f5f77e: rasterize_points.cu, cuda_rasterizer/)
+ * is an EMPTY directory in /root/reference, so no file:line exists for the pybind functions;
+ * by name (BASELINE.json north_star) they are
+ *   _C.rasterize_gaussians           -> gsb_forward
+ *   _C.rasterize_gaussians_backward  -> gsb_backward
+ *   _C.mark_visible                  -> gsb_mark_visible
+ * The reference-side binding a maintainer adds is a ctypes stub: INTEGRATION.md.
+ *
+ * Conventions
+ *  - all tensors float32, contiguous, on the device that is current when the call is made;
+ *  - viewmatrix / projmatrix are the TRANSPOSED 4x4 matrices of scene/cameras.py:86-88,
+ *    flattened row-major (element [r][c] at 4*r+c), i.e. p_view = [x y z 1] * viewmatrix;
+ *  - shs is [P, sh_coeffs, 3]; sh_degree is the ACTIVE degree (0..3)
+ *    (gaussian_renderer/__init__.py:45,76);
+ *  - every kernel is enqueued on `stream`; the only host synchronisation is the read-back of
+ *    the instance count inside gsb_forward;
+ *  - memory is obtained through the caller's allocator so that it lives in the caller's pool
+ *    (torch caching allocator): scratch is released by the caller after the call returns,
+ *    GEOM / BINNING / IMAGE must stay alive until gsb_backward has been enqueued.
+ */
+#ifndef GS_B200_H
+#define GS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSB_ABI_VERSION 1
+
+/* error codes (0 = ok); gsb_last_error() holds the message of the calling thread's last failure */
+#define GSB_OK 0
+#define GSB_ERR_ARGUMENT 1
+#define GSB_ERR_CUDA 2
+#define GSB_ERR_ALLOC 3
+#define GSB_ERR_OVERFLOW 4
+
+/* buffer classes passed to the allocator */
+#define GSB_BUF_GEOM 0     /* per-gaussian forward state, kept for backward   */
+#define GSB_BUF_BINNING 1  /* sorted per-tile gaussian lists + tile ranges    */
+#define GSB_BUF_IMAGE 2    /* per-pixel final transmittance + contributor count */
+#define GSB_BUF_SCRATCH0 3 /* temporaries, may be freed when the call returns */
+#define GSB_BUF_SCRATCH1 4
+#define GSB_BUF_SCRATCH2 5
+
+/* returns a device pointer aligned to >= 256 bytes, or NULL */
+typedef void *(*gsb_alloc_fn)(void *ctx, int32_t which, size_t bytes);
+
+/* the 13 fields of GaussianRasterizationSettings (gaussian_renderer/__init__.py:36-50)
+ * plus the coefficient count of the shs tensor */
+typedef struct GsbSettings {
+    int32_t image_height;
+    int32_t image_width;
+    float tanfovx;
+    float tanfovy;
+    const float *bg;         /* device [3]  */
+    float scale_modifier;
+    const float *viewmatrix; /* device [16] */
+    const float *projmatrix; /* device [16] */
+    int32_t sh_degree;
+    const float *campos;     /* device [3]  */
+    int32_t prefiltered;
+    int32_t debug;           /* !=0: synchronise + check after every kernel */
+    int32_t antialiasing;
+    int32_t sh_coeffs;       /* M of shs[P,M,3]; 0 when colors_precomp is given */
+} GsbSettings;
+
+/* arguments of GaussianRasterizer.forward (gaussian_renderer/__init__.py:102-110).
+ * Exactly one of shs / colors_precomp and one of (scales+rotations) / cov3D_precomp is non-NULL. */
+typedef struct GsbInputs {
+    int32_t P;
+    const float *means3D;        /* [P,3] */
+    const float *shs;            /* [P,M,3] or NULL */
+    const float *colors_precomp; /* [P,3] or NULL */
+    const float *opacities;      /* [P] */
+    const float *scales;         /* [P,3] or NULL */
+    const float *rotations;      /* [P,4] or NULL */
+    const float *cov3D_precomp;  /* [P,6] or NULL */
+} GsbInputs;
+
+/* forward state handed back to gsb_backward (plain data; the caller owns the three buffers) */
+typedef struct GsbState {
+    int32_t P;
+    int32_t num_tiles;
+    int64_t num_rendered;   /* D: (gaussian, tile) instances after exact tile culling */
+    int64_t num_visible;    /* gaussians with radius > 0 */
+    void *geom;
+    size_t geom_bytes;
+    void *binning;
+    size_t binning_bytes;
+    void *image;
+    size_t image_bytes;
+} GsbState;
+
+/* gradient outputs of the autograd.Function's backward; NULL pointers are skipped */
+typedef struct GsbGrads {
+    float *dL_dmeans3D;      /* [P,3] */
+    float *dL_dmeans2D;      /* [P,3]  (x,y = gradient of the NDC 2D mean, z = 0) */
+    float *dL_dshs;          /* [P,M,3] */
+    float *dL_dcolors;       /* [P,3] */
+    float *dL_dopacities;    /* [P] */
+    float *dL_dscales;       /* [P,3] */
+    float *dL_drotations;    /* [P,4] */
+    float *dL_dcov3D;        /* [P,6] */
+} GsbGrads;
+
+/* Forward: preprocess -> depth sort -> tile binning -> tile sort -> tile ranges -> blend.
+ * out_color [3,H,W], out_radii [P] int32, out_invdepth [H*W]. */
+int32_t gsb_forward(const GsbSettings *settings, const GsbInputs *in, float *out_color,
+                    int32_t *out_radii, float *out_invdepth, gsb_alloc_fn alloc, void *alloc_ctx,
+                    GsbState *state_out, void *cuda_stream);
+
+/* Backward.  dL_dinvdepth may be NULL.  accumulate != 0 adds into the gradient tensors
+ * instead of overwriting them (view-batch path: one buffer summed over views). */
+int32_t gsb_backward(const GsbSettings *settings, const GsbInputs *in, const GsbState *state,
+                     const float *dL_dcolor, const float *dL_dinvdepth, const GsbGrads *grads,
+                     int32_t accumulate, gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream);
+
+/* Frustum test only (GaussianRasterizer.markVisible): present[i] = 1 if view-space z > 0.2 */
+int32_t gsb_mark_visible(int32_t P, const float *means3D, const float *viewmatrix,
+                         const float *projmatrix, uint8_t *present, void *cuda_stream);
+
+/* Stand-alone stable LSD radix sort of (u32 key, u32 value) pairs on bits [begin_bit,end_bit):
+ * the replacement of the reference's cub::DeviceRadixSort call, exported for tests.
+ * keys/vals are overwritten with the sorted result; scratch is obtained through alloc. */
+int32_t gsb_sort_pairs(uint32_t *keys, uint32_t *vals, int64_t n, int32_t begin_bit, int32_t end_bit,
+                       gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream);
+
+const char *gsb_last_error(void);
+int32_t gsb_abi_version(void);
+/* number of kernels this library has launched in this process since the last reset */
+int64_t gsb_launch_count(void);
+void gsb_reset_launch_count(void);
+/* CUDA-event time of the launches of kernel `name` ("" = all) recorded on their launching stream since
+ * the last reset, while option "time_kernels" was 1 (blend kernels) or 2 (all).  Synchronises on the events. */
+int32_t gsb_kernel_time(const char *name, double *total_ms, int64_t *launches, int32_t reset);
+/* tuning knobs (integers), e.g. gsb_set_option("render_variant", 1); returns 0 if known */
+int32_t gsb_set_option(const char *name, int32_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GS_B200_H */

@@ -1,0 +1,186 @@
+"""GPU parity tests (-m gpu): the sm_100a CUDA path, called through the drop-in package and the C ABI,
+against the CPU oracle (oracle/gs_oracle.c) on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): forward 1e-5 abs, gradients 1e-4 rel; see tests/_util.py for how
+threshold flips at alpha = 1/255 are counted rather than absorbed."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_oracle as TO
+import gs_test_util as U
+
+pytestmark = pytest.mark.gpu
+
+
+def _weights(cam, seed=5):
+    gen = torch.Generator().manual_seed(seed)
+    H, W = cam.image_height, cam.image_width
+    return torch.randn(3, H, W, generator=gen).numpy(), torch.randn(1, H, W, generator=gen).numpy()
+
+
+def _check(scene, cam, mode, with_depth_grad=True, grad_slack=0.0):
+    args = U.make_args(scene, mode)
+    wc, wd = _weights(cam)
+    if not with_depth_grad:
+        wd = None
+    got = U.run_cuda(args, cam, wc, wd)
+    ref = U.run_oracle(args, cam, wc, wd)
+    assert (got["radii"] == ref["radii"]).all(), "radii differ"
+    mx, frac = U.assert_image_close(got["color"], ref["color"], "color")
+    U.assert_image_close(got["invdepth"], ref["invdepth"], "invdepth")
+    slack = grad_slack + (5e-3 if frac > 0 else 0.0)
+    U.assert_grads_close(got["grads"], ref["grads"], flips=slack)
+    return got, ref
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_sh_degrees(deg):
+    scene = TO.make_scene(2000, seed=10 + deg, log_scale_mean=-2.8)
+    cam = TO.make_camera(160, 96, sh_degree=deg, bg=(0.1, 0.3, 0.6))
+    _check(scene, cam, "sh")
+
+
+@pytest.mark.parametrize("aa", [False, True])
+@pytest.mark.parametrize("mode", ["sh", "precomp"])
+def test_modes_and_antialiasing(aa, mode):
+    scene = TO.make_scene(3000, seed=21, log_scale_mean=-3.0)
+    cam = TO.make_camera(200, 120, sh_degree=3, antialiasing=aa, bg=(1.0, 1.0, 1.0))
+    _check(scene, cam, mode)
+
+
+def test_ragged_image_size_and_scale_modifier():
+    scene = TO.make_scene(1500, seed=33, log_scale_mean=-2.6)
+    cam = TO.make_camera(131, 77, sh_degree=2, scale_modifier=0.7, bg=(0.0, 0.0, 0.0))
+    _check(scene, cam, "sh")
+
+
+def test_no_depth_gradient():
+    scene = TO.make_scene(1000, seed=34, log_scale_mean=-2.6)
+    cam = TO.make_camera(96, 64, sh_degree=1)
+    _check(scene, cam, "sh", with_depth_grad=False)
+
+
+def test_large_and_anisotropic_gaussians():
+    """Gaussians spanning many tiles, strongly anisotropic: exercises the exact tile culling."""
+    scene = TO.make_scene(400, seed=35, log_scale_mean=-1.2, log_scale_std=1.2)
+    cam = TO.make_camera(256, 160, sh_degree=3, bg=(0.5, 0.5, 0.5))
+    _check(scene, cam, "sh")
+
+
+def test_camera_inside_the_cloud():
+    """Points behind / beside the camera: near cull, frustum clamp of the Jacobian."""
+    scene = TO.make_scene(4000, seed=36, log_scale_mean=-3.0)
+    cam = TO.make_camera(160, 120, sh_degree=3, eye=(0.1, 0.05, -0.4))
+    _check(scene, cam, "sh", grad_slack=1e-3)
+
+
+def test_low_opacity_never_visible():
+    scene = TO.make_scene(500, seed=37, log_scale_mean=-2.5)
+    scene["opacities"] = scene["opacities"] * 0.003  # below 1/255: contributes nowhere
+    cam = TO.make_camera(96, 64, sh_degree=0)
+    got, ref = _check(scene, cam, "sh")
+    assert (got["radii"] > 0).any()
+    assert np.abs(got["color"]).max() == 0.0
+
+
+def test_empty_input_and_all_culled():
+    import diff_gaussian_rasterization as dgr
+    cam = TO.make_camera(64, 48, sh_degree=0, bg=(0.2, 0.4, 0.6))
+    rs = U.settings_to(cam, "cuda")
+    rast = dgr.GaussianRasterizer(rs)
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    color, radii, invd = rast(means3D=z(0, 3), means2D=z(0, 3), opacities=z(0, 1), shs=z(0, 1, 3), scales=z(0, 3), rotations=z(0, 4))
+    assert radii.numel() == 0
+    assert torch.allclose(color, cam.bg.cuda()[:, None, None].expand(3, 48, 64))
+    scene = TO.make_scene(100, seed=1, sh_coeffs=1)
+    scene["means3D"][:, 2] -= 100.0
+    got = U.run_cuda(U.make_args(scene, "sh"), cam, *_weights(cam))
+    assert (got["radii"] == 0).all()
+    assert all(np.all(v == 0) for v in got["grads"].values() if v is not None)
+
+
+def test_cull_on_off_identical_image():
+    """Exact tile culling must not change a single pixel or gradient beyond atomics' summation order."""
+    import diff_gaussian_rasterization as dgr
+    scene = TO.make_scene(5000, seed=40, log_scale_mean=-2.5, log_scale_std=0.9)
+    cam = TO.make_camera(320, 200, sh_degree=3, bg=(0.3, 0.2, 0.1))
+    args = U.make_args(scene, "sh")
+    wc, wd = _weights(cam)
+    dgr.set_option("cull", 0)
+    try:
+        a = U.run_cuda(args, cam, wc, wd)
+    finally:
+        dgr.set_option("cull", 1)
+    b = U.run_cuda(args, cam, wc, wd)
+    assert np.array_equal(a["color"], b["color"])
+    assert np.array_equal(a["invdepth"], b["invdepth"])
+    for k, v in a["grads"].items():
+        if v is not None:
+            assert np.abs(v - b["grads"][k]).max() <= 1e-5 * (np.abs(v).max() + 1e-20), k
+
+
+def test_mark_visible():
+    import diff_gaussian_rasterization as dgr
+    scene = TO.make_scene(1000, seed=41)
+    cam = TO.make_camera(64, 64, eye=(0.0, 0.0, -0.5))
+    rast = dgr.GaussianRasterizer(U.settings_to(cam, "cuda"))
+    vis = rast.markVisible(scene["means3D"].cuda()).cpu().numpy()
+    pv = (scene["means3D"] @ cam.viewmatrix[:3, :3] + cam.viewmatrix[3, :3])[:, 2].numpy()
+    assert (vis == (pv > 0.2)).all()
+
+
+def test_python_side_sh_and_cov_switches_agree():
+    """The reference's self-consistency switches (--convert_SHs_python / --compute_cov3D_python,
+    gaussian_renderer/__init__.py:64-80): torch-side colour / covariance vs in-kernel must give the same image."""
+    scene = TO.make_scene(2500, seed=42, log_scale_mean=-2.8)
+    cam = TO.make_camera(160, 100, sh_degree=3)
+    a = U.run_cuda(U.make_args(scene, "sh"), cam)
+    d = scene["means3D"] - cam.campos[None]
+    d = d / d.norm(dim=1, keepdim=True)
+    cols = torch.clamp_min(TO.eval_sh(3, scene["shs"].transpose(1, 2), d) + 0.5, 0.0)
+    cov = TO.build_covariance(scene["scales"], 1.0, scene["rotations"], normalize=True)
+    args = dict(means3D=scene["means3D"], shs=None, colors_precomp=cols, opacities=scene["opacities"], scales=None,
+                rotations=None, cov3D_precomp=cov)
+    b = U.run_cuda(args, cam)
+    U.assert_image_close(a["color"], b["color"], "python-vs-kernel SH/cov")
+
+
+@pytest.mark.parametrize("n,bits", [(1, 32), (1000, 32), (4096, 13), (100003, 32), (1 << 20, 20)])
+def test_radix_sort_pairs_is_stable_and_sorted(n, bits):
+    import ctypes
+    import diff_gaussian_rasterization as dgr
+    g = torch.Generator().manual_seed(n)
+    hi = (1 << bits) - 1
+    keys = torch.randint(0, min(hi, 2**31 - 1) + 1, (n,), generator=g, dtype=torch.int64)
+    if bits == 32:
+        keys = keys * 2 + torch.randint(0, 2, (n,), generator=g)
+    keys = keys.clamp_max(hi)
+    k32 = keys.to(torch.uint32).cuda() if hasattr(torch, "uint32") else None
+    kd = (keys & 0xffffffff).to(torch.int64)
+    kdev = torch.empty(n, dtype=torch.int32, device="cuda")
+    kdev.copy_(torch.from_numpy(kd.numpy().astype(np.uint32).view(np.int32)))
+    vdev = torch.arange(n, dtype=torch.int32, device="cuda")
+    arena = dgr._Arena(torch.device("cuda", torch.cuda.current_device()))
+    rc = dgr._C.gsb_sort_pairs(kdev.data_ptr(), vdev.data_ptr(), n, 0, bits, arena.cb, None,
+                               torch.cuda.current_stream().cuda_stream)
+    dgr._check(rc, arena)
+    torch.cuda.synchronize()
+    out_k = kdev.cpu().numpy().view(np.uint32).astype(np.int64)
+    out_v = vdev.cpu().numpy()
+    order = np.argsort(kd.numpy(), kind="stable")
+    assert np.array_equal(out_k, kd.numpy()[order])
+    assert np.array_equal(out_v, order.astype(np.int32))
+
+
+def test_full_size_properties_config2():
+    """BASELINE.json configs[1]: 100k gaussians, 800x800, SH degree 0 -- checked against the oracle in full."""
+    scene = TO.make_scene(100_000, seed=0, sh_coeffs=1, log_scale_mean=-4.3)
+    cam = TO.make_camera(800, 800, sh_degree=0)
+    args = U.make_args(scene, "sh")
+    wc, wd = _weights(cam)
+    got = U.run_cuda(args, cam, wc, wd)
+    ref = U.run_oracle(args, cam, wc, wd)
+    assert (got["radii"] == ref["radii"]).all()
+    mx, frac = U.assert_image_close(got["color"], ref["color"], "color")
+    U.assert_grads_close(got["grads"], ref["grads"], flips=5e-3 if frac > 0 else 0.0)
