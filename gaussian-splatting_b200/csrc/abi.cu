@@ -182,7 +182,7 @@ int32_t gsb_kernel_time(const char *name, double *total_ms, int64_t *launches, i
 
 int32_t gsb_forward(const GsbSettings *s, const GsbInputs *in, float *out_color, int32_t *out_radii,
                     float *out_invdepth, gsb_alloc_fn alloc, void *alloc_ctx, GsbState *st, void *cuda_stream) {
-    if (!s || !in || !out_color || !out_radii || !out_invdepth || !alloc || !st) {
+    if (!s || !in || !out_color || (!out_radii && in->P > 0) || !out_invdepth || !alloc || !st) {
         set_error("gsb_forward: NULL argument");
         return GSB_ERR_ARGUMENT;
     }
@@ -297,13 +297,15 @@ int32_t gsb_forward(const GsbSettings *s, const GsbInputs *in, float *out_color,
     ra.W = cam.W; ra.H = cam.H; ra.gx = cam.gx; ra.gy = cam.gy; ra.ranges = bv.ranges; ra.point_list = bv.point_list;
     ra.splat = splat; ra.bg = s->bg; ra.out_color = out_color; ra.out_invdepth = out_invdepth; ra.final_T = iv.final_T;
     ra.n_contrib = iv.n_contrib;
-    return launch_render_fwd(ra, opt_fwd_variant, debug, stream);
+    return opt_fwd_variant >= 2 ? launch_render_fwd_mp(ra, opt_fwd_variant == 3 ? 4 : 2, debug, stream)
+                                : launch_render_fwd(ra, opt_fwd_variant, debug, stream);
 }
 
-int32_t gsb_backward(const GsbSettings *s, const GsbInputs *in, const GsbState *st, const float *dL_dcolor,
-                     const float *dL_dinvdepth, const GsbGrads *grads, int32_t accumulate, gsb_alloc_fn alloc,
-                     void *alloc_ctx, void *cuda_stream) {
-    if (!s || !in || !st || !dL_dcolor || !grads || !alloc) {
+int32_t gsb_backward(const GsbSettings *s, const GsbInputs *in, const GsbState *st, const float *out_color,
+                     const float *out_invdepth, const float *dL_dcolor, const float *dL_dinvdepth,
+                     const GsbGrads *grads, int32_t accumulate, gsb_alloc_fn alloc, void *alloc_ctx,
+                     void *cuda_stream) {
+    if (!s || !in || !st || !out_color || !out_invdepth || !dL_dcolor || !grads || !alloc) {
         set_error("gsb_backward: NULL argument");
         return GSB_ERR_ARGUMENT;
     }
@@ -336,13 +338,15 @@ int32_t gsb_backward(const GsbSettings *s, const GsbInputs *in, const GsbState *
         RenderBwdArgs ra;
         ra.W = cam.W; ra.H = cam.H; ra.gx = cam.gx; ra.gy = cam.gy; ra.ranges = bv.ranges; ra.point_list = bv.point_list;
         ra.splat = splat; ra.bg = s->bg; ra.final_T = iv.final_T; ra.n_contrib = iv.n_contrib; ra.dL_dcolor = dL_dcolor;
-        ra.dL_dinvdepth = dL_dinvdepth; ra.dacc = dacc;
-        rc = launch_render_bwd(ra, opt_bwd_variant, debug, stream);
+        ra.dL_dinvdepth = dL_dinvdepth; ra.dacc = dacc; ra.out_color = out_color; ra.out_invdepth = out_invdepth;
+        rc = opt_bwd_variant >= 2 ? launch_render_bwd_mp(ra, opt_bwd_variant == 3 ? 4 : 2, debug, stream)
+                                  : launch_render_bwd(ra, opt_bwd_variant, debug, stream);
         if (rc) return rc;
     }
     PreBwdArgs pa;
     pa.P = P; pa.means = in->means3D; pa.shs = in->shs; pa.opac = in->opacities; pa.scales = in->scales; pa.rots = in->rotations;
     pa.cov_pre = in->cov3D_precomp; pa.splat = splat; pa.dacc = dacc; pa.g = *grads;
+    pa.moments = opt_bwd_variant >= 2 ? 1 : 0;
     return launch_preprocess_bwd(cam, pa, accumulate != 0, debug, stream);
 }
 

@@ -26,6 +26,7 @@ struct PreBwdArgs {
     const float *means, *shs, *opac, *scales, *rots, *cov_pre;
     const float4 *splat;
     const float *dacc;    // [P*DACC_STRIDE]
+    int moments;          // dacc[0..4] hold raw moments of d(power) (render_mp.cu) instead of mean/conic gradients
     GsbGrads g;
 };
 
@@ -59,6 +60,7 @@ struct RenderBwdArgs {
     const float *bg;
     const float *final_T;
     const uint32_t *n_contrib;
+    const float *out_color, *out_invdepth;   // forward outputs
     const float *dL_dcolor, *dL_dinvdepth;
     float *dacc;
 };
@@ -75,5 +77,7 @@ int launch_tile_ranges(const uint32_t *sorted_tiles, int64_t D, int num_tiles, u
 
 int launch_render_fwd(const RenderFwdArgs &a, int variant, bool debug, cudaStream_t stream);
 int launch_render_bwd(const RenderBwdArgs &a, int variant, bool debug, cudaStream_t stream);
+int launch_render_fwd_mp(const RenderFwdArgs &a, int qh, bool debug, cudaStream_t stream);
+int launch_render_bwd_mp(const RenderBwdArgs &a, int qh, bool debug, cudaStream_t stream);
 
 }  // namespace gsb

@@ -12,14 +12,55 @@
 
 namespace gsb {
 
-constexpr int PRE_THREADS = 256;
+constexpr int PRE_THREADS = 128;
+
+// SH rows ([3*M] floats per gaussian, 192 B at degree 3) dominate this kernel's traffic.  A thread-per-gaussian
+// access would touch 32 different 128-byte lines per warp instruction, so the block's rows are moved between
+// global and shared memory with fully coalesced accesses and each thread works on its own row in shared memory
+// (row stride padded to an odd word count: conflict-free).
+__device__ __forceinline__ int sh_row_stride(const int n) { return n | 1; }
+
+// global -> shared: first `ncols` floats of each of the block's rows (row length n)
+__device__ __forceinline__ void stage_rows_in(const float *__restrict__ g, float *s, const int row0, const int nrows,
+                                              const int n, const int ncols) {
+    const int stride = sh_row_stride(n);
+    const int total = nrows * ncols;
+    int r = threadIdx.x / ncols, c = threadIdx.x % ncols;
+    const int dr = PRE_THREADS / ncols, dc = PRE_THREADS % ncols;
+    for (int idx = threadIdx.x; idx < total; idx += PRE_THREADS) {
+        s[r * stride + c] = __ldg(g + (size_t)(row0 + r) * n + c);
+        r += dr; c += dc;
+        if (c >= ncols) { c -= ncols; ++r; }
+    }
+}
+
+// shared -> global: full rows
+template <bool ACC>
+__device__ __forceinline__ void stage_rows_out(float *__restrict__ g, const float *s, const int row0, const int nrows,
+                                               const int n) {
+    const int stride = sh_row_stride(n);
+    const int total = nrows * n;
+    int r = threadIdx.x / n, c = threadIdx.x % n;
+    const int dr = PRE_THREADS / n, dc = PRE_THREADS % n;
+    for (int idx = threadIdx.x; idx < total; idx += PRE_THREADS) {
+        float *dst = g + (size_t)(row0 + r) * n + c;
+        if (ACC) *dst += s[r * stride + c]; else *dst = s[r * stride + c];
+        r += dr; c += dc;
+        if (c >= n) { c -= n; ++r; }
+    }
+}
 
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_fwd_kernel(const CamArgs ca, const PreFwdArgs a) {
     __shared__ CamParams cam;
+    extern __shared__ float sh_rows[];
     load_cam(ca, cam);
+    const int row0 = blockIdx.x * PRE_THREADS;
+    const int nrows = min(PRE_THREADS, a.P - row0);
+    const int shn = 3 * ca.sh_coeffs;
+    if (a.shs) stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * (ca.sh_degree + 1) * (ca.sh_degree + 1));
     __syncthreads();
-    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
+    const int i = row0 + threadIdx.x;
     if (i >= a.P) return;
 
     // defaults for a culled gaussian
@@ -77,7 +118,7 @@ preprocess_fwd_kernel(const CamArgs ca, const PreFwdArgs a) {
                     float bas[16];
                     sh_basis(cam.sh_degree, dx * inv, dy * inv, dz * inv, bas);
                     const int nb = (cam.sh_degree + 1) * (cam.sh_degree + 1);
-                    const float *sh = a.shs + (size_t)i * cam.sh_coeffs * 3;
+                    const float *sh = sh_rows + threadIdx.x * sh_row_stride(shn);
                     for (int k = 0; k < nb; ++k) {
                         r += bas[k] * sh[3 * k]; g += bas[k] * sh[3 * k + 1]; b += bas[k] * sh[3 * k + 2];
                     }
@@ -153,14 +194,20 @@ template <bool ACC>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_bwd_kernel(const CamArgs ca, const PreBwdArgs a) {
     __shared__ CamParams cam;
+    extern __shared__ float sh_rows[];
     load_cam(ca, cam);
+    const int row0 = blockIdx.x * PRE_THREADS;
+    const int nrows = min(PRE_THREADS, a.P - row0);
+    const int shn = 3 * ca.sh_coeffs;
+    const int nb = (ca.sh_degree + 1) * (ca.sh_degree + 1);
+    if (a.shs) stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * nb);
     __syncthreads();
-    const int i = blockIdx.x * PRE_THREADS + threadIdx.x;
-    if (i >= a.P) return;
+    const int i = row0 + threadIdx.x;
+    const bool live = i < a.P;
     const int M = cam.sh_coeffs;
 
-    const float4 q2 = a.splat[(size_t)i * SPLAT_F4 + 2];
-    const uint32_t bits = __float_as_uint(q2.w);
+    uint32_t bits = 0u;
+    if (live) bits = __float_as_uint(a.splat[(size_t)i * SPLAT_F4 + 2].w);
     const bool visible = (bits & 8u) != 0u;
 
     float gm[3] = {0.f, 0.f, 0.f};
@@ -174,15 +221,24 @@ preprocess_bwd_kernel(const CamArgs ca, const PreBwdArgs a) {
     float bas[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) bas[k] = 0.f;
-    const int nb = (cam.sh_degree + 1) * (cam.sh_degree + 1);
 
     if (visible) {
-        const float *acc = a.dacc + (size_t)i * DACC_STRIDE;
-        const float d_m2x = acc[0], d_m2y = acc[1];
-        const float dA = acc[2], dB = acc[3], dC = acc[4];
-        const float d_w = acc[5];
-        const float d_rgb[3] = {acc[6], acc[7], acc[8]};
-        const float d_invd = acc[9];
+        const float4 *acc = reinterpret_cast<const float4 *>(a.dacc + (size_t)i * DACC_STRIDE);
+        const float4 A0 = acc[0], A1 = acc[1], A2 = acc[2];
+        float d_m2x = A0.x, d_m2y = A0.y;
+        float dA = A0.z, dB = A0.w, dC = A1.x;
+        if (a.moments) {
+            // raw moments of t = dL/d(power):  sum t dx, t dy, t dx^2, t dx dy, t dy^2   (render_mp.cu)
+            const float4 r0 = a.splat[(size_t)i * SPLAT_F4], r1 = a.splat[(size_t)i * SPLAT_F4 + 1];
+            const float cA = r0.z, cB = r0.w, cC = r1.x;
+            const float Mx = A0.x, My = A0.y, Mxx = A0.z, Mxy = A0.w, Myy = A1.x;
+            d_m2x = (-cA * Mx - cB * My) * (0.5f * cam.W);
+            d_m2y = (-cC * My - cB * Mx) * (0.5f * cam.H);
+            dA = -0.5f * Mxx; dB = -Mxy; dC = -0.5f * Myy;
+        }
+        const float d_w = A1.y;
+        const float d_rgb[3] = {A1.z, A1.w, A2.x};
+        const float d_invd = A2.y;
         g_m2[0] = d_m2x; g_m2[1] = d_m2y;
         const float px = a.means[3 * i], py = a.means[3 * i + 1], pz = a.means[3 * i + 2];
 
@@ -197,7 +253,7 @@ preprocess_bwd_kernel(const CamArgs ca, const PreBwdArgs a) {
             d_rgb_sh[0] = (bits & 1u) ? 0.f : d_rgb[0];
             d_rgb_sh[1] = (bits & 2u) ? 0.f : d_rgb[1];
             d_rgb_sh[2] = (bits & 4u) ? 0.f : d_rgb[2];
-            const float *sh = a.shs + (size_t)i * M * 3;
+            const float *sh = sh_rows + threadIdx.x * sh_row_stride(shn);
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;
             for (int k = 1; k < nb; ++k) {
                 const float s = sh[3 * k] * d_rgb_sh[0] + sh[3 * k + 1] * d_rgb_sh[1] + sh[3 * k + 2] * d_rgb_sh[2];
@@ -316,6 +372,20 @@ preprocess_bwd_kernel(const CamArgs ca, const PreBwdArgs a) {
         }
     }
 
+    // SH gradient rows go out through shared memory (coalesced); each thread rewrites only its own row
+    if (a.g.dL_dshs && a.shs) {
+        if (live) {
+            float *o = sh_rows + threadIdx.x * sh_row_stride(shn);
+            for (int k = 0; k < M; ++k) {
+                const float bk = (k < nb && k < 16) ? bas[k] : 0.f;
+                o[3 * k] = bk * d_rgb_sh[0]; o[3 * k + 1] = bk * d_rgb_sh[1]; o[3 * k + 2] = bk * d_rgb_sh[2];
+            }
+        }
+        __syncthreads();
+        stage_rows_out<ACC>(a.g.dL_dshs, sh_rows, row0, nrows, shn);
+    }
+    if (!live) return;
+
     if (a.g.dL_dmeans3D) {
         put<ACC>(a.g.dL_dmeans3D + 3 * (size_t)i, gm[0]); put<ACC>(a.g.dL_dmeans3D + 3 * (size_t)i + 1, gm[1]);
         put<ACC>(a.g.dL_dmeans3D + 3 * (size_t)i + 2, gm[2]);
@@ -328,14 +398,6 @@ preprocess_bwd_kernel(const CamArgs ca, const PreBwdArgs a) {
     if (a.g.dL_dcolors) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) put<ACC>(a.g.dL_dcolors + 3 * (size_t)i + c, g_rgb[c]);
-    }
-    if (a.g.dL_dshs && a.shs) {
-        float *o = a.g.dL_dshs + (size_t)i * M * 3;
-        for (int k = 0; k < M; ++k) {
-            const float bk = (k < nb && k < 16) ? bas[k] : 0.f;
-            put<ACC>(o + 3 * k, bk * d_rgb_sh[0]); put<ACC>(o + 3 * k + 1, bk * d_rgb_sh[1]);
-            put<ACC>(o + 3 * k + 2, bk * d_rgb_sh[2]);
-        }
     }
     if (a.cov_pre) {
         if (a.g.dL_dcov3D) {
@@ -364,17 +426,22 @@ mark_visible_kernel(const int P, const float *__restrict__ means, const float *_
 
 int launch_preprocess_fwd(const CamArgs &ca, const PreFwdArgs &a, bool debug, cudaStream_t stream) {
     if (a.P <= 0) return GSB_OK;
-    GSB_LAUNCH("preprocess_fwd", debug, stream, preprocess_fwd_kernel, (int)ceil_div(a.P, PRE_THREADS), PRE_THREADS, 0, ca, a);
+    const size_t smem = a.shs ? (size_t)PRE_THREADS * ((3 * ca.sh_coeffs) | 1) * sizeof(float) : 0;
+    if (smem > 48 * 1024) GSB_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GSB_LAUNCH("preprocess_fwd", debug, stream, preprocess_fwd_kernel, (int)ceil_div(a.P, PRE_THREADS), PRE_THREADS, smem, ca, a);
     return GSB_OK;
 }
 
 int launch_preprocess_bwd(const CamArgs &ca, const PreBwdArgs &a, bool accumulate, bool debug, cudaStream_t stream) {
     if (a.P <= 0) return GSB_OK;
     const int grid = (int)ceil_div(a.P, PRE_THREADS);
+    const size_t smem = a.shs ? (size_t)PRE_THREADS * ((3 * ca.sh_coeffs) | 1) * sizeof(float) : 0;
     if (accumulate) {
-        GSB_LAUNCH("preprocess_bwd", debug, stream, preprocess_bwd_kernel<true>, grid, PRE_THREADS, 0, ca, a);
+        if (smem > 48 * 1024) GSB_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSB_LAUNCH("preprocess_bwd", debug, stream, preprocess_bwd_kernel<true>, grid, PRE_THREADS, smem, ca, a);
     } else {
-        GSB_LAUNCH("preprocess_bwd", debug, stream, preprocess_bwd_kernel<false>, grid, PRE_THREADS, 0, ca, a);
+        if (smem > 48 * 1024) GSB_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSB_LAUNCH("preprocess_bwd", debug, stream, preprocess_bwd_kernel<false>, grid, PRE_THREADS, smem, ca, a);
     }
     return GSB_OK;
 }

@@ -86,7 +86,40 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// v0: per-pixel threads, butterfly warp reduction of the 10 per-gaussian gradient terms, one lane adds.
+// 8 values per lane -> lane L ends with the warp total of value (L >> 2): 9 shuffles instead of 40.
+// Each xor step halves the number of values a lane carries: the lane keeps the half selected by its own
+// bit and adds the partner's copy of that half.
+__device__ __forceinline__ float warp_reduce8_transposed(const float v0, const float v1, const float v2, const float v3,
+                                                         const float v4, const float v5, const float v6, const float v7) {
+    const int lane = threadIdx.x & 31;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    const float k0 = (b4 ? v4 : v0) + __shfl_xor_sync(0xffffffffu, b4 ? v0 : v4, 16);
+    const float k1 = (b4 ? v5 : v1) + __shfl_xor_sync(0xffffffffu, b4 ? v1 : v5, 16);
+    const float k2 = (b4 ? v6 : v2) + __shfl_xor_sync(0xffffffffu, b4 ? v2 : v6, 16);
+    const float k3 = (b4 ? v7 : v3) + __shfl_xor_sync(0xffffffffu, b4 ? v3 : v7, 16);
+    const float m0 = (b3 ? k2 : k0) + __shfl_xor_sync(0xffffffffu, b3 ? k0 : k2, 8);
+    const float m1 = (b3 ? k3 : k1) + __shfl_xor_sync(0xffffffffu, b3 ? k1 : k3, 8);
+    float r = (b2 ? m1 : m0) + __shfl_xor_sync(0xffffffffu, b2 ? m0 : m1, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;  // value index = 4*b4 + 2*b3 + b2 = lane >> 2
+}
+
+// 2 values per lane -> lanes 0..15 end with the total of v0, lanes 16..31 with the total of v1: 5 shuffles
+__device__ __forceinline__ float warp_reduce2_transposed(const float v0, const float v1) {
+    const bool b4 = threadIdx.x & 16;
+    float r = (b4 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, b4 ? v0 : v1, 16);
+    r += __shfl_xor_sync(0xffffffffu, r, 8);
+    r += __shfl_xor_sync(0xffffffffu, r, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+
+// per-pixel threads; the 10 per-gaussian gradient terms are reduced over the warp and added to the
+// per-gaussian accumulator.  VARIANT 0: butterfly all-reduce, lane 0 issues 10 atomics.
+// VARIANT 1: transposed reduction (14 shuffles), 8 + 2 lanes issue one atomic each.
+template <int VARIANT>
 __global__ void __launch_bounds__(256)
 render_bwd_kernel(const RenderBwdArgs a) {
     __shared__ float4 s0[RB], s1[RB], s2[RB];
@@ -169,13 +202,21 @@ render_bwd_kernel(const RenderBwdArgs a) {
                 g_C = dL_dpow * (-0.5f * dy * dy);
                 g_o = G * dL_dalpha;
             }
-            g_mx = warp_sum(g_mx); g_my = warp_sum(g_my); g_A = warp_sum(g_A); g_B = warp_sum(g_B); g_C = warp_sum(g_C);
-            g_o = warp_sum(g_o); g_r = warp_sum(g_r); g_g = warp_sum(g_g); g_b = warp_sum(g_b); g_d = warp_sum(g_d);
-            if ((threadIdx.x & 31) == 0) {
-                float *d = a.dacc + (size_t)sid[j] * DACC_STRIDE;
-                atomicAdd(d + 0, g_mx); atomicAdd(d + 1, g_my); atomicAdd(d + 2, g_A); atomicAdd(d + 3, g_B);
-                atomicAdd(d + 4, g_C); atomicAdd(d + 5, g_o); atomicAdd(d + 6, g_r); atomicAdd(d + 7, g_g);
-                atomicAdd(d + 8, g_b); atomicAdd(d + 9, g_d);
+            float *d = a.dacc + (size_t)sid[j] * DACC_STRIDE;
+            if (VARIANT == 0) {
+                g_mx = warp_sum(g_mx); g_my = warp_sum(g_my); g_A = warp_sum(g_A); g_B = warp_sum(g_B); g_C = warp_sum(g_C);
+                g_o = warp_sum(g_o); g_r = warp_sum(g_r); g_g = warp_sum(g_g); g_b = warp_sum(g_b); g_d = warp_sum(g_d);
+                if ((threadIdx.x & 31) == 0) {
+                    atomicAdd(d + 0, g_mx); atomicAdd(d + 1, g_my); atomicAdd(d + 2, g_A); atomicAdd(d + 3, g_B);
+                    atomicAdd(d + 4, g_C); atomicAdd(d + 5, g_o); atomicAdd(d + 6, g_r); atomicAdd(d + 7, g_g);
+                    atomicAdd(d + 8, g_b); atomicAdd(d + 9, g_d);
+                }
+            } else {
+                const int lane = threadIdx.x & 31;
+                const float ra = warp_reduce8_transposed(g_mx, g_my, g_A, g_B, g_C, g_o, g_r, g_g);
+                const float rb = warp_reduce2_transposed(g_b, g_d);
+                if ((lane & 3) == 0) atomicAdd(d + (lane >> 2), ra);
+                if ((lane & 15) == 1) atomicAdd(d + 8 + (lane >> 4), rb);
             }
         }
     }
@@ -190,10 +231,13 @@ int launch_render_fwd(const RenderFwdArgs &a, int variant, bool debug, cudaStrea
 }
 
 int launch_render_bwd(const RenderBwdArgs &a, int variant, bool debug, cudaStream_t stream) {
-    (void)variant;
     const int tiles = a.gx * a.gy;
     if (tiles <= 0) return GSB_OK;
-    GSB_LAUNCH("render_bwd", debug, stream, render_bwd_kernel, tiles, 256, 0, a);
+    if (variant == 0) {
+        GSB_LAUNCH("render_bwd", debug, stream, render_bwd_kernel<0>, tiles, 256, 0, a);
+    } else {
+        GSB_LAUNCH("render_bwd", debug, stream, render_bwd_kernel<1>, tiles, 256, 0, a);
+    }
     return GSB_OK;
 }
 

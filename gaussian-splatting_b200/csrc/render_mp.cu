@@ -1,0 +1,312 @@
+// render_mp.cu -- multi-pixel-per-thread blend kernels (forward K6 and backward K7).
+//
+// ncu on the one-pixel-per-thread kernels (profiles/r1_render_v0.md) shows both are bound by the SM
+// issue rate (issue active 81-87 %, DRAM 1-2 %): the cost is instructions per (pixel, gaussian) pair,
+// not bytes.  These kernels cut that count:
+//   * a thread owns a 2 x QH pixel block, so the shared-memory reads, loop overhead and -- in the
+//     backward pass -- the cross-lane reduction of the ten per-gaussian gradient terms are paid once per
+//     2*QH pixels instead of once per pixel;
+//   * the exponent is evaluated in the log2 domain (conic pre-scaled while staging): one MUFU.EX2;
+//   * the backward pass walks FRONT to back with two scalars of state per pixel (T and the running
+//     dL-weighted front colour F) instead of the ten the back-to-front recursion carries:
+//         dL/dalpha_k = T_k g_k - (S - F_k) / (1 - alpha_k),   g_k = dLdC . c_k + dLdD / z_k,
+//         S = dLdC . C_out + dLdD D_out,   F_k = sum_{j<=k} alpha_j T_j g_j
+//     (algebraically the recursion of oracle/gs_oracle.c; background enters through C_out);
+//   * the geometric gradient terms are accumulated as raw moments of d(power) (sum t dx, t dy, t dx^2,
+//     t dx dy, t dy^2) and turned into mean / conic gradients once per gaussian in preprocess_bwd.
+#include "kernels.cuh"
+
+namespace gsb {
+
+constexpr int MP_R = 128;           // gaussians staged per round
+constexpr float LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ float ex2_approx(const float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// staged record: q0 = {x, y, A', B'}, q1 = {C', opacity, r, g} with A' = -0.5 log2e A, B' = -log2e B, C' = -0.5 log2e C
+__device__ __forceinline__ void stage_scale(float4 &q0, float4 &q1) {
+    q0.z = __fmul_rn(q0.z, -0.5f * LOG2E);
+    q0.w = __fmul_rn(q0.w, -LOG2E);
+    q1.x = __fmul_rn(q1.x, -0.5f * LOG2E);
+}
+
+// log2-domain exponent at offset (dx, dy); pinned operation order: forward and backward must agree bit for bit
+__device__ __forceinline__ float power2_at(const float Axx, const float Cyy, const float Bx, const float dy) {
+    return __fmaf_rn(Bx, dy, __fadd_rn(Axx, Cyy));
+}
+
+template <int QH>
+__global__ void __launch_bounds__(256 / (2 * QH))
+render_fwd_mp_kernel(const RenderFwdArgs a) {
+    constexpr int NT = 256 / (2 * QH);
+    constexpr int NPX = 2 * QH;
+    __shared__ float4 s0[MP_R], s1[MP_R];
+    __shared__ float2 s2[MP_R];
+    const int tile = blockIdx.x;
+    const int ox = (tile % a.gx) * TILE, oy = (tile / a.gx) * TILE;
+    const int t = threadIdx.x;
+    const int px0 = ox + 2 * (t & 7), py0 = oy + QH * (t >> 3);
+    const float fx0 = (float)px0, fy0 = (float)py0;
+    const uint2 range = a.ranges[tile];
+    const int todo = (int)(range.y - range.x);
+
+    float T[NPX], C0[NPX], C1[NPX], C2[NPX], Dp[NPX];
+    uint32_t last[NPX];
+    bool done[NPX];
+#pragma unroll
+    for (int i = 0; i < NPX; ++i) {
+        T[i] = 1.0f; C0[i] = C1[i] = C2[i] = Dp[i] = 0.f; last[i] = 0u;
+        done[i] = !((px0 + (i & 1)) < a.W && (py0 + (i >> 1)) < a.H);
+    }
+
+    for (int base = 0; base < todo; base += MP_R) {
+        bool all_done = true;
+#pragma unroll
+        for (int i = 0; i < NPX; ++i) all_done = all_done && done[i];
+        if (__syncthreads_and(all_done)) break;
+        const int n = min(MP_R, todo - base);
+        for (int k = t; k < n; k += NT) {
+            const uint32_t g = a.point_list[range.x + base + k];
+            const float4 *rec = a.splat + (size_t)g * SPLAT_F4;
+            float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
+            const float4 q2 = __ldg(rec + 2);
+            stage_scale(q0, q1);
+            s0[k] = q0; s1[k] = q1; s2[k] = make_float2(q2.x, q2.y);
+        }
+        __syncthreads();
+        for (int j = 0; j < n; ++j) {
+            const float4 q0 = s0[j];
+            const float4 q1 = s1[j];
+            float dx[2], Axx[2], Bx[2], dy[QH], Cyy[QH];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                dx[c] = q0.x - (fx0 + (float)c);
+                Axx[c] = __fmul_rn(__fmul_rn(q0.z, dx[c]), dx[c]);
+                Bx[c] = __fmul_rn(q0.w, dx[c]);
+            }
+#pragma unroll
+            for (int r = 0; r < QH; ++r) {
+                dy[r] = q0.y - (fy0 + (float)r);
+                Cyy[r] = __fmul_rn(__fmul_rn(q1.x, dy[r]), dy[r]);
+            }
+            float al[NPX];
+            bool valid[NPX];
+            bool any = false;
+#pragma unroll
+            for (int i = 0; i < NPX; ++i) {
+                const float p = power2_at(Axx[i & 1], Cyy[i >> 1], Bx[i & 1], dy[i >> 1]);
+                al[i] = fminf(ALPHA_MAX, __fmul_rn(q1.y, ex2_approx(p)));
+                valid[i] = (p <= 0.0f) && (al[i] >= ALPHA_MIN) && !done[i];
+                any = any || valid[i];
+            }
+            if (!__any_sync(0xffffffffu, any)) continue;
+            const float2 q2 = s2[j];
+            const uint32_t pos = (uint32_t)(base + j + 1);
+#pragma unroll
+            for (int i = 0; i < NPX; ++i) {
+                const float test_T = __fmul_rn(T[i], __fsub_rn(1.0f, al[i]));
+                const bool stop = valid[i] && (test_T < T_STOP);
+                done[i] = done[i] || stop;
+                const bool use = valid[i] && !stop;
+                const float w = use ? __fmul_rn(al[i], T[i]) : 0.0f;
+                C0[i] = __fmaf_rn(q1.z, w, C0[i]);
+                C1[i] = __fmaf_rn(q1.w, w, C1[i]);
+                C2[i] = __fmaf_rn(q2.x, w, C2[i]);
+                Dp[i] = __fmaf_rn(q2.y, w, Dp[i]);
+                T[i] = use ? test_T : T[i];
+                last[i] = use ? pos : last[i];
+            }
+        }
+    }
+    const float bg0 = __ldg(a.bg), bg1 = __ldg(a.bg + 1), bg2 = __ldg(a.bg + 2);
+    const size_t HW = (size_t)a.W * a.H;
+#pragma unroll
+    for (int r = 0; r < QH; ++r) {
+        const int py = py0 + r;
+        if (py >= a.H) continue;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int px = px0 + c;
+            if (px >= a.W) continue;
+            const int i = 2 * r + c;
+            const size_t pid = (size_t)py * a.W + px;
+            a.final_T[pid] = T[i];
+            a.n_contrib[pid] = last[i];
+            a.out_color[pid] = C0[i] + T[i] * bg0;
+            a.out_color[HW + pid] = C1[i] + T[i] * bg1;
+            a.out_color[2 * HW + pid] = C2[i] + T[i] * bg2;
+            a.out_invdepth[pid] = Dp[i];
+        }
+    }
+}
+
+// lane L ends with the warp total of value (L >> 2): 9 shuffles
+__device__ __forceinline__ float reduce8_transposed(const float v0, const float v1, const float v2, const float v3,
+                                                    const float v4, const float v5, const float v6, const float v7) {
+    const int lane = threadIdx.x & 31;
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    const float k0 = (b4 ? v4 : v0) + __shfl_xor_sync(0xffffffffu, b4 ? v0 : v4, 16);
+    const float k1 = (b4 ? v5 : v1) + __shfl_xor_sync(0xffffffffu, b4 ? v1 : v5, 16);
+    const float k2 = (b4 ? v6 : v2) + __shfl_xor_sync(0xffffffffu, b4 ? v2 : v6, 16);
+    const float k3 = (b4 ? v7 : v3) + __shfl_xor_sync(0xffffffffu, b4 ? v3 : v7, 16);
+    const float m0 = (b3 ? k2 : k0) + __shfl_xor_sync(0xffffffffu, b3 ? k0 : k2, 8);
+    const float m1 = (b3 ? k3 : k1) + __shfl_xor_sync(0xffffffffu, b3 ? k1 : k3, 8);
+    float r = (b2 ? m1 : m0) + __shfl_xor_sync(0xffffffffu, b2 ? m0 : m1, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+
+// lanes 0..15 end with the total of v0, lanes 16..31 with the total of v1: 5 shuffles
+__device__ __forceinline__ float reduce2_transposed(const float v0, const float v1) {
+    const bool b4 = threadIdx.x & 16;
+    float r = (b4 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, b4 ? v0 : v1, 16);
+    r += __shfl_xor_sync(0xffffffffu, r, 8);
+    r += __shfl_xor_sync(0xffffffffu, r, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+
+// dacc layout written here (DACC_MOMENTS): 0 sum t dx, 1 sum t dy, 2 sum t dx^2, 3 sum t dx dy, 4 sum t dy^2,
+// 5 sum G dL/dalpha, 6..8 sum w dL/dC, 9 sum w dL/dD, with t = opacity G dL/dalpha = dL/d(power).
+template <int QH>
+__global__ void __launch_bounds__(256 / (2 * QH))
+render_bwd_mp_kernel(const RenderBwdArgs a) {
+    constexpr int NT = 256 / (2 * QH);
+    constexpr int NPX = 2 * QH;
+    __shared__ float4 s0[MP_R], s1[MP_R];
+    __shared__ float2 s2[MP_R];
+    __shared__ uint32_t sid[MP_R];
+    __shared__ uint32_t s_max;
+    const int tile = blockIdx.x;
+    const int ox = (tile % a.gx) * TILE, oy = (tile / a.gx) * TILE;
+    const int t = threadIdx.x;
+    const int px0 = ox + 2 * (t & 7), py0 = oy + QH * (t >> 3);
+    const float fx0 = (float)px0, fy0 = (float)py0;
+    const uint2 range = a.ranges[tile];
+    const size_t HW = (size_t)a.W * a.H;
+
+    float T[NPX], F[NPX], S[NPX], dL0[NPX], dL1[NPX], dL2[NPX], dLd[NPX];
+    uint32_t last[NPX];
+    uint32_t my_max = 0;
+#pragma unroll
+    for (int i = 0; i < NPX; ++i) {
+        const int px = px0 + (i & 1), py = py0 + (i >> 1);
+        T[i] = 1.0f; F[i] = 0.f; S[i] = 0.f; dL0[i] = dL1[i] = dL2[i] = dLd[i] = 0.f; last[i] = 0u;
+        if (px < a.W && py < a.H) {
+            const size_t pid = (size_t)py * a.W + px;
+            last[i] = a.n_contrib[pid];
+            dL0[i] = a.dL_dcolor[pid]; dL1[i] = a.dL_dcolor[HW + pid]; dL2[i] = a.dL_dcolor[2 * HW + pid];
+            dLd[i] = a.dL_dinvdepth ? a.dL_dinvdepth[pid] : 0.f;
+            S[i] = dL0[i] * a.out_color[pid] + dL1[i] * a.out_color[HW + pid] + dL2[i] * a.out_color[2 * HW + pid] +
+                   dLd[i] * a.out_invdepth[pid];
+        }
+        my_max = max(my_max, last[i]);
+    }
+    if (t == 0) s_max = 0;
+    __syncthreads();
+    my_max = __reduce_max_sync(0xffffffffu, my_max);
+    if ((t & 31) == 0) atomicMax(&s_max, my_max);
+    __syncthreads();
+    const int todo = (int)s_max;  // the deepest list position any pixel of the tile blended
+
+    for (int base = 0; base < todo; base += MP_R) {
+        __syncthreads();
+        const int n = min(MP_R, todo - base);
+        for (int k = t; k < n; k += NT) {
+            const uint32_t g = a.point_list[range.x + base + k];
+            const float4 *rec = a.splat + (size_t)g * SPLAT_F4;
+            float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
+            const float4 q2 = __ldg(rec + 2);
+            stage_scale(q0, q1);
+            s0[k] = q0; s1[k] = q1; s2[k] = make_float2(q2.x, q2.y); sid[k] = g;
+        }
+        __syncthreads();
+        for (int j = 0; j < n; ++j) {
+            const float4 q0 = s0[j];
+            const float4 q1 = s1[j];
+            const uint32_t pos = (uint32_t)(base + j + 1);
+            float dx[2], Axx[2], Bx[2], dy[QH], Cyy[QH];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                dx[c] = q0.x - (fx0 + (float)c);
+                Axx[c] = __fmul_rn(__fmul_rn(q0.z, dx[c]), dx[c]);
+                Bx[c] = __fmul_rn(q0.w, dx[c]);
+            }
+#pragma unroll
+            for (int r = 0; r < QH; ++r) {
+                dy[r] = q0.y - (fy0 + (float)r);
+                Cyy[r] = __fmul_rn(__fmul_rn(q1.x, dy[r]), dy[r]);
+            }
+            float al[NPX], G[NPX];
+            bool valid[NPX];
+            bool any = false;
+#pragma unroll
+            for (int i = 0; i < NPX; ++i) {
+                const float p = power2_at(Axx[i & 1], Cyy[i >> 1], Bx[i & 1], dy[i >> 1]);
+                G[i] = ex2_approx(p);
+                al[i] = fminf(ALPHA_MAX, __fmul_rn(q1.y, G[i]));
+                valid[i] = (p <= 0.0f) && (al[i] >= ALPHA_MIN) && (pos <= last[i]);
+                any = any || valid[i];
+            }
+            if (!__any_sync(0xffffffffu, any)) continue;
+            const float2 q2 = s2[j];
+            float m_x = 0.f, m_y = 0.f, m_xx = 0.f, m_xy = 0.f, m_yy = 0.f, g_o = 0.f, g_r = 0.f, g_g = 0.f, g_b = 0.f, g_d = 0.f;
+#pragma unroll
+            for (int i = 0; i < NPX; ++i) {
+                const float ai = valid[i] ? al[i] : 0.0f;
+                const float w = __fmul_rn(ai, T[i]);
+                const float g = dL0[i] * q1.z + dL1[i] * q1.w + dL2[i] * q2.x + dLd[i] * q2.y;
+                F[i] = __fmaf_rn(w, g, F[i]);
+                g_r = __fmaf_rn(w, dL0[i], g_r); g_g = __fmaf_rn(w, dL1[i], g_g);
+                g_b = __fmaf_rn(w, dL2[i], g_b); g_d = __fmaf_rn(w, dLd[i], g_d);
+                const float om = __fsub_rn(1.0f, ai);
+                float dLda = T[i] * g - (S[i] - F[i]) * __frcp_rn(om);
+                T[i] = __fmul_rn(T[i], om);
+                dLda = valid[i] ? dLda : 0.0f;
+                g_o = __fmaf_rn(G[i], dLda, g_o);
+                const float tt = q1.y * G[i] * dLda;
+                const float u = tt * dx[i & 1], v = tt * dy[i >> 1];
+                m_x += u; m_y += v;
+                m_xx = __fmaf_rn(u, dx[i & 1], m_xx);
+                m_xy = __fmaf_rn(u, dy[i >> 1], m_xy);
+                m_yy = __fmaf_rn(v, dy[i >> 1], m_yy);
+            }
+            const int lane = t & 31;
+            const float ra = reduce8_transposed(m_x, m_y, m_xx, m_xy, m_yy, g_o, g_r, g_g);
+            const float rb = reduce2_transposed(g_b, g_d);
+            float *d = a.dacc + (size_t)sid[j] * DACC_STRIDE;
+            if ((lane & 3) == 0) atomicAdd(d + (lane >> 2), ra);
+            if ((lane & 15) == 1) atomicAdd(d + 8 + (lane >> 4), rb);
+        }
+    }
+}
+
+int launch_render_fwd_mp(const RenderFwdArgs &a, int qh, bool debug, cudaStream_t stream) {
+    const int tiles = a.gx * a.gy;
+    if (tiles <= 0) return GSB_OK;
+    if (qh == 4) {
+        GSB_LAUNCH("render_fwd", debug, stream, render_fwd_mp_kernel<4>, tiles, 32, 0, a);
+    } else {
+        GSB_LAUNCH("render_fwd", debug, stream, render_fwd_mp_kernel<2>, tiles, 64, 0, a);
+    }
+    return GSB_OK;
+}
+
+int launch_render_bwd_mp(const RenderBwdArgs &a, int qh, bool debug, cudaStream_t stream) {
+    const int tiles = a.gx * a.gy;
+    if (tiles <= 0) return GSB_OK;
+    if (qh == 4) {
+        GSB_LAUNCH("render_bwd", debug, stream, render_bwd_mp_kernel<4>, tiles, 32, 0, a);
+    } else {
+        GSB_LAUNCH("render_bwd", debug, stream, render_bwd_mp_kernel<2>, tiles, 64, 0, a);
+    }
+    return GSB_OK;
+}
+
+}  // namespace gsb

@@ -65,8 +65,8 @@ def _load():
     lib.gsb_forward.argtypes = [POINTER(_Settings), POINTER(_Inputs), c_void_p, c_void_p, c_void_p, _ALLOC_FN,
                                 c_void_p, POINTER(_State), c_void_p]
     lib.gsb_backward.restype = c_int32
-    lib.gsb_backward.argtypes = [POINTER(_Settings), POINTER(_Inputs), POINTER(_State), c_void_p, c_void_p,
-                                 POINTER(_Grads), c_int32, _ALLOC_FN, c_void_p, c_void_p]
+    lib.gsb_backward.argtypes = [POINTER(_Settings), POINTER(_Inputs), POINTER(_State), c_void_p, c_void_p, c_void_p,
+                                 c_void_p, POINTER(_Grads), c_int32, _ALLOC_FN, c_void_p, c_void_p]
     lib.gsb_mark_visible.restype = c_int32
     lib.gsb_mark_visible.argtypes = [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.gsb_sort_pairs.restype = c_int32
@@ -79,8 +79,8 @@ def _load():
     lib.gsb_kernel_time.argtypes = [c_char_p, POINTER(ctypes.c_double), POINTER(c_int64), c_int32]
     lib.gsb_set_option.restype = c_int32
     lib.gsb_set_option.argtypes = [c_char_p, c_int32]
-    if lib.gsb_abi_version() != 1:
-        raise ImportError(f"{_LIB_PATH}: ABI version {lib.gsb_abi_version()} != 1")
+    if lib.gsb_abi_version() != 2:
+        raise ImportError(f"{_LIB_PATH}: ABI version {lib.gsb_abi_version()} != 2")
     return lib
 
 
@@ -235,7 +235,7 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
 
 
 def _backward_impl(pack, rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                   grad_color, grad_invdepth, grads: dict, accumulate: bool):
+                   out_color, out_invdepth, grad_color, grad_invdepth, grads: dict, accumulate: bool):
     dev = means3D.device
     P = int(means3D.shape[0])
     with torch.cuda.device(dev):
@@ -250,8 +250,9 @@ def _backward_impl(pack, rs, means3D, sh, colors_precomp, opacities, scales, rot
         g.dL_dcov3D = _ptr(grads.get("cov3D_precomp"))
         arena = _Arena(dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = _C.gsb_backward(byref(cs), byref(ci), byref(pack["state"]), grad_color.data_ptr(), _ptr(grad_invdepth),
-                             byref(g), int(bool(accumulate)), arena.cb, None, stream)
+        rc = _C.gsb_backward(byref(cs), byref(ci), byref(pack["state"]), out_color.data_ptr(), out_invdepth.data_ptr(),
+                             grad_color.data_ptr(), _ptr(grad_invdepth), byref(g), int(bool(accumulate)), arena.cb,
+                             None, stream)
         _check(rc, arena)
 
 
@@ -280,15 +281,16 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.pack = pack
         ctx.shapes = dict(means2D=None if means2D is None else tuple(means2D.shape), opacities=tuple(opacities.shape),
                           sh=None if sh is None else tuple(sh.shape))
-        ctx.save_for_backward(*[a if a is not None else torch.empty(0) for a in args])
+        ctx.save_for_backward(*[a if a is not None else torch.empty(0) for a in args], color, invdepth)
         ctx.mark_non_differentiable(radii)
         return color, radii, invdepth
 
     @staticmethod
     def backward(ctx, grad_out_color, _grad_radii, grad_out_depth):
         rs = ctx.raster_settings
-        saved = [t if t.numel() > 0 else None for t in ctx.saved_tensors]
+        saved = [t if t.numel() > 0 else None for t in ctx.saved_tensors[:7]]
         means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp = saved
+        out_color, out_invdepth = ctx.saved_tensors[7], ctx.saved_tensors[8]
         if means3D is None:
             means3D = ctx.saved_tensors[0]
         dev = means3D.device
@@ -310,7 +312,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         gd = _f32c(grad_out_depth)
         try:
             _backward_impl(ctx.pack, rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                           gc, gd, grads, accumulate=False)
+                           out_color, out_invdepth, gc, gd, grads, accumulate=False)
         except Exception:
             if rs.debug:
                 torch.save([t.detach().cpu() for t in ctx.saved_tensors] + [gc.cpu()], "snapshot_bw.dump")

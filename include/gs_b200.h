@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define GSB_ABI_VERSION 1
+#define GSB_ABI_VERSION 2
 
 /* error codes (0 = ok); gsb_last_error() holds the message of the calling thread's last failure */
 #define GSB_OK 0
@@ -123,11 +123,13 @@ int32_t gsb_forward(const GsbSettings *settings, const GsbInputs *in, float *out
                     int32_t *out_radii, float *out_invdepth, gsb_alloc_fn alloc, void *alloc_ctx,
                     GsbState *state_out, void *cuda_stream);
 
-/* Backward.  dL_dinvdepth may be NULL.  accumulate != 0 adds into the gradient tensors
- * instead of overwriting them (view-batch path: one buffer summed over views). */
+/* Backward.  out_color / out_invdepth are the forward call's outputs (the front-to-back backward blend
+ * reads them); dL_dinvdepth may be NULL.  accumulate != 0 adds into the gradient tensors instead of
+ * overwriting them (view-batch path: one buffer summed over views). */
 int32_t gsb_backward(const GsbSettings *settings, const GsbInputs *in, const GsbState *state,
-                     const float *dL_dcolor, const float *dL_dinvdepth, const GsbGrads *grads,
-                     int32_t accumulate, gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream);
+                     const float *out_color, const float *out_invdepth, const float *dL_dcolor,
+                     const float *dL_dinvdepth, const GsbGrads *grads, int32_t accumulate,
+                     gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream);
 
 /* Frustum test only (GaussianRasterizer.markVisible): present[i] = 1 if view-space z > 0.2 */
 int32_t gsb_mark_visible(int32_t P, const float *means3D, const float *viewmatrix,

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in decl:
         assert hasattr(lib, name), f"{name} declared in include/ but not exported"
     lib.gsb_abi_version.restype = ctypes.c_int32
-    assert lib.gsb_abi_version() == 1
+    assert lib.gsb_abi_version() == 2
 
 
 def test_struct_sizes_match_header():

@@ -117,7 +117,7 @@ def test_cull_on_off_identical_image():
     assert np.array_equal(a["invdepth"], b["invdepth"])
     for k, v in a["grads"].items():
         if v is not None:
-            assert np.abs(v - b["grads"][k]).max() <= 1e-5 * (np.abs(v).max() + 1e-20), k
+            assert np.abs(v - b["grads"][k]).max() <= 1e-4 * (np.abs(v).max() + 1e-20), k
 
 
 def test_mark_visible():
