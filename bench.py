@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--sh-degree", type=int, default=3)
+    ap.add_argument("--api", default="views", choices=["views", "render"],
+                    help="views: fused view-batch path render_views_backward(); render: per-view render() + autograd")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
     return ap.parse_args()
@@ -205,6 +207,7 @@ def workload_config(a, world):
             "gaussians": a.gaussians, "image": [a.width, a.height], "sh_degree": a.sh_degree,
             "views_per_rank": a.views_per_rank, "views_total": a.views_per_rank * world,
             "parallelism": f"view-parallel x{world}, gaussians replicated, one all-reduce of 59 floats/gaussian",
+            "api": a.api,
             "l2": "inputs_exceed_l2 (236 MB parameters + 8 distinct views per step; no explicit flush)",
             "scene": f"xyz~U([-1,1]^3), log-scale~N({LOG_SCALE_MEAN},0.5), opacity=sigmoid(U(-2,4)), cameras on sphere r=3, seed 0"}
 
@@ -246,7 +249,7 @@ def main():
     import torch.distributed as dist
     from oracle import torch_oracle as TO   # scene + camera generators (shared with the tests); no compute
     import diff_gaussian_rasterization as dgr
-    from gaussian_renderer import GradientBucket, render
+    from gaussian_renderer import GradientBucket, render, render_views_backward
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the rasterizer has no CPU path (use --impl reference for the CPU port)")
@@ -273,19 +276,34 @@ def main():
     gt_dev = [g.to(dev) for g in gt_host]
     mpix_step = V * world * H * W / 1e6
 
+    class HostCams:
+        """e2e leg: a camera's tensors are uploaded from pinned host memory when the view comes up."""
+
+        def __iter__(self):
+            for cam in cams:
+                cam.upload(dev)
+                yield cam
+
     def step(host_inputs: bool):
         bucket.zero_()
-        total = torch.zeros((), device=dev)
-        for i, cam in enumerate(cams):
-            if host_inputs:
-                cam.upload(dev)
-                gt = gt_host[i].to(dev, non_blocking=True)
-            else:
-                gt = gt_dev[i]
-            pkg = render(cam, pc, pipe, bg)
-            loss = (pkg["render"] - gt).abs().mean()
-            loss.backward()
-            total += loss.detach()
+        if a.api == "views":
+            def loss_fn(img, _invdepth, i):
+                gt = gt_host[i].to(dev, non_blocking=True) if host_inputs else gt_dev[i]
+                return (img - gt).abs().mean()
+            out = render_views_backward(HostCams() if host_inputs else cams, pc, pipe, bg, loss_fn)
+            total = out["losses"].sum()
+        else:
+            total = torch.zeros((), device=dev)
+            for i, cam in enumerate(cams):
+                if host_inputs:
+                    cam.upload(dev)
+                    gt = gt_host[i].to(dev, non_blocking=True)
+                else:
+                    gt = gt_dev[i]
+                pkg = render(cam, pc, pipe, bg)
+                loss = (pkg["render"] - gt).abs().mean()
+                loss.backward()
+                total += loss.detach()
         bucket.all_reduce()
         if host_inputs:
             return float(total.item())   # device -> host read of the step's result

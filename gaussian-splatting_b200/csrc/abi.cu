@@ -68,6 +68,14 @@ static unsigned long long *pinned_slot() {
     return slots[dev];
 }
 
+static cudaEvent_t readback_event() {
+    static cudaEvent_t evs[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!evs[dev] && cudaEventCreateWithFlags(&evs[dev], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    return evs[dev];
+}
+
 static int bits_for(uint32_t max_value) {
     int b = 1;
     while (b < 32 && (max_value >> b) != 0u) ++b;
@@ -181,7 +189,8 @@ int32_t gsb_kernel_time(const char *name, double *total_ms, int64_t *launches, i
 }
 
 int32_t gsb_forward(const GsbSettings *s, const GsbInputs *in, float *out_color, int32_t *out_radii,
-                    float *out_invdepth, gsb_alloc_fn alloc, void *alloc_ctx, GsbState *st, void *cuda_stream) {
+                    float *out_invdepth, int64_t capacity_hint, gsb_alloc_fn alloc, void *alloc_ctx, GsbState *st,
+                    void *cuda_stream) {
     if (!s || !in || !out_color || (!out_radii && in->P > 0) || !out_invdepth || !alloc || !st) {
         set_error("gsb_forward: NULL argument");
         return GSB_ERR_ARGUMENT;
@@ -195,6 +204,7 @@ int32_t gsb_forward(const GsbSettings *s, const GsbInputs *in, float *out_color,
     if (rc) return rc;
     const int P = in->P;
     const int num_tiles = cam.gx * cam.gy;
+    const int tile_bits = bits_for((uint32_t)num_tiles);
     const size_t npix = (size_t)cam.W * cam.H;
     memset(st, 0, sizeof(*st));
     st->P = P; st->num_tiles = num_tiles; st->num_visible = -1;
@@ -206,20 +216,66 @@ int32_t gsb_forward(const GsbSettings *s, const GsbInputs *in, float *out_color,
     if (!st->geom) return GSB_ERR_ALLOC;
     float4 *splat = static_cast<float4 *>(st->geom);
 
-    Carver c0(nullptr);
-    auto carve0 = [&](Carver &c, uint32_t *&key, uint32_t *&idx, uint32_t *&key_alt, uint32_t *&idx_alt, uint32_t *&tiles,
-                      uint2 *&rect, uint32_t *&offsets, uint32_t *&partials, unsigned long long *&total, char *&sortscr) {
+    // ---- per-pixel state (allocated up front so that nothing host-side sits between binning and blending) ----
+    ImageView iv;
+    st->image_bytes = carve_image(nullptr, npix, iv);
+    st->image = do_alloc(alloc, alloc_ctx, GSB_BUF_IMAGE, st->image_bytes);
+    if (!st->image) return GSB_ERR_ALLOC;
+    carve_image(st->image, npix, iv);
+
+    uint32_t *key, *idx, *key_alt, *idx_alt, *tiles, *offsets, *partials; uint2 *rect; unsigned long long *total; char *sortscr;
+    auto carve0 = [&](Carver &c) {
         key = c.take<uint32_t>(Pn); idx = c.take<uint32_t>(Pn); key_alt = c.take<uint32_t>(Pn); idx_alt = c.take<uint32_t>(Pn);
         tiles = c.take<uint32_t>(Pn); rect = c.take<uint2>(Pn); offsets = c.take<uint32_t>(Pn);
         partials = c.take<uint32_t>(scan_partials_count(P)); total = c.take<unsigned long long>(4);
         sortscr = c.take<char>(sort_scratch_bytes(P));
     };
-    uint32_t *key, *idx, *key_alt, *idx_alt, *tiles, *offsets, *partials; uint2 *rect; unsigned long long *total; char *sortscr;
-    carve0(c0, key, idx, key_alt, idx_alt, tiles, rect, offsets, partials, total, sortscr);
+    Carver c0(nullptr);
+    carve0(c0);
     void *scr0 = do_alloc(alloc, alloc_ctx, GSB_BUF_SCRATCH0, c0.bytes());
     if (!scr0) return GSB_ERR_ALLOC;
     Carver c0r(scr0);
-    carve0(c0r, key, idx, key_alt, idx_alt, tiles, rect, offsets, partials, total, sortscr);
+    carve0(c0r);
+
+    BinArgs ba;
+    ba.P = P; ba.num_tiles = num_tiles; ba.gx = cam.gx; ba.order = idx; ba.tiles = tiles; ba.rect = rect; ba.splat = splat;
+    ba.offsets = offsets; ba.partials = partials; ba.total = total;
+
+    // binning + blend for an instance capacity `cap`; the true count is read by the kernels from *n_dev when given
+    BinningView bv;
+    auto bin_and_blend = [&](int64_t cap, const unsigned long long *n_dev) -> int {
+        st->binning_capacity = cap;
+        st->binning_bytes = carve_binning(nullptr, cap, num_tiles, bv);
+        st->binning = do_alloc(alloc, alloc_ctx, GSB_BUF_BINNING, st->binning_bytes);
+        if (!st->binning) return GSB_ERR_ALLOC;
+        carve_binning(st->binning, cap, num_tiles, bv);
+        int r;
+        if (cap > 0 && P > 0) {
+            const size_t Dn = (size_t)cap;
+            Carver c1(nullptr);
+            c1.take<uint32_t>(Dn); c1.take<uint32_t>(Dn); c1.take<uint32_t>(Dn); c1.take<char>(sort_scratch_bytes(cap));
+            void *scr1 = do_alloc(alloc, alloc_ctx, GSB_BUF_SCRATCH1, c1.bytes());
+            if (!scr1) return GSB_ERR_ALLOC;
+            Carver c1r(scr1);
+            uint32_t *inst_tile = c1r.take<uint32_t>(Dn), *inst_tile_alt = c1r.take<uint32_t>(Dn), *inst_gauss_alt = c1r.take<uint32_t>(Dn);
+            char *sortscr1 = c1r.take<char>(sort_scratch_bytes(cap));
+            r = launch_emit(ba, inst_tile, bv.point_list, cap, debug, stream);
+            if (r) return r;
+            r = sort_pairs(inst_tile, bv.point_list, inst_tile_alt, inst_gauss_alt, cap, n_dev, 0, tile_bits, sortscr1, debug, stream);
+            if (r) return r;
+            r = launch_tile_ranges(inst_tile, cap, n_dev, num_tiles, bv.ranges, debug, stream);
+            if (r) return r;
+        } else {
+            r = launch_tile_ranges(nullptr, 0, nullptr, num_tiles, bv.ranges, debug, stream);
+            if (r) return r;
+        }
+        RenderFwdArgs ra;
+        ra.W = cam.W; ra.H = cam.H; ra.gx = cam.gx; ra.gy = cam.gy; ra.ranges = bv.ranges; ra.point_list = bv.point_list;
+        ra.splat = splat; ra.bg = s->bg; ra.out_color = out_color; ra.out_invdepth = out_invdepth; ra.final_T = iv.final_T;
+        ra.n_contrib = iv.n_contrib;
+        return opt_fwd_variant >= 2 ? launch_render_fwd_mp(ra, opt_fwd_variant == 3 ? 4 : 2, debug, stream)
+                                    : launch_render_fwd(ra, opt_fwd_variant, debug, stream);
+    };
 
     int64_t D = 0;
     if (P > 0) {
@@ -231,74 +287,40 @@ int32_t gsb_forward(const GsbSettings *s, const GsbInputs *in, float *out_color,
         rc = launch_preprocess_fwd(cam, pa, debug, stream);
         if (rc) return rc;
         // gaussians by depth (culled ones carry key 0xffffffff and sort to the end)
-        rc = sort_pairs(key, idx, key_alt, idx_alt, P, 0, 32, sortscr, debug, stream);
+        rc = sort_pairs(key, idx, key_alt, idx_alt, P, nullptr, 0, 32, sortscr, debug, stream);
         if (rc) return rc;
-        BinArgs ba;
-        ba.P = P; ba.num_tiles = num_tiles; ba.gx = cam.gx; ba.order = idx; ba.tiles = tiles; ba.rect = rect; ba.splat = splat;
-        ba.offsets = offsets; ba.partials = partials; ba.total = total;
         rc = launch_tile_scan(ba, debug, stream);
         if (rc) return rc;
-        // the one host synchronisation of the forward pass: the instance count sizes the next buffers
+        // The instance count D sizes the binning buffers, so it has to reach the host: ONE read-back per forward.
         unsigned long long *h = pinned_slot();
-        if (!h) { set_error("pinned read-back slot unavailable"); return GSB_ERR_CUDA; }
+        cudaEvent_t ev = readback_event();
+        if (!h || !ev) { set_error("pinned read-back slot unavailable"); return GSB_ERR_CUDA; }
         GSB_CUDA(cudaMemcpyAsync(h, total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-        GSB_CUDA(cudaStreamSynchronize(stream));
+        GSB_CUDA(cudaEventRecord(ev, stream));
+        bool blended = false;
+        if (capacity_hint > 0 && capacity_hint < (1ll << 31)) {
+            // Speculate: with the caller's capacity estimate (e.g. the previous frame's count plus slack) the rest of
+            // the forward pass is enqueued BEFORE waiting for the count, so the GPU keeps running while the host waits.
+            rc = bin_and_blend(capacity_hint, total);
+            if (rc) return rc;
+            blended = true;
+        }
+        GSB_CUDA(cudaEventSynchronize(ev));
         if (*h >= (1ull << 31)) {
             set_error("instance count %llu exceeds 2^31", *h);
             return GSB_ERR_OVERFLOW;
         }
         D = (int64_t)*h;
-
-        BinningView bv;
-        st->binning_bytes = carve_binning(nullptr, D, num_tiles, bv);
-        st->binning = do_alloc(alloc, alloc_ctx, GSB_BUF_BINNING, st->binning_bytes);
-        if (!st->binning) return GSB_ERR_ALLOC;
-        carve_binning(st->binning, D, num_tiles, bv);
-
-        if (D > 0) {
-            const size_t Dn = (size_t)D;
-            Carver c1(nullptr);
-            c1.take<uint32_t>(Dn); c1.take<uint32_t>(Dn); c1.take<uint32_t>(Dn); c1.take<char>(sort_scratch_bytes(D));
-            void *scr1 = do_alloc(alloc, alloc_ctx, GSB_BUF_SCRATCH1, c1.bytes());
-            if (!scr1) return GSB_ERR_ALLOC;
-            Carver c1r(scr1);
-            uint32_t *inst_tile = c1r.take<uint32_t>(Dn), *inst_tile_alt = c1r.take<uint32_t>(Dn), *inst_gauss_alt = c1r.take<uint32_t>(Dn);
-            char *sortscr1 = c1r.take<char>(sort_scratch_bytes(D));
-            rc = launch_emit(ba, inst_tile, bv.point_list, debug, stream);
-            if (rc) return rc;
-            rc = sort_pairs(inst_tile, bv.point_list, inst_tile_alt, inst_gauss_alt, D, 0, bits_for((uint32_t)num_tiles), sortscr1, debug, stream);
-            if (rc) return rc;
-            rc = launch_tile_ranges(inst_tile, D, num_tiles, bv.ranges, debug, stream);
-            if (rc) return rc;
-        } else {
-            rc = launch_tile_ranges(nullptr, 0, num_tiles, bv.ranges, debug, stream);
+        if (!blended || D > capacity_hint) {   // exact path, also the (rare) repair when the estimate was too small
+            rc = bin_and_blend(D, nullptr);
             if (rc) return rc;
         }
     } else {
-        BinningView bv;
-        st->binning_bytes = carve_binning(nullptr, 0, num_tiles, bv);
-        st->binning = do_alloc(alloc, alloc_ctx, GSB_BUF_BINNING, st->binning_bytes);
-        if (!st->binning) return GSB_ERR_ALLOC;
-        carve_binning(st->binning, 0, num_tiles, bv);
-        rc = launch_tile_ranges(nullptr, 0, num_tiles, bv.ranges, debug, stream);
+        rc = bin_and_blend(0, nullptr);
         if (rc) return rc;
     }
     st->num_rendered = D;
-
-    // ---- per-pixel state + blend ----
-    ImageView iv;
-    st->image_bytes = carve_image(nullptr, npix, iv);
-    st->image = do_alloc(alloc, alloc_ctx, GSB_BUF_IMAGE, st->image_bytes);
-    if (!st->image) return GSB_ERR_ALLOC;
-    carve_image(st->image, npix, iv);
-    BinningView bv;
-    carve_binning(st->binning, D, num_tiles, bv);
-    RenderFwdArgs ra;
-    ra.W = cam.W; ra.H = cam.H; ra.gx = cam.gx; ra.gy = cam.gy; ra.ranges = bv.ranges; ra.point_list = bv.point_list;
-    ra.splat = splat; ra.bg = s->bg; ra.out_color = out_color; ra.out_invdepth = out_invdepth; ra.final_T = iv.final_T;
-    ra.n_contrib = iv.n_contrib;
-    return opt_fwd_variant >= 2 ? launch_render_fwd_mp(ra, opt_fwd_variant == 3 ? 4 : 2, debug, stream)
-                                : launch_render_fwd(ra, opt_fwd_variant, debug, stream);
+    return GSB_OK;
 }
 
 int32_t gsb_backward(const GsbSettings *s, const GsbInputs *in, const GsbState *st, const float *out_color,
@@ -331,7 +353,7 @@ int32_t gsb_backward(const GsbSettings *s, const GsbInputs *in, const GsbState *
     ImageView iv;
     carve_image(st->image, npix, iv);
     BinningView bv;
-    carve_binning(st->binning, st->num_rendered, st->num_tiles, bv);
+    carve_binning(st->binning, st->binning_capacity, st->num_tiles, bv);
     const float4 *splat = static_cast<const float4 *>(st->geom);
 
     if (st->num_rendered > 0) {
@@ -374,7 +396,7 @@ int32_t gsb_sort_pairs(uint32_t *keys, uint32_t *vals, int64_t n, int32_t begin_
     Carver cr(scr);
     uint32_t *ka = cr.take<uint32_t>((size_t)n), *va = cr.take<uint32_t>((size_t)n);
     char *ss = cr.take<char>(sort_scratch_bytes(n));
-    return sort_pairs(keys, vals, ka, va, n, begin_bit, end_bit, ss, false, static_cast<cudaStream_t>(cuda_stream));
+    return sort_pairs(keys, vals, ka, va, n, nullptr, begin_bit, end_bit, ss, false, static_cast<cudaStream_t>(cuda_stream));
 }
 
 }  // extern "C"

@@ -107,13 +107,16 @@ int launch_tile_scan(const BinArgs &a, bool debug, cudaStream_t stream) {
 
 // K3: one thread per depth rank; writes (tile id, gaussian id) for every tile the gaussian's cull ellipse meets.
 __global__ void __launch_bounds__(256)
-emit_kernel(const BinArgs a, uint32_t *__restrict__ inst_tile, uint32_t *__restrict__ inst_gauss) {
+emit_kernel(const BinArgs a, uint32_t *__restrict__ inst_tile, uint32_t *__restrict__ inst_gauss, const uint32_t cap) {
     const int r = blockIdx.x * 256 + threadIdx.x;
     if (r >= a.P) return;
     const uint32_t g = a.order[r];
-    const uint32_t n = a.tiles[g];
+    uint32_t n = a.tiles[g];
     if (n == 0) return;
     const uint32_t start = a.offsets[r];
+    // speculative capacity (abi.cu): never write past it; the host re-runs binning when the count did not fit
+    if (start >= cap) return;
+    n = min(n, cap - start);
     const float4 q0 = a.splat[(size_t)g * SPLAT_F4], q1 = a.splat[(size_t)g * SPLAT_F4 + 1], q2 = a.splat[(size_t)g * SPLAT_F4 + 2];
     const uint2 rc = a.rect[g];
     CullGeom cg;
@@ -146,14 +149,16 @@ emit_kernel(const BinArgs a, uint32_t *__restrict__ inst_tile, uint32_t *__restr
     }
 }
 
-int launch_emit(const BinArgs &a, uint32_t *inst_tile, uint32_t *inst_gauss, bool debug, cudaStream_t stream) {
-    GSB_LAUNCH("emit", debug, stream, emit_kernel, (int)ceil_div(a.P, 256), 256, 0, a, inst_tile, inst_gauss);
+int launch_emit(const BinArgs &a, uint32_t *inst_tile, uint32_t *inst_gauss, int64_t cap, bool debug, cudaStream_t stream) {
+    GSB_LAUNCH("emit", debug, stream, emit_kernel, (int)ceil_div(a.P, 256), 256, 0, a, inst_tile, inst_gauss, (uint32_t)cap);
     return GSB_OK;
 }
 
 // K5: ranges[t] = [first, last+1) of tile t in the tile-sorted instance list (ranges pre-zeroed)
 __global__ void __launch_bounds__(256)
-tile_ranges_kernel(const uint32_t *__restrict__ sorted_tiles, const int64_t D, const int num_tiles, uint2 *ranges) {
+tile_ranges_kernel(const uint32_t *__restrict__ sorted_tiles, int64_t D, const unsigned long long *__restrict__ n_dev,
+                   const int num_tiles, uint2 *ranges) {
+    if (n_dev) D = min((int64_t)*n_dev, D);
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= D) return;
     const uint32_t t = sorted_tiles[i];
@@ -162,11 +167,11 @@ tile_ranges_kernel(const uint32_t *__restrict__ sorted_tiles, const int64_t D, c
     if (i == D - 1 || sorted_tiles[i + 1] != t) ranges[t].y = (uint32_t)(i + 1);
 }
 
-int launch_tile_ranges(const uint32_t *sorted_tiles, int64_t D, int num_tiles, uint2 *ranges, bool debug,
-                       cudaStream_t stream) {
+int launch_tile_ranges(const uint32_t *sorted_tiles, int64_t D, const unsigned long long *n_dev, int num_tiles,
+                       uint2 *ranges, bool debug, cudaStream_t stream) {
     GSB_CUDA(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), stream));
     if (D <= 0) return GSB_OK;
-    GSB_LAUNCH("tile_ranges", debug, stream, tile_ranges_kernel, (int)ceil_div(D, 256), 256, 0, sorted_tiles, D, num_tiles, ranges);
+    GSB_LAUNCH("tile_ranges", debug, stream, tile_ranges_kernel, (int)ceil_div(D, 256), 256, 0, sorted_tiles, D, n_dev, num_tiles, ranges);
     return GSB_OK;
 }
 

@@ -87,8 +87,10 @@ struct Carver {
 size_t sort_scratch_bytes(int64_t n);
 // Stable LSD sort of pairs on bits [begin_bit, end_bit).  Result is left in (keys, vals);
 // (keys_alt, vals_alt) are ping-pong buffers of the same size; scratch >= sort_scratch_bytes(n).
+// n sizes the launch; if n_dev != NULL the kernels sort min(*n_dev, n) pairs (count known only on the device).
 int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n,
-               int begin_bit, int end_bit, void *scratch, bool debug, cudaStream_t stream);
+               const unsigned long long *n_dev, int begin_bit, int end_bit, void *scratch, bool debug,
+               cudaStream_t stream);
 size_t scan_scratch_bytes(int64_t n);
 
 }  // namespace gsb

@@ -71,9 +71,9 @@ int launch_mark_visible(int P, const float *means, const float *view, uint8_t *p
 
 size_t scan_partials_count(int P);
 int launch_tile_scan(const BinArgs &a, bool debug, cudaStream_t stream);
-int launch_emit(const BinArgs &a, uint32_t *inst_tile, uint32_t *inst_gauss, bool debug, cudaStream_t stream);
-int launch_tile_ranges(const uint32_t *sorted_tiles, int64_t D, int num_tiles, uint2 *ranges, bool debug,
-                       cudaStream_t stream);
+int launch_emit(const BinArgs &a, uint32_t *inst_tile, uint32_t *inst_gauss, int64_t cap, bool debug, cudaStream_t stream);
+int launch_tile_ranges(const uint32_t *sorted_tiles, int64_t D, const unsigned long long *n_dev, int num_tiles,
+                       uint2 *ranges, bool debug, cudaStream_t stream);
 
 int launch_render_fwd(const RenderFwdArgs &a, int variant, bool debug, cudaStream_t stream);
 int launch_render_bwd(const RenderBwdArgs &a, int variant, bool debug, cudaStream_t stream);

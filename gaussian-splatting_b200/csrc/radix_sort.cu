@@ -22,9 +22,10 @@ constexpr int SORT_IPT = 16;
 constexpr int SORT_KPB = SORT_THREADS * SORT_IPT;  // keys per block
 
 __global__ void __launch_bounds__(SORT_THREADS)
-sort_hist_kernel(const uint32_t *__restrict__ keys, uint32_t *__restrict__ table, int64_t n, int nblocks,
-                 int shift, uint32_t mask) {
+sort_hist_kernel(const uint32_t *__restrict__ keys, uint32_t *__restrict__ table, int64_t n,
+                 const unsigned long long *__restrict__ n_dev, int nblocks, int shift, uint32_t mask) {
     __shared__ uint32_t hist[RADIX];
+    if (n_dev) n = min((int64_t)*n_dev, n);
     const int tid = threadIdx.x;
     hist[tid] = 0;
     __syncthreads();
@@ -78,8 +79,9 @@ __global__ void __launch_bounds__(SORT_THREADS)
 sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                     const uint32_t *__restrict__ table, const uint32_t *__restrict__ totals, int64_t n,
-                    int nblocks, int shift, uint32_t mask) {
+                    const unsigned long long *__restrict__ n_dev, int nblocks, int shift, uint32_t mask) {
     __shared__ uint32_t warp_cnt[SORT_THREADS / 32][RADIX];
+    if (n_dev) n = min((int64_t)*n_dev, n);
     __shared__ uint32_t warp_sums[8];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 #pragma unroll
@@ -151,7 +153,8 @@ size_t sort_scratch_bytes(int64_t n) {
 }
 
 int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n,
-               int begin_bit, int end_bit, void *scratch, bool debug, cudaStream_t stream) {
+               const unsigned long long *n_dev, int begin_bit, int end_bit, void *scratch, bool debug,
+               cudaStream_t stream) {
     if (n <= 0 || end_bit <= begin_bit) return GSB_OK;
     if (n >= (int64_t)1 << 32) {
         set_error("sort_pairs: n=%lld does not fit 32-bit positions", (long long)n);
@@ -166,11 +169,11 @@ int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *val
     for (int bit = begin_bit; bit < end_bit; bit += RADIX_BITS) {
         const int bits = (end_bit - bit) < RADIX_BITS ? (end_bit - bit) : RADIX_BITS;
         const uint32_t mask = (1u << bits) - 1u;
-        GSB_LAUNCH("sort_hist", debug, stream, sort_hist_kernel, nblocks, SORT_THREADS, 0, kin, table, n, nblocks,
-                   bit, mask);
+        GSB_LAUNCH("sort_hist", debug, stream, sort_hist_kernel, nblocks, SORT_THREADS, 0, kin, table, n, n_dev,
+                   nblocks, bit, mask);
         GSB_LAUNCH("sort_rowscan", debug, stream, sort_rowscan_kernel, RADIX, 256, 0, table, totals, nblocks);
         GSB_LAUNCH("sort_scatter", debug, stream, sort_scatter_kernel, nblocks, SORT_THREADS, 0, kin, vin, kout,
-                   vout, table, totals, n, nblocks, bit, mask);
+                   vout, table, totals, n, n_dev, nblocks, bit, mask);
         uint32_t *t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
         ++passes;

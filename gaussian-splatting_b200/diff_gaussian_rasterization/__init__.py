@@ -41,7 +41,7 @@ class _Inputs(Structure):
 
 class _State(Structure):
     _fields_ = [("P", c_int32), ("num_tiles", c_int32), ("num_rendered", c_int64), ("num_visible", c_int64),
-                ("geom", c_void_p), ("geom_bytes", c_size_t), ("binning", c_void_p), ("binning_bytes", c_size_t),
+                ("binning_capacity", c_int64), ("geom", c_void_p), ("geom_bytes", c_size_t), ("binning", c_void_p), ("binning_bytes", c_size_t),
                 ("image", c_void_p), ("image_bytes", c_size_t)]
 
 
@@ -62,7 +62,7 @@ def _load():
             f"(or `make -C gaussian-splatting_b200/csrc`).  There is no CPU fallback.")
     lib = ctypes.CDLL(_LIB_PATH)
     lib.gsb_forward.restype = c_int32
-    lib.gsb_forward.argtypes = [POINTER(_Settings), POINTER(_Inputs), c_void_p, c_void_p, c_void_p, _ALLOC_FN,
+    lib.gsb_forward.argtypes = [POINTER(_Settings), POINTER(_Inputs), c_void_p, c_void_p, c_void_p, c_int64, _ALLOC_FN,
                                 c_void_p, POINTER(_State), c_void_p]
     lib.gsb_backward.restype = c_int32
     lib.gsb_backward.argtypes = [POINTER(_Settings), POINTER(_Inputs), POINTER(_State), c_void_p, c_void_p, c_void_p,
@@ -79,8 +79,8 @@ def _load():
     lib.gsb_kernel_time.argtypes = [c_char_p, POINTER(ctypes.c_double), POINTER(c_int64), c_int32]
     lib.gsb_set_option.restype = c_int32
     lib.gsb_set_option.argtypes = [c_char_p, c_int32]
-    if lib.gsb_abi_version() != 2:
-        raise ImportError(f"{_LIB_PATH}: ABI version {lib.gsb_abi_version()} != 2")
+    if lib.gsb_abi_version() != 3:
+        raise ImportError(f"{_LIB_PATH}: ABI version {lib.gsb_abi_version()} != 3")
     return lib
 
 
@@ -117,7 +117,7 @@ def state_views(pack: dict, height: int, width: int):
     img, binning, D = pack["image"], pack["binning"], pack["num_rendered"]
     final_T = img[:npix * 4].view(torch.float32).view(height, width)
     n_contrib = img[al(npix * 4):al(npix * 4) + npix * 4].view(torch.int32).view(height, width)
-    pl_bytes = max(D, 1) * 4
+    pl_bytes = max(int(pack["state"].binning_capacity), 1) * 4
     point_list = binning[:D * 4].view(torch.int32)
     num_tiles = int(pack["state"].num_tiles)
     ranges = binning[al(pl_bytes):al(pl_bytes) + num_tiles * 8].view(torch.int32).view(num_tiles, 2)
@@ -208,6 +208,11 @@ def _c_inputs(P, means3D, sh, colors, opac, scales, rots, cov) -> _Inputs:
     return i
 
 
+# instance-count estimate per (P, H, W): the previous call's count + 25 % (+64 Ki); see gsb_forward's capacity_hint
+_capacity_hints = {}
+speculative_binning = True
+
+
 def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs):
     """Returns (color, radii, invdepth, ctx_pack).  All tensor arguments already float32-contiguous or None."""
     if not means3D.is_cuda:
@@ -226,16 +231,24 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
         arena = _Arena(dev)
         st = _State()
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = _C.gsb_forward(byref(cs), byref(ci), color.data_ptr(), radii.data_ptr(), invdepth.data_ptr(), arena.cb,
-                            None, byref(st), stream)
+        hkey = (P, H, W, dev.index)
+        hint = _capacity_hints.get(hkey, 0) if speculative_binning else 0
+        rc = _C.gsb_forward(byref(cs), byref(ci), color.data_ptr(), radii.data_ptr(), invdepth.data_ptr(), hint,
+                            arena.cb, None, byref(st), stream)
         _check(rc, arena)
+        _capacity_hints[hkey] = int(st.num_rendered * 1.25) + 65536
     pack = dict(state=st, geom=arena.bufs.get(BUF_GEOM), binning=arena.bufs.get(BUF_BINNING),
                 image=arena.bufs.get(BUF_IMAGE), num_rendered=int(st.num_rendered), sh_coeffs=M)
     return color, radii, invdepth, pack
 
 
 def _backward_impl(pack, rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                   out_color, out_invdepth, grad_color, grad_invdepth, grads: dict, accumulate: bool):
+                   out_color, out_invdepth, grad_color, grad_invdepth, grads: dict, accumulate: bool,
+                   accumulate_means2D: Optional[bool] = None):
+    """grads: tensors to fill (accumulate=False) or add into (accumulate=True).  The C ABI has one accumulate
+    switch; a per-view means2D buffer (accumulate_means2D=False while the rest accumulates) is zeroed here."""
+    if accumulate and accumulate_means2D is False and grads.get("means2D") is not None:
+        grads["means2D"].zero_()
     dev = means3D.device
     P = int(means3D.shape[0])
     with torch.cuda.device(dev):

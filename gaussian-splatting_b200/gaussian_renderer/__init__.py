@@ -18,9 +18,10 @@ from typing import Iterable, List, Optional, Sequence
 
 import torch
 
+import diff_gaussian_rasterization as _dgr
 from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
 
-__all__ = ["render", "render_views", "GradientBucket", "shard_views"]
+__all__ = ["render", "render_views", "render_views_backward", "GradientBucket", "shard_views"]
 
 
 def _eval_sh(deg, sh, dirs):
@@ -104,6 +105,92 @@ def render_views(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch.Tensor, 
     stays connected to autograd, so ``sum(losses).backward()`` accumulates every view's per-gaussian gradient
     into the parameters' ``.grad`` (which GradientBucket maps onto one flat buffer)."""
     return [render(cam, pc, pipe, bg_color, **kw) for cam in viewpoint_cameras]
+
+
+def _settings_for(cam, pc, pipe, bg_color, scaling_modifier):
+    return GaussianRasterizationSettings(
+        image_height=int(cam.image_height), image_width=int(cam.image_width),
+        tanfovx=math.tan(cam.FoVx * 0.5), tanfovy=math.tan(cam.FoVy * 0.5), bg=bg_color,
+        scale_modifier=scaling_modifier, viewmatrix=cam.world_view_transform, projmatrix=cam.full_proj_transform,
+        sh_degree=pc.active_sh_degree, campos=cam.camera_center, prefiltered=False,
+        debug=bool(getattr(pipe, "debug", False)), antialiasing=bool(getattr(pipe, "antialiasing", False)))
+
+
+def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch.Tensor, loss_fn, *,
+                          scaling_modifier: float = 1.0, densify_stats: Optional[dict] = None,
+                          keep_images: bool = False) -> dict:
+    """Fused view-batch training step: forward + loss + backward for every camera, with the per-gaussian
+    gradients of ALL views summed in place.
+
+    The activations (exp / sigmoid / normalize / cat in scene.GaussianModel, gaussian_model.py:102-130) do not
+    depend on the view, so they run ONCE per batch; each view then goes straight through the C ABI
+    (gsb_forward / gsb_backward with accumulate=1) and adds its gradient w.r.t. the activated tensors into one
+    buffer; one ``torch.autograd.backward`` at the end chains that sum into the leaf parameters.  When the
+    rasterizer's inputs already ARE leaves whose ``.grad`` is set (GradientBucket), the kernels accumulate
+    directly into ``.grad`` and no extra pass over the 59 floats/gaussian is made.
+
+    ``loss_fn(image[3,H,W] (clamped to [0,1] like render() does), invdepth[1,H,W], view_index) -> scalar``.
+    Returns {"losses": [V] tensor, "radii_max": [P] int32, "images": list (if keep_images)}; nothing in here
+    synchronises with the host except the one instance-count read-back per forward.
+    """
+    xyz, opacity = pc.get_xyz, pc.get_opacity
+    scales, rotations, shs = pc.get_scaling, pc.get_rotation, pc.get_features
+    inputs = dict(means3D=xyz, shs=shs, opacities=opacity, scales=scales, rotations=rotations)
+    P = int(xyz.shape[0])
+    dev = xyz.device
+
+    def grad_target(t):
+        if t.is_leaf and t.requires_grad and t.grad is not None and t.grad.is_contiguous():
+            return t.grad, True
+        return torch.zeros_like(t, dtype=torch.float32, memory_format=torch.contiguous_format), False
+
+    targets = {k: grad_target(v) for k, v in inputs.items()}
+    grads = {k: tv[0] for k, tv in targets.items()}
+    if densify_stats is not None:
+        m2d = torch.empty((P, 3), dtype=torch.float32, device=dev)
+    c = {k: _dgr._f32c(v.detach()) for k, v in inputs.items()}
+    c["opacities"] = c["opacities"].reshape(-1) if c["opacities"] is not None else None
+    losses, images = [], []
+    radii_max = torch.zeros((P,), dtype=torch.int32, device=dev)
+    for vi, cam in enumerate(viewpoint_cameras):
+        rs = _settings_for(cam, pc, pipe, bg_color, scaling_modifier)
+        color, radii, invdepth, pack = _dgr._forward_impl(c["means3D"], c["shs"], None, c["opacities"], c["scales"],
+                                                          c["rotations"], None, rs)
+        img = color.requires_grad_(True)
+        dep = invdepth.requires_grad_(True)
+        with torch.enable_grad():
+            loss = loss_fn(img.clamp(0, 1), dep, vi)
+        g_img, g_dep = torch.autograd.grad(loss, (img, dep), allow_unused=True)
+        if g_img is None:
+            g_img = torch.zeros_like(color)
+        vg = dict(grads)
+        if densify_stats is not None:
+            vg["means2D"] = m2d
+        _dgr._backward_impl(pack, rs, c["means3D"], c["shs"], None, c["opacities"], c["scales"], c["rotations"], None,
+                            color.detach(), invdepth.detach(), _dgr._f32c(g_img), _dgr._f32c(g_dep), vg,
+                            accumulate=True, accumulate_means2D=False)
+        torch.maximum(radii_max, radii, out=radii_max)
+        if densify_stats is not None:
+            # add_densification_stats (gaussian_model.py:471-473) + max_radii2D update (train.py:166), sync-free
+            vis = radii > 0
+            densify_stats["xyz_gradient_accum"] += (m2d[:, :2].norm(dim=-1, keepdim=True) * vis[:, None])
+            densify_stats["denom"] += vis[:, None].to(densify_stats["denom"].dtype)
+        losses.append(loss.detach())
+        if keep_images:
+            images.append(color.detach())
+    # chain the summed gradient into non-leaf inputs' graphs (one pass, view independent)
+    chain_t, chain_g = [], []
+    for k, v in inputs.items():
+        g, direct = targets[k]
+        if not direct and v.requires_grad:
+            chain_t.append(v)
+            chain_g.append(g.view_as(v))
+    if chain_t:
+        torch.autograd.backward(chain_t, chain_g)
+    out = {"losses": torch.stack(losses) if losses else torch.zeros(0, device=dev), "radii_max": radii_max}
+    if keep_images:
+        out["images"] = images
+    return out
 
 
 def shard_views(views: Sequence, rank: int, world_size: int) -> list:

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define GSB_ABI_VERSION 2
+#define GSB_ABI_VERSION 3
 
 /* error codes (0 = ok); gsb_last_error() holds the message of the calling thread's last failure */
 #define GSB_OK 0
@@ -96,7 +96,8 @@ typedef struct GsbState {
     int32_t P;
     int32_t num_tiles;
     int64_t num_rendered;   /* D: (gaussian, tile) instances after exact tile culling */
-    int64_t num_visible;    /* gaussians with radius > 0 */
+    int64_t num_visible;    /* gaussians with radius > 0 (-1: not counted) */
+    int64_t binning_capacity; /* instances the binning buffer was sized for (>= num_rendered) */
     void *geom;
     size_t geom_bytes;
     void *binning;
@@ -118,10 +119,13 @@ typedef struct GsbGrads {
 } GsbGrads;
 
 /* Forward: preprocess -> depth sort -> tile binning -> tile sort -> tile ranges -> blend.
- * out_color [3,H,W], out_radii [P] int32, out_invdepth [H*W]. */
+ * out_color [3,H,W], out_radii [P] int32, out_invdepth [H*W].
+ * capacity_hint: the caller's estimate of the instance count (0 = none).  With an estimate the binning and
+ * blend kernels are enqueued before the host waits for the true count, so the device never idles on the
+ * read-back; if the true count exceeds the estimate the tail is re-run exactly (results never depend on it). */
 int32_t gsb_forward(const GsbSettings *settings, const GsbInputs *in, float *out_color,
-                    int32_t *out_radii, float *out_invdepth, gsb_alloc_fn alloc, void *alloc_ctx,
-                    GsbState *state_out, void *cuda_stream);
+                    int32_t *out_radii, float *out_invdepth, int64_t capacity_hint, gsb_alloc_fn alloc,
+                    void *alloc_ctx, GsbState *state_out, void *cuda_stream);
 
 /* Backward.  out_color / out_invdepth are the forward call's outputs (the front-to-back backward blend
  * reads them); dL_dinvdepth may be NULL.  accumulate != 0 adds into the gradient tensors instead of
