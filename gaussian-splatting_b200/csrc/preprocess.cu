@@ -20,33 +20,57 @@ constexpr int PRE_THREADS = 128;
 // (row stride padded to an odd word count: conflict-free).
 __device__ __forceinline__ int sh_row_stride(const int n) { return n | 1; }
 
-// global -> shared: first `ncols` floats of each of the block's rows (row length n)
+// global -> shared: first `ncols` floats of each of the block's rows (row length n); four loads in flight per thread
 __device__ __forceinline__ void stage_rows_in(const float *__restrict__ g, float *s, const int row0, const int nrows,
                                               const int n, const int ncols) {
     const int stride = sh_row_stride(n);
     const int total = nrows * ncols;
-    int r = threadIdx.x / ncols, c = threadIdx.x % ncols;
-    const int dr = PRE_THREADS / ncols, dc = PRE_THREADS % ncols;
-    for (int idx = threadIdx.x; idx < total; idx += PRE_THREADS) {
-        s[r * stride + c] = __ldg(g + (size_t)(row0 + r) * n + c);
-        r += dr; c += dc;
-        if (c >= ncols) { c -= ncols; ++r; }
+    const float inv = 1.0f / (float)ncols;
+    const float *gb = g + (size_t)row0 * n;
+    for (int base = 0; base < total; base += 4 * PRE_THREADS) {
+        float v[4];
+        int si[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * PRE_THREADS + threadIdx.x;
+            si[u] = -1;
+            if (idx < total) {
+                const int r = (int)(((float)idx + 0.5f) * inv), c = idx - r * ncols;
+                si[u] = r * stride + c;
+                v[u] = __ldg(gb + (size_t)r * n + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (si[u] >= 0) s[si[u]] = v[u];
     }
 }
 
-// shared -> global: full rows
+// shared -> global: full rows (contiguous in global memory); ACC adds into the destination
 template <bool ACC>
 __device__ __forceinline__ void stage_rows_out(float *__restrict__ g, const float *s, const int row0, const int nrows,
                                                const int n) {
     const int stride = sh_row_stride(n);
     const int total = nrows * n;
-    int r = threadIdx.x / n, c = threadIdx.x % n;
-    const int dr = PRE_THREADS / n, dc = PRE_THREADS % n;
-    for (int idx = threadIdx.x; idx < total; idx += PRE_THREADS) {
-        float *dst = g + (size_t)(row0 + r) * n + c;
-        if (ACC) *dst += s[r * stride + c]; else *dst = s[r * stride + c];
-        r += dr; c += dc;
-        if (c >= n) { c -= n; ++r; }
+    const float inv = 1.0f / (float)n;
+    float *gb = g + (size_t)row0 * n;
+    for (int base = 0; base < total; base += 4 * PRE_THREADS) {
+        float v[4];
+        int gi[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * PRE_THREADS + threadIdx.x;
+            gi[u] = -1;
+            if (idx < total) {
+                const int r = (int)(((float)idx + 0.5f) * inv), c = idx - r * n;
+                gi[u] = idx;
+                v[u] = s[r * stride + c];
+                if (ACC) v[u] += gb[idx];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (gi[u] >= 0) gb[gi[u]] = v[u];
     }
 }
 

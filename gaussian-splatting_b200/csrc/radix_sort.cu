@@ -18,12 +18,18 @@ namespace gsb {
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_IPT = 16;
-constexpr int SORT_KPB = SORT_THREADS * SORT_IPT;  // keys per block
+// keys per thread: 16 for large inputs; 4 below ~2.4 M keys so that even the 1 M-gaussian depth sort fills
+// 148 SMs with several blocks each (the first version ran 245 blocks of 4096 keys: latency bound)
+constexpr int SORT_IPT_BIG = 16;
+constexpr int SORT_IPT_SMALL = 4;
+constexpr int64_t SORT_SMALL_LIMIT = 148 * 4 * 4096;
+static inline int sort_ipt(int64_t n) { return n < SORT_SMALL_LIMIT ? SORT_IPT_SMALL : SORT_IPT_BIG; }
 
+template <int SORT_IPT>
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_hist_kernel(const uint32_t *__restrict__ keys, uint32_t *__restrict__ table, int64_t n,
                  const unsigned long long *__restrict__ n_dev, int nblocks, int shift, uint32_t mask) {
+    constexpr int SORT_KPB = SORT_THREADS * SORT_IPT;
     __shared__ uint32_t hist[RADIX];
     if (n_dev) n = min((int64_t)*n_dev, n);
     const int tid = threadIdx.x;
@@ -75,11 +81,13 @@ sort_rowscan_kernel(uint32_t *__restrict__ table, uint32_t *__restrict__ totals,
     if (tid == 0) totals[blockIdx.x] = carry_s;
 }
 
+template <int SORT_IPT>
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                     const uint32_t *__restrict__ table, const uint32_t *__restrict__ totals, int64_t n,
                     const unsigned long long *__restrict__ n_dev, int nblocks, int shift, uint32_t mask) {
+    constexpr int SORT_KPB = SORT_THREADS * SORT_IPT;
     __shared__ uint32_t warp_cnt[SORT_THREADS / 32][RADIX];
     if (n_dev) n = min((int64_t)*n_dev, n);
     __shared__ uint32_t warp_sums[8];
@@ -148,7 +156,7 @@ sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__rest
 }
 
 size_t sort_scratch_bytes(int64_t n) {
-    int64_t nblocks = ceil_div(n > 0 ? n : 1, SORT_KPB);
+    int64_t nblocks = ceil_div(n > 0 ? n : 1, SORT_THREADS * sort_ipt(n));
     return align_up((size_t)RADIX * nblocks * sizeof(uint32_t), 256) + align_up(RADIX * sizeof(uint32_t), 256);
 }
 
@@ -160,7 +168,8 @@ int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *val
         set_error("sort_pairs: n=%lld does not fit 32-bit positions", (long long)n);
         return GSB_ERR_OVERFLOW;
     }
-    const int nblocks = (int)ceil_div(n, SORT_KPB);
+    const bool small = sort_ipt(n) == SORT_IPT_SMALL;
+    const int nblocks = (int)ceil_div(n, SORT_THREADS * sort_ipt(n));
     uint32_t *table = static_cast<uint32_t *>(scratch);
     uint32_t *totals = reinterpret_cast<uint32_t *>(static_cast<char *>(scratch) +
                                                     align_up((size_t)RADIX * nblocks * sizeof(uint32_t), 256));
@@ -169,11 +178,21 @@ int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *val
     for (int bit = begin_bit; bit < end_bit; bit += RADIX_BITS) {
         const int bits = (end_bit - bit) < RADIX_BITS ? (end_bit - bit) : RADIX_BITS;
         const uint32_t mask = (1u << bits) - 1u;
-        GSB_LAUNCH("sort_hist", debug, stream, sort_hist_kernel, nblocks, SORT_THREADS, 0, kin, table, n, n_dev,
-                   nblocks, bit, mask);
+        if (small) {
+            GSB_LAUNCH("sort_hist", debug, stream, sort_hist_kernel<SORT_IPT_SMALL>, nblocks, SORT_THREADS, 0, kin, table, n,
+                       n_dev, nblocks, bit, mask);
+        } else {
+            GSB_LAUNCH("sort_hist", debug, stream, sort_hist_kernel<SORT_IPT_BIG>, nblocks, SORT_THREADS, 0, kin, table, n,
+                       n_dev, nblocks, bit, mask);
+        }
         GSB_LAUNCH("sort_rowscan", debug, stream, sort_rowscan_kernel, RADIX, 256, 0, table, totals, nblocks);
-        GSB_LAUNCH("sort_scatter", debug, stream, sort_scatter_kernel, nblocks, SORT_THREADS, 0, kin, vin, kout,
-                   vout, table, totals, n, n_dev, nblocks, bit, mask);
+        if (small) {
+            GSB_LAUNCH("sort_scatter", debug, stream, sort_scatter_kernel<SORT_IPT_SMALL>, nblocks, SORT_THREADS, 0, kin, vin,
+                       kout, vout, table, totals, n, n_dev, nblocks, bit, mask);
+        } else {
+            GSB_LAUNCH("sort_scatter", debug, stream, sort_scatter_kernel<SORT_IPT_BIG>, nblocks, SORT_THREADS, 0, kin, vin,
+                       kout, vout, table, totals, n, n_dev, nblocks, bit, mask);
+        }
         uint32_t *t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
         ++passes;

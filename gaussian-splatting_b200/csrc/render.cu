@@ -10,6 +10,7 @@
 // memory 256 at a time.  One 16x16 tile per CTA; a warp owns an 8x4 pixel patch so that a gaussian
 // which misses the patch is skipped by the whole warp.
 #include "kernels.cuh"
+#include "patch_cull.cuh"
 
 namespace gsb {
 
@@ -67,6 +68,73 @@ render_fwd_kernel(const RenderFwdArgs a) {
             Dp += q2.y * w;
             T = test_T;
             last = contributor;
+        }
+    }
+    if (inside) {
+        const size_t pid = (size_t)py * a.W + px, HW = (size_t)a.W * a.H;
+        a.final_T[pid] = T;
+        a.n_contrib[pid] = last;
+        a.out_color[pid] = C0 + T * __ldg(a.bg);
+        a.out_color[HW + pid] = C1 + T * __ldg(a.bg + 1);
+        a.out_color[2 * HW + pid] = C2 + T * __ldg(a.bg + 2);
+        a.out_invdepth[pid] = Dp;
+    }
+}
+
+// forward with sub-tile culling: each warp (8x4 patch) walks only the staged gaussians whose cull ellipse
+// meets its patch (patch_cull.cuh).  Blend arithmetic identical to render_fwd_kernel.
+__global__ void __launch_bounds__(256)
+render_fwd_pc_kernel(const RenderFwdArgs a) {
+    __shared__ float4 s0[RB], s1[RB];
+    __shared__ float2 s2[RB];
+    __shared__ uint8_t smask[RB];
+    __shared__ uint8_t slist[8][RB];
+    const int tile = blockIdx.x;
+    const int tile_x = tile % a.gx, tile_y = tile / a.gx;
+    int px, py;
+    pixel_of_thread(tile_x, tile_y, px, py);
+    const bool inside = px < a.W && py < a.H;
+    const float fx = (float)px, fy = (float)py;
+    const float ox = (float)(tile_x * TILE), oy = (float)(tile_y * TILE);
+    const uint2 range = a.ranges[tile];
+    const int todo = (int)(range.y - range.x);
+    const int rounds = (todo + RB - 1) / RB;
+    const int w = threadIdx.x >> 5;
+
+    bool done = !inside;
+    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
+    uint32_t last = 0;
+
+    for (int rd = 0; rd < rounds; ++rd) {
+        if (__syncthreads_count(done) == 256) break;
+        const int idx = rd * RB + threadIdx.x;
+        if (idx < todo) {
+            const uint32_t g = a.point_list[range.x + idx];
+            const float4 *rec = a.splat + (size_t)g * SPLAT_F4;
+            const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+            s0[threadIdx.x] = q0; s1[threadIdx.x] = q1; s2[threadIdx.x] = make_float2(q2.x, q2.y);
+            smask[threadIdx.x] = (uint8_t)patch_mask(q0.x, q0.y, q0.z, q0.w, q1.x, q2.z, ox, oy);
+        }
+        __syncthreads();
+        const int n = min(RB, todo - rd * RB);
+        const int cnt = compact_hits(smask, n, 1u << w, slist[w]);
+        for (int k = 0; !done && k < cnt; ++k) {
+            const int j = slist[w][k];
+            const float4 q0 = s0[j];
+            const float4 q1 = s1[j];
+            const float dx = q0.x - fx, dy = q0.y - fy;
+            const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
+            if (power > 0.0f) continue;
+            const float alpha = fminf(ALPHA_MAX, q1.y * __expf(power));
+            if (alpha < ALPHA_MIN) continue;
+            const float test_T = T * (1.0f - alpha);
+            if (test_T < T_STOP) { done = true; continue; }
+            const float2 q2 = s2[j];
+            const float wgt = alpha * T;
+            C0 += q1.z * wgt; C1 += q1.w * wgt; C2 += q2.x * wgt;
+            Dp += q2.y * wgt;
+            T = test_T;
+            last = (uint32_t)(rd * RB + j + 1);
         }
     }
     if (inside) {
@@ -223,10 +291,13 @@ render_bwd_kernel(const RenderBwdArgs a) {
 }
 
 int launch_render_fwd(const RenderFwdArgs &a, int variant, bool debug, cudaStream_t stream) {
-    (void)variant;
     const int tiles = a.gx * a.gy;
     if (tiles <= 0) return GSB_OK;
-    GSB_LAUNCH("render_fwd", debug, stream, render_fwd_kernel, tiles, 256, 0, a);
+    if (variant == 4) {
+        GSB_LAUNCH("render_fwd", debug, stream, render_fwd_pc_kernel, tiles, 256, 0, a);
+    } else {
+        GSB_LAUNCH("render_fwd", debug, stream, render_fwd_kernel, tiles, 256, 0, a);
+    }
     return GSB_OK;
 }
 

@@ -15,6 +15,7 @@
 //   * the geometric gradient terms are accumulated as raw moments of d(power) (sum t dx, t dy, t dx^2,
 //     t dx dy, t dy^2) and turned into mean / conic gradients once per gaussian in preprocess_bwd.
 #include "kernels.cuh"
+#include "patch_cull.cuh"
 
 namespace gsb {
 
@@ -174,15 +175,20 @@ __device__ __forceinline__ float reduce2_transposed(const float v0, const float 
 
 // dacc layout written here (DACC_MOMENTS): 0 sum t dx, 1 sum t dy, 2 sum t dx^2, 3 sum t dx dy, 4 sum t dy^2,
 // 5 sum G dL/dalpha, 6..8 sum w dL/dC, 9 sum w dL/dD, with t = opacity G dL/dalpha = dL/d(power).
-template <int QH>
+template <int QH, bool CULL>
 __global__ void __launch_bounds__(256 / (2 * QH))
 render_bwd_mp_kernel(const RenderBwdArgs a) {
     constexpr int NT = 256 / (2 * QH);
     constexpr int NPX = 2 * QH;
+    constexpr int NW = NT / 32;
     __shared__ float4 s0[MP_R], s1[MP_R];
     __shared__ float2 s2[MP_R];
     __shared__ uint32_t sid[MP_R];
     __shared__ uint32_t s_max;
+    __shared__ uint8_t smask[CULL ? MP_R : 1];
+    __shared__ uint8_t slist[CULL ? NW : 1][CULL ? MP_R : 1];
+    // rows covered by this warp: [16/NW * w, ...) = 4-row bands 4/NW*w .. ; mask bits 2*band + col
+    const uint32_t want = CULL ? (((1u << (8 / NW)) - 1u) << ((8 / NW) * (threadIdx.x >> 5))) : 0u;
     const int tile = blockIdx.x;
     const int ox = (tile % a.gx) * TILE, oy = (tile / a.gx) * TILE;
     const int t = threadIdx.x;
@@ -223,11 +229,14 @@ render_bwd_mp_kernel(const RenderBwdArgs a) {
             const float4 *rec = a.splat + (size_t)g * SPLAT_F4;
             float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
             const float4 q2 = __ldg(rec + 2);
+            if (CULL) smask[k] = (uint8_t)patch_mask(q0.x, q0.y, q0.z, q0.w, q1.x, q2.z, (float)ox, (float)oy);
             stage_scale(q0, q1);
             s0[k] = q0; s1[k] = q1; s2[k] = make_float2(q2.x, q2.y); sid[k] = g;
         }
         __syncthreads();
-        for (int j = 0; j < n; ++j) {
+        const int cnt = CULL ? compact_hits(smask, n, want, slist[CULL ? (t >> 5) : 0]) : n;
+        for (int kk = 0; kk < cnt; ++kk) {
+            const int j = CULL ? (int)slist[CULL ? (t >> 5) : 0][kk] : kk;
             const float4 q0 = s0[j];
             const float4 q1 = s1[j];
             const uint32_t pos = (uint32_t)(base + j + 1);
@@ -302,9 +311,11 @@ int launch_render_bwd_mp(const RenderBwdArgs &a, int qh, bool debug, cudaStream_
     const int tiles = a.gx * a.gy;
     if (tiles <= 0) return GSB_OK;
     if (qh == 4) {
-        GSB_LAUNCH("render_bwd", debug, stream, render_bwd_mp_kernel<4>, tiles, 32, 0, a);
-    } else {
-        GSB_LAUNCH("render_bwd", debug, stream, render_bwd_mp_kernel<2>, tiles, 64, 0, a);
+        GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp_kernel<4, false>), tiles, 32, 0, a);
+    } else if (qh == 2) {
+        GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp_kernel<2, false>), tiles, 64, 0, a);
+    } else {   // qh == -2: 2x2 pixels per thread + sub-tile culling
+        GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp_kernel<2, true>), tiles, 64, 0, a);
     }
     return GSB_OK;
 }
