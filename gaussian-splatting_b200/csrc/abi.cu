@@ -35,7 +35,7 @@ void timer_end(void *token, cudaStream_t stream) {
 }
 
 static int opt_cull = 1;
-static int opt_fwd_variant = 0;
+static int opt_fwd_variant = 4;  // one pixel per thread + sub-tile patch culling (tools/sweep.py: 0.33 ms vs 0.42)
 static int opt_bwd_variant = 2;  // render_mp.cu, 2x2 pixels per thread (tools/sweep.py: 0.74 ms vs 1.41 / 1.03)
 
 void set_error(const char *fmt, ...) {
@@ -162,6 +162,7 @@ int32_t gsb_set_option(const char *name, int32_t value) {
     if (!name) return 1;
     if (!strcmp(name, "cull")) { opt_cull = value; return 0; }
     if (!strcmp(name, "time_kernels")) { g_time_kernels = value; return 0; }
+    if (!strcmp(name, "sort_variant")) { g_sort_variant = value; return 0; }
     if (!strcmp(name, "render_fwd_variant")) { opt_fwd_variant = value; return 0; }
     if (!strcmp(name, "render_bwd_variant")) { opt_bwd_variant = value; return 0; }
     return 1;

@@ -91,6 +91,6 @@ size_t sort_scratch_bytes(int64_t n);
 int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n,
                const unsigned long long *n_dev, int begin_bit, int end_bit, void *scratch, bool debug,
                cudaStream_t stream);
-size_t scan_scratch_bytes(int64_t n);
+extern int g_sort_variant;
 
 }  // namespace gsb

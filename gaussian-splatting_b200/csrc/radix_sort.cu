@@ -155,19 +155,207 @@ sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__rest
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Single-pass-per-digit variant ("onesweep"): one upfront kernel builds the global digit histograms of
+// every pass, then each pass is ONE kernel whose blocks obtain their per-digit offsets by decoupled
+// look-back over a status word per (block, digit) -- no per-pass histogram / row-scan kernels, keys and
+// values are read once and written once per pass (16 B / pair).
+//   status word: bits 31..30 = 0 not ready | 1 block aggregate | 2 inclusive prefix; bits 29..0 = count.
+// Blocks take a ticket from an atomic counter, so a block only ever waits for blocks that started before
+// it: forward progress does not depend on the hardware's block scheduling order.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t OS_FLAG_AGG = 1u << 30, OS_FLAG_PREFIX = 2u << 30, OS_VALUE_MASK = (1u << 30) - 1u;
+constexpr int OS_MAX_PASSES = 4;
+
+struct OnesweepPasses {
+    int npass;
+    int shift[OS_MAX_PASSES];
+    uint32_t mask[OS_MAX_PASSES];
+};
+
+__global__ void __launch_bounds__(256)
+onesweep_hist_kernel(const uint32_t *__restrict__ keys, uint32_t *__restrict__ ghist, int64_t n,
+                     const unsigned long long *__restrict__ n_dev, const OnesweepPasses ps) {
+    __shared__ uint32_t hist[OS_MAX_PASSES][RADIX];
+    if (n_dev) n = min((int64_t)*n_dev, n);
+    for (int p = 0; p < ps.npass; ++p) hist[p][threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        const uint32_t k = keys[i];
+        for (int p = 0; p < ps.npass; ++p) atomicAdd(&hist[p][(k >> ps.shift[p]) & ps.mask[p]], 1u);
+    }
+    __syncthreads();
+    for (int p = 0; p < ps.npass; ++p) {
+        const uint32_t c = hist[p][threadIdx.x];
+        if (c) atomicAdd(&ghist[p * RADIX + threadIdx.x], c);
+    }
+}
+
+template <int SORT_IPT>
+__global__ void __launch_bounds__(SORT_THREADS)
+onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                     uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                     const uint32_t *__restrict__ ghist, volatile uint32_t *status, uint32_t *ticket, int64_t n,
+                     const unsigned long long *__restrict__ n_dev, int shift, uint32_t mask) {
+    constexpr int SORT_KPB = SORT_THREADS * SORT_IPT;
+    __shared__ uint32_t warp_cnt[SORT_THREADS / 32][RADIX];
+    __shared__ uint32_t warp_sums[8];
+    __shared__ uint32_t s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (n_dev) n = min((int64_t)*n_dev, n);
+    if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
+#pragma unroll
+    for (int k = 0; k < SORT_THREADS / 32; ++k) warp_cnt[k][tid] = 0;
+    __syncthreads();
+    const uint32_t b = s_ticket;
+    if ((int64_t)b * SORT_KPB >= n) return;
+
+    // global base of digit `tid`: exclusive scan of the 256 digit totals of this pass
+    const uint32_t tot = ghist[tid];
+    uint32_t incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    uint32_t digit_base = incl - tot;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k < w) digit_base += warp_sums[k];
+
+    // stable local ranks, block order = (warp, round, lane)
+    const int64_t seg = (int64_t)b * SORT_KPB + (int64_t)w * (32 * SORT_IPT);
+    uint32_t key[SORT_IPT], rank[SORT_IPT];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; ++r) {
+        const int64_t idx = seg + r * 32 + lane;
+        const bool valid = idx < n;
+        key[r] = valid ? keys_in[idx] : 0xffffffffu;
+        const uint32_t d = valid ? ((key[r] >> shift) & mask) : (uint32_t)RADIX;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader && valid) {
+            base = warp_cnt[w][d];
+            warp_cnt[w][d] = base + __popc(peers);
+        }
+        base = __shfl_sync(0xffffffffu, base, leader);
+        rank[r] = base + __popc(peers & lt_mask);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // per-digit block count; warp_cnt becomes the exclusive prefix over warps
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int k = 0; k < SORT_THREADS / 32; ++k) {
+        const uint32_t c = warp_cnt[k][tid];
+        warp_cnt[k][tid] = cnt;
+        cnt += c;
+    }
+    // decoupled look-back for digit `tid`
+    volatile uint32_t *my = status + (size_t)b * RADIX + tid;
+    uint32_t excl = 0;
+    if (b == 0) {
+        *my = cnt | OS_FLAG_PREFIX;
+    } else {
+        *my = cnt | OS_FLAG_AGG;
+        int64_t pb = (int64_t)b - 1;
+        while (true) {
+            uint32_t v;
+            do { v = status[(size_t)pb * RADIX + tid]; } while ((v >> 30) == 0u);
+            excl += v & OS_VALUE_MASK;
+            if ((v >> 30) == 2u) break;
+            --pb;
+        }
+        *my = ((excl + cnt) & OS_VALUE_MASK) | OS_FLAG_PREFIX;
+    }
+    const uint32_t run = digit_base + excl;
+#pragma unroll
+    for (int k = 0; k < SORT_THREADS / 32; ++k) warp_cnt[k][tid] += run;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SORT_IPT; ++r) {
+        const int64_t idx = seg + r * 32 + lane;
+        if (idx < n) {
+            const uint32_t d = (key[r] >> shift) & mask;
+            const uint32_t pos = warp_cnt[w][d] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = vals_in[idx];
+        }
+    }
+}
+
+int g_sort_variant = 1;  // 0: histogram / row scan / scatter per pass, 1: onesweep
+
+static size_t onesweep_scratch_bytes(int64_t n) {
+    const int64_t nblocks = ceil_div(n > 0 ? n : 1, SORT_THREADS * sort_ipt(n));
+    return align_up((size_t)OS_MAX_PASSES * RADIX * 4 + 256 + (size_t)OS_MAX_PASSES * nblocks * RADIX * 4, 256);
+}
+
+static int onesweep_sort(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n,
+                         const unsigned long long *n_dev, int begin_bit, int end_bit, void *scratch, bool debug,
+                         cudaStream_t stream) {
+    OnesweepPasses ps;
+    ps.npass = 0;
+    for (int bit = begin_bit; bit < end_bit; bit += RADIX_BITS) {
+        if (ps.npass == OS_MAX_PASSES) { set_error("onesweep: more than %d passes", OS_MAX_PASSES); return GSB_ERR_ARGUMENT; }
+        const int bits = (end_bit - bit) < RADIX_BITS ? (end_bit - bit) : RADIX_BITS;
+        ps.shift[ps.npass] = bit;
+        ps.mask[ps.npass] = (1u << bits) - 1u;
+        ++ps.npass;
+    }
+    const bool small = sort_ipt(n) == SORT_IPT_SMALL;
+    const int nblocks = (int)ceil_div(n, SORT_THREADS * sort_ipt(n));
+    // layout: ghist[4][256] | ticket[4] (padded to 256 B) | status[npass][nblocks][256]
+    uint32_t *ghist = static_cast<uint32_t *>(scratch);
+    uint32_t *ticket = ghist + OS_MAX_PASSES * RADIX;
+    uint32_t *status = ticket + 64;
+    const size_t zero_bytes = (size_t)OS_MAX_PASSES * RADIX * 4 + 256 + (size_t)ps.npass * nblocks * RADIX * 4;
+    GSB_CUDA(cudaMemsetAsync(scratch, 0, zero_bytes, stream));
+    const int hist_blocks = (int)(ceil_div(n, 256 * 16) < 148 * 8 ? ceil_div(n, 256 * 16) : 148 * 8);
+    GSB_LAUNCH("sort_hist", debug, stream, onesweep_hist_kernel, hist_blocks, 256, 0, keys, ghist, n, n_dev, ps);
+    uint32_t *kin = keys, *vin = vals, *kout = keys_alt, *vout = vals_alt;
+    for (int p = 0; p < ps.npass; ++p) {
+        uint32_t *st = status + (size_t)p * nblocks * RADIX;
+        if (small) {
+            GSB_LAUNCH("sort_scatter", debug, stream, onesweep_pass_kernel<SORT_IPT_SMALL>, nblocks, SORT_THREADS, 0, kin,
+                       vin, kout, vout, ghist + p * RADIX, st, ticket + p, n, n_dev, ps.shift[p], ps.mask[p]);
+        } else {
+            GSB_LAUNCH("sort_scatter", debug, stream, onesweep_pass_kernel<SORT_IPT_BIG>, nblocks, SORT_THREADS, 0, kin,
+                       vin, kout, vout, ghist + p * RADIX, st, ticket + p, n, n_dev, ps.shift[p], ps.mask[p]);
+        }
+        uint32_t *t = kin; kin = kout; kout = t;
+        t = vin; vin = vout; vout = t;
+    }
+    if (ps.npass & 1) {
+        GSB_CUDA(cudaMemcpyAsync(keys, keys_alt, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+        GSB_CUDA(cudaMemcpyAsync(vals, vals_alt, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+    }
+    return GSB_OK;
+}
+
 size_t sort_scratch_bytes(int64_t n) {
     int64_t nblocks = ceil_div(n > 0 ? n : 1, SORT_THREADS * sort_ipt(n));
-    return align_up((size_t)RADIX * nblocks * sizeof(uint32_t), 256) + align_up(RADIX * sizeof(uint32_t), 256);
+    const size_t classic = align_up((size_t)RADIX * nblocks * sizeof(uint32_t), 256) + align_up(RADIX * sizeof(uint32_t), 256);
+    const size_t os = onesweep_scratch_bytes(n);
+    return classic > os ? classic : os;
 }
 
 int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n,
                const unsigned long long *n_dev, int begin_bit, int end_bit, void *scratch, bool debug,
                cudaStream_t stream) {
     if (n <= 0 || end_bit <= begin_bit) return GSB_OK;
-    if (n >= (int64_t)1 << 32) {
-        set_error("sort_pairs: n=%lld does not fit 32-bit positions", (long long)n);
+    if (n >= (int64_t)1 << 30) {
+        set_error("sort_pairs: n=%lld does not fit 30-bit positions", (long long)n);
         return GSB_ERR_OVERFLOW;
     }
+    if (g_sort_variant == 1 && (end_bit - begin_bit) <= OS_MAX_PASSES * RADIX_BITS)
+        return onesweep_sort(keys, vals, keys_alt, vals_alt, n, n_dev, begin_bit, end_bit, scratch, debug, stream);
     const bool small = sort_ipt(n) == SORT_IPT_SMALL;
     const int nblocks = (int)ceil_div(n, SORT_THREADS * sort_ipt(n));
     uint32_t *table = static_cast<uint32_t *>(scratch);

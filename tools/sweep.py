@@ -27,9 +27,11 @@ pc = bench.BenchGaussians(scene, 3, dev)
 bg = torch.zeros(3, device=dev)
 gt = torch.rand(3, H, W, device=dev)
 cams = [bench.BenchCamera(W, H, math.radians(60.0), *bench.view_pose(i, 3.0), dev) for i in range(4)]
-for fv, bv in combos:
-    dgr.set_option("render_fwd_variant", fv); dgr.set_option("render_bwd_variant", bv)
-    out = {"fwd": fv, "bwd": bv}
+for combo in combos:
+    fv, bv = combo[0], combo[1]
+    sv = combo[2] if len(combo) > 2 else 1
+    dgr.set_option("render_fwd_variant", fv); dgr.set_option("render_bwd_variant", bv); dgr.set_option("sort_variant", sv)
+    out = {"fwd": fv, "bwd": bv, "sort": sv}
     try:
         got = U.run_cuda(args, cam_s, wc, wd)
         out["img_max_err"] = float(np.abs(got["color"] - ref["color"]).max())
@@ -46,7 +48,7 @@ for fv, bv in combos:
             (pkg["render"] - gt).abs().mean().backward()
     torch.cuda.synchronize()
     n = 2 * len(cams)
-    out["ms"] = {k: round(dgr.kernel_time(k)[0] / n, 4) for k in ("render_fwd", "render_bwd", "preprocess_fwd", "preprocess_bwd")}
+    out["ms"] = {k: round(dgr.kernel_time(k)[0] / n, 4) for k in ("render_fwd", "render_bwd", "preprocess_fwd", "preprocess_bwd", "sort_hist", "sort_rowscan", "sort_scatter", "emit", "tile_ranges")}
     out["ms"]["all_kernels"] = round(dgr.kernel_time("")[0] / n, 4)
     dgr.kernel_time("", reset=True); dgr.set_option("time_kernels", 0)
     print(json.dumps(out), flush=True)
