@@ -274,6 +274,7 @@ int32_t gsb_forward(const GsbSettings *s, const GsbInputs *in, float *out_color,
         ra.W = cam.W; ra.H = cam.H; ra.gx = cam.gx; ra.gy = cam.gy; ra.ranges = bv.ranges; ra.point_list = bv.point_list;
         ra.splat = splat; ra.bg = s->bg; ra.out_color = out_color; ra.out_invdepth = out_invdepth; ra.final_T = iv.final_T;
         ra.n_contrib = iv.n_contrib;
+        if (opt_fwd_variant == 5) return launch_render_fwd_ps(ra, debug, stream);
         return (opt_fwd_variant == 2 || opt_fwd_variant == 3) ? launch_render_fwd_mp(ra, opt_fwd_variant == 3 ? 4 : 2, debug, stream)
                                                               : launch_render_fwd(ra, opt_fwd_variant, debug, stream);
     };
@@ -362,7 +363,7 @@ int32_t gsb_backward(const GsbSettings *s, const GsbInputs *in, const GsbState *
         ra.W = cam.W; ra.H = cam.H; ra.gx = cam.gx; ra.gy = cam.gy; ra.ranges = bv.ranges; ra.point_list = bv.point_list;
         ra.splat = splat; ra.bg = s->bg; ra.final_T = iv.final_T; ra.n_contrib = iv.n_contrib; ra.dL_dcolor = dL_dcolor;
         ra.dL_dinvdepth = dL_dinvdepth; ra.dacc = dacc; ra.out_color = out_color; ra.out_invdepth = out_invdepth;
-        rc = opt_bwd_variant >= 2 ? launch_render_bwd_mp(ra, opt_bwd_variant == 3 ? 4 : (opt_bwd_variant == 4 ? -2 : 2), debug, stream)
+        rc = opt_bwd_variant == 5 ? launch_render_bwd_ps(ra, debug, stream) : opt_bwd_variant >= 2 ? launch_render_bwd_mp(ra, opt_bwd_variant == 3 ? 4 : (opt_bwd_variant == 4 ? -2 : 2), debug, stream)
                                   : launch_render_bwd(ra, opt_bwd_variant, debug, stream);
         if (rc) return rc;
     }

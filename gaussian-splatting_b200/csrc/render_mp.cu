@@ -14,31 +14,9 @@
 //     (algebraically the recursion of oracle/gs_oracle.c; background enters through C_out);
 //   * the geometric gradient terms are accumulated as raw moments of d(power) (sum t dx, t dy, t dx^2,
 //     t dx dy, t dy^2) and turned into mean / conic gradients once per gaussian in preprocess_bwd.
-#include "kernels.cuh"
-#include "patch_cull.cuh"
+#include "blend_common.cuh"
 
 namespace gsb {
-
-constexpr int MP_R = 128;           // gaussians staged per round
-constexpr float LOG2E = 1.4426950408889634f;
-
-__device__ __forceinline__ float ex2_approx(const float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// staged record: q0 = {x, y, A', B'}, q1 = {C', opacity, r, g} with A' = -0.5 log2e A, B' = -log2e B, C' = -0.5 log2e C
-__device__ __forceinline__ void stage_scale(float4 &q0, float4 &q1) {
-    q0.z = __fmul_rn(q0.z, -0.5f * LOG2E);
-    q0.w = __fmul_rn(q0.w, -LOG2E);
-    q1.x = __fmul_rn(q1.x, -0.5f * LOG2E);
-}
-
-// log2-domain exponent at offset (dx, dy); pinned operation order: forward and backward must agree bit for bit
-__device__ __forceinline__ float power2_at(const float Axx, const float Cyy, const float Bx, const float dy) {
-    return __fmaf_rn(Bx, dy, __fadd_rn(Axx, Cyy));
-}
 
 template <int QH>
 __global__ void __launch_bounds__(256 / (2 * QH))
@@ -143,34 +121,6 @@ render_fwd_mp_kernel(const RenderFwdArgs a) {
             a.out_invdepth[pid] = Dp[i];
         }
     }
-}
-
-// lane L ends with the warp total of value (L >> 2): 9 shuffles
-__device__ __forceinline__ float reduce8_transposed(const float v0, const float v1, const float v2, const float v3,
-                                                    const float v4, const float v5, const float v6, const float v7) {
-    const int lane = threadIdx.x & 31;
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-    const float k0 = (b4 ? v4 : v0) + __shfl_xor_sync(0xffffffffu, b4 ? v0 : v4, 16);
-    const float k1 = (b4 ? v5 : v1) + __shfl_xor_sync(0xffffffffu, b4 ? v1 : v5, 16);
-    const float k2 = (b4 ? v6 : v2) + __shfl_xor_sync(0xffffffffu, b4 ? v2 : v6, 16);
-    const float k3 = (b4 ? v7 : v3) + __shfl_xor_sync(0xffffffffu, b4 ? v3 : v7, 16);
-    const float m0 = (b3 ? k2 : k0) + __shfl_xor_sync(0xffffffffu, b3 ? k0 : k2, 8);
-    const float m1 = (b3 ? k3 : k1) + __shfl_xor_sync(0xffffffffu, b3 ? k1 : k3, 8);
-    float r = (b2 ? m1 : m0) + __shfl_xor_sync(0xffffffffu, b2 ? m0 : m1, 4);
-    r += __shfl_xor_sync(0xffffffffu, r, 2);
-    r += __shfl_xor_sync(0xffffffffu, r, 1);
-    return r;
-}
-
-// lanes 0..15 end with the total of v0, lanes 16..31 with the total of v1: 5 shuffles
-__device__ __forceinline__ float reduce2_transposed(const float v0, const float v1) {
-    const bool b4 = threadIdx.x & 16;
-    float r = (b4 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, b4 ? v0 : v1, 16);
-    r += __shfl_xor_sync(0xffffffffu, r, 8);
-    r += __shfl_xor_sync(0xffffffffu, r, 4);
-    r += __shfl_xor_sync(0xffffffffu, r, 2);
-    r += __shfl_xor_sync(0xffffffffu, r, 1);
-    return r;
 }
 
 // dacc layout written here (DACC_MOMENTS): 0 sum t dx, 1 sum t dy, 2 sum t dx^2, 3 sum t dx dy, 4 sum t dy^2,

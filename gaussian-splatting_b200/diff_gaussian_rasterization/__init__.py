@@ -290,6 +290,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 torch.save([a.detach().cpu() if a is not None else None for a in args], "snapshot_fw.dump")
                 print("\nAn error occured in forward. Writing snapshot_fw.dump for debugging.")
             raise
+        ctx.set_materialize_grads(False)   # an unused inverse-depth output reaches backward as None, not zeros
         ctx.raster_settings = raster_settings
         ctx.pack = pack
         ctx.shapes = dict(means2D=None if means2D is None else tuple(means2D.shape), opacities=tuple(opacities.shape),
@@ -319,6 +320,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         else:
             grads["scales"] = new(P, 3)
             grads["rotations"] = new(P, 4)
+        if grad_out_color is None and grad_out_depth is None:
+            return (None,) * 9
         gc = _f32c(grad_out_color)
         if gc is None:
             gc = torch.zeros((3, int(rs.image_height), int(rs.image_width)), dtype=torch.float32, device=dev)
