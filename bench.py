@@ -289,8 +289,8 @@ def main():
         if a.api == "views":
             def loss_fn(img, _invdepth, i):
                 gt = gt_host[i].to(dev, non_blocking=True) if host_inputs else gt_dev[i]
-                return (img - gt).abs().mean()
-            out = render_views_backward(HostCams() if host_inputs else cams, pc, pipe, bg, loss_fn)
+                return dgr.l1_loss_and_grad(img, gt)      # fused L1 (train.py:120) + gradient, one kernel
+            out = render_views_backward(HostCams() if host_inputs else cams, pc, pipe, bg, loss_fn, loss_returns_grad=True)
             total = out["losses"].sum()
         else:
             total = torch.zeros((), device=dev)

@@ -384,6 +384,15 @@ int32_t gsb_mark_visible(int32_t P, const float *means3D, const float *viewmatri
     return launch_mark_visible(P, means3D, viewmatrix, present, static_cast<cudaStream_t>(cuda_stream));
 }
 
+int32_t gsb_l1_loss_grad(const float *image, const float *target, int64_t n, float scale, float *grad_out,
+                         float *loss_accum, void *cuda_stream) {
+    if (n < 0 || (n > 0 && (!image || !target || !grad_out || !loss_accum))) {
+        set_error("gsb_l1_loss_grad: bad argument");
+        return GSB_ERR_ARGUMENT;
+    }
+    return launch_l1_loss_grad(image, target, n, scale, grad_out, loss_accum, static_cast<cudaStream_t>(cuda_stream));
+}
+
 int32_t gsb_sort_pairs(uint32_t *keys, uint32_t *vals, int64_t n, int32_t begin_bit, int32_t end_bit,
                        gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream) {
     if (n < 0 || (n > 0 && (!keys || !vals)) || !alloc || begin_bit < 0 || end_bit > 32 || begin_bit > end_bit) {

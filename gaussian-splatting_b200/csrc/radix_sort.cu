@@ -264,13 +264,26 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
         *my = cnt | OS_FLAG_PREFIX;
     } else {
         *my = cnt | OS_FLAG_AGG;
+        // Walk back over the predecessors' status words, eight loads in flight at a time: with ~300 blocks resident
+        // most predecessors only show an aggregate, so the walk is long and must not be one L2 round trip per step.
         int64_t pb = (int64_t)b - 1;
-        while (true) {
-            uint32_t v;
-            do { v = status[(size_t)pb * RADIX + tid]; } while ((v >> 30) == 0u);
-            excl += v & OS_VALUE_MASK;
-            if ((v >> 30) == 2u) break;
-            --pb;
+        bool found = false;
+        while (!found) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t q = pb - u;
+                v[u] = q >= 0 ? status[(size_t)q * RADIX + tid] : OS_FLAG_PREFIX;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (!found) {
+                    while ((v[u] >> 30) == 0u) v[u] = status[(size_t)(pb - u) * RADIX + tid];
+                    excl += v[u] & OS_VALUE_MASK;
+                    found = (v[u] >> 30) == 2u;
+                }
+            }
+            pb -= 8;
         }
         *my = ((excl + cnt) & OS_VALUE_MASK) | OS_FLAG_PREFIX;
     }

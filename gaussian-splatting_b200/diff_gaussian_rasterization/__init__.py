@@ -71,6 +71,8 @@ def _load():
     lib.gsb_mark_visible.argtypes = [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.gsb_sort_pairs.restype = c_int32
     lib.gsb_sort_pairs.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, _ALLOC_FN, c_void_p, c_void_p]
+    lib.gsb_l1_loss_grad.restype = c_int32
+    lib.gsb_l1_loss_grad.argtypes = [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p]
     lib.gsb_last_error.restype = c_char_p
     lib.gsb_abi_version.restype = c_int32
     lib.gsb_launch_count.restype = c_int64
@@ -122,6 +124,21 @@ def state_views(pack: dict, height: int, width: int):
     num_tiles = int(pack["state"].num_tiles)
     ranges = binning[al(pl_bytes):al(pl_bytes) + num_tiles * 8].view(torch.int32).view(num_tiles, 2)
     return dict(final_T=final_T, n_contrib=n_contrib, point_list=point_list, ranges=ranges)
+
+
+def l1_loss_and_grad(image: torch.Tensor, target: torch.Tensor, loss_accum: Optional[torch.Tensor] = None):
+    """mean |clamp(image,0,1) - target| and its gradient w.r.t. `image`, in one kernel.  Returns (loss, grad);
+    `loss` is `loss_accum` (a 1-element float32 tensor that is ADDED to) or a fresh scalar tensor."""
+    img, gt = _f32c(image), _f32c(target)
+    n = img.numel()
+    grad = torch.empty_like(img)
+    if loss_accum is None:
+        loss_accum = torch.zeros(1, dtype=torch.float32, device=img.device)
+    with torch.cuda.device(img.device):
+        rc = _C.gsb_l1_loss_grad(img.data_ptr(), gt.data_ptr(), n, 1.0 / n, grad.data_ptr(), loss_accum.data_ptr(),
+                                 torch.cuda.current_stream(img.device).cuda_stream)
+    _check(rc)
+    return loss_accum, grad
 
 
 class _Arena:

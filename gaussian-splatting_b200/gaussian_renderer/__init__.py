@@ -118,7 +118,7 @@ def _settings_for(cam, pc, pipe, bg_color, scaling_modifier):
 
 def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch.Tensor, loss_fn, *,
                           scaling_modifier: float = 1.0, densify_stats: Optional[dict] = None,
-                          keep_images: bool = False) -> dict:
+                          keep_images: bool = False, loss_returns_grad: bool = False) -> dict:
     """Fused view-batch training step: forward + loss + backward for every camera, with the per-gaussian
     gradients of ALL views summed in place.
 
@@ -129,7 +129,9 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
     rasterizer's inputs already ARE leaves whose ``.grad`` is set (GradientBucket), the kernels accumulate
     directly into ``.grad`` and no extra pass over the 59 floats/gaussian is made.
 
-    ``loss_fn(image[3,H,W] (clamped to [0,1] like render() does), invdepth[1,H,W], view_index) -> scalar``.
+    ``loss_fn(image[3,H,W] (clamped to [0,1] like render() does), invdepth[1,H,W], view_index) -> scalar``, or,
+    with ``loss_returns_grad=True``, ``loss_fn(raw_image, invdepth, view_index) -> (loss, dL/d raw_image[, dL/d invdepth])``
+    for a loss that brings its own gradient (e.g. ``diff_gaussian_rasterization.l1_loss_and_grad``); no autograd then.
     Returns {"losses": [V] tensor, "radii_max": [P] int32, "images": list (if keep_images)}; nothing in here
     synchronises with the host except the one instance-count read-back per forward.
     """
@@ -156,13 +158,18 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
         rs = _settings_for(cam, pc, pipe, bg_color, scaling_modifier)
         color, radii, invdepth, pack = _dgr._forward_impl(c["means3D"], c["shs"], None, c["opacities"], c["scales"],
                                                           c["rotations"], None, rs)
-        img = color.requires_grad_(True)
-        dep = invdepth.requires_grad_(True)
-        with torch.enable_grad():
-            loss = loss_fn(img.clamp(0, 1), dep, vi)
-        g_img, g_dep = torch.autograd.grad(loss, (img, dep), allow_unused=True)
-        if g_img is None:
-            g_img = torch.zeros_like(color)
+        if loss_returns_grad:
+            res = loss_fn(color, invdepth, vi)
+            loss, g_img = res[0], res[1]
+            g_dep = res[2] if len(res) > 2 else None
+        else:
+            img = color.requires_grad_(True)
+            dep = invdepth.requires_grad_(True)
+            with torch.enable_grad():
+                loss = loss_fn(img.clamp(0, 1), dep, vi)
+            g_img, g_dep = torch.autograd.grad(loss, (img, dep), allow_unused=True)
+            if g_img is None:
+                g_img = torch.zeros_like(color)
         vg = dict(grads)
         if densify_stats is not None:
             vg["means2D"] = m2d
@@ -175,7 +182,7 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
             vis = radii > 0
             densify_stats["xyz_gradient_accum"] += (m2d[:, :2].norm(dim=-1, keepdim=True) * vis[:, None])
             densify_stats["denom"] += vis[:, None].to(densify_stats["denom"].dtype)
-        losses.append(loss.detach())
+        losses.append(loss.detach().reshape(()).clone() if loss_returns_grad else loss.detach())
         if keep_images:
             images.append(color.detach())
     # chain the summed gradient into non-leaf inputs' graphs (one pass, view independent)

@@ -145,6 +145,12 @@ int32_t gsb_mark_visible(int32_t P, const float *means3D, const float *viewmatri
 int32_t gsb_sort_pairs(uint32_t *keys, uint32_t *vals, int64_t n, int32_t begin_bit, int32_t end_bit,
                        gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream);
 
+/* Fused L1 photometric loss of the step after the path (train.py:120-126 with render()'s clamp,
+ * gaussian_renderer/__init__.py:119): *loss_accum += scale * sum |clamp(image,0,1) - target| and
+ * grad_out = d(that)/d(image).  n (elements) must be a multiple of 4; pointers 16-byte aligned. */
+int32_t gsb_l1_loss_grad(const float *image, const float *target, int64_t n, float scale, float *grad_out,
+                         float *loss_accum, void *cuda_stream);
+
 const char *gsb_last_error(void);
 int32_t gsb_abi_version(void);
 /* number of kernels this library has launched in this process since the last reset */
