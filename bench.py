@@ -125,7 +125,7 @@ class Pipe:
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -137,7 +137,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -146,7 +146,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark(self, which):
+        """start / end of the timed region (wall clock): only samples taken inside it are reported."""
+        setattr(self, "t_" + which, time.time())
 
     def stop(self):
         if not self.proc:
@@ -158,7 +162,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0, t1 = getattr(self, "t_start", 0.0), getattr(self, "t_end", float("inf"))
+        inside = [ln for (ts, ln) in self.lines if t0 <= ts <= t1 + 0.15]
+        for ln in (inside if inside else [ln for (_ts, ln) in self.lines[-3:]]):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -327,15 +333,21 @@ def main():
         return float(ms.item())
 
     # ---- device-resident leg ----
-    for _ in range(max(a.warmup, 3)):
-        step(False)
+    # the sampler starts BEFORE the warm-up: nvidia-smi's own start-up disturbs the driver for a second or two
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(a.warmup, 3)):
+        step(False)
+    torch.cuda.synchronize()
+    if rank == 0:
+        time.sleep(1.0)
     dgr.set_option("time_kernels", 1)
     dgr.kernel_time("", reset=True)
     dgr.reset_launch_count()
+    sampler.mark("start")
     ms_total = timed(False, a.steps)
+    sampler.mark("end")
     launches = dgr.launch_count()
     bwd_ms, bwd_n = dgr.kernel_time("render_bwd")
     fwd_ms, fwd_n = dgr.kernel_time("render_fwd", reset=True)

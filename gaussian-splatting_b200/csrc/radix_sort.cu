@@ -164,7 +164,9 @@ sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__rest
 // Blocks take a ticket from an atomic counter, so a block only ever waits for blocks that started before
 // it: forward progress does not depend on the hardware's block scheduling order.
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t OS_FLAG_AGG = 1u << 30, OS_FLAG_PREFIX = 2u << 30, OS_VALUE_MASK = (1u << 30) - 1u;
+#define OS_FLAG_AGG (1u << 30)
+#define OS_FLAG_PREFIX (2u << 30)
+#define OS_VALUE_MASK ((1u << 30) - 1u)
 constexpr int OS_MAX_PASSES = 4;
 
 struct OnesweepPasses {
