@@ -124,59 +124,88 @@ class Pipe:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region.  In-process NVML (nvidia_ml_py) every 100 ms:
+    an external `nvidia-smi -lms` loop was measured to stall kernel launches (the device-resident leg ran 2-3x
+    slower than the end-to-end leg whenever it was polling), so it is only the fallback, at 500 ms."""
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.lines = []
+        self.samples = []          # (wall time, sm_mhz, sm_max_mhz, reasons bitmask or list)
+        self.thread = None
         self.proc = None
+        self.stop_flag = False
+        self.t_start, self.t_end = 0.0, float("inf")
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        try:
+                            r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.samples.append((time.time(), float(sm), float(mx), int(r)))
+                    except Exception:
+                        pass
+                    time.sleep(0.1)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.kind = "nvml"
+        except Exception:
+            self._start_smi()
+
+    def _start_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "500",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+
+            def read():
+                for line in self.proc.stdout:
+                    f = [x.strip() for x in line.split(",")]
+                    try:
+                        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                        rs = [n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")]
+                        self.samples.append((time.time(), float(f[0]), float(f[1]), rs))
+                    except Exception:
+                        pass
+            self.thread = threading.Thread(target=read, daemon=True)
+            self.thread.start()
+            self.kind = "nvidia-smi"
+        except Exception:
+            self.kind = "unavailable"
 
     def mark(self, which):
         """start / end of the timed region (wall clock): only samples taken inside it are reported."""
         setattr(self, "t_" + which, time.time())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        t0, t1 = getattr(self, "t_start", 0.0), getattr(self, "t_end", float("inf"))
-        inside = [ln for (ts, ln) in self.lines if t0 <= ts <= t1 + 0.15]
-        for ln in (inside if inside else [ln for (_ts, ln) in self.lines[-3:]]):
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        inside = [s for s in self.samples if self.t_start <= s[0] <= self.t_end + 0.05] or self.samples[-2:]
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sample"], "source": getattr(self, "kind", "?")}
+        reasons = set()
+        # NVML bit masks (nvml.h): 0x8 hw_slowdown, 0x40 hw_thermal, 0x20 sw_thermal, 0x4 sw_power_cap
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        for s in inside:
+            if isinstance(s[3], int):
+                reasons |= {n for b, n in bits.items() if s[3] & b}
+            else:
+                reasons |= set(s[3])
+        return {"sm_mhz": statistics.median(s[1] for s in inside), "sm_max_mhz": max(s[2] for s in inside),
+                "reasons": sorted(reasons), "samples": len(inside), "source": getattr(self, "kind", "?")}
 
 
 def cpu_reference_pass(scene, cam_settings, repeats):
