@@ -366,11 +366,12 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(a.warmup, 3)):
+    # untimed warm-up: at least 3 steps (contract) and at least 5 so that buffer sizes / the caching allocator settle
+    for _ in range(max(a.warmup, 5)):
         step(False)
     torch.cuda.synchronize()
     if rank == 0:
-        time.sleep(1.0)
+        time.sleep(0.5)
     dgr.set_option("time_kernels", 1)
     dgr.kernel_time("", reset=True)
     dgr.reset_launch_count()

@@ -142,22 +142,42 @@ def l1_loss_and_grad(image: torch.Tensor, target: torch.Tensor, loss_accum: Opti
 
 
 class _Arena:
-    """Hands torch-owned device memory to the library (torch caching allocator)."""
+    """Hands torch-owned device memory to the library (torch caching allocator).
 
-    def __init__(self, device):
+    State buffers (GEOM / BINNING / IMAGE) are fresh tensors: they live until the backward pass.  SCRATCH buffers
+    are only used by kernels enqueued during the call, on the caller's stream, so one grow-only tensor per
+    (device, stream, class) is reused across calls: stream order makes that safe, and it keeps the allocator out
+    of the steady-state loop (view-dependent sizes otherwise keep triggering cudaMalloc for tens of steps)."""
+    _scratch = {}
+
+    def __init__(self, device, stream=None):
         self.device = device
+        self.stream = stream
         self.bufs = {}
         self.error = None
         self.cb = _ALLOC_FN(self._alloc)
 
     def _alloc(self, _ctx, which, nbytes):
         try:
-            t = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-            self.bufs[int(which)] = t
+            which, nbytes = int(which), int(nbytes)
+            if which >= 3 and self.stream is not None:
+                key = (self.device.index, self.stream, which)
+                t = _Arena._scratch.get(key)
+                if t is None or t.numel() < nbytes:
+                    t = torch.empty(max(nbytes, int(nbytes * 1.25)), dtype=torch.uint8, device=self.device)
+                    _Arena._scratch[key] = t
+            else:
+                t = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.bufs[which] = t
             return t.data_ptr()
         except Exception as e:  # never let an exception cross the C ABI
             self.error = e
             return None
+
+
+def release_scratch():
+    """Drop the cached scratch buffers (e.g. before torch.cuda.empty_cache())."""
+    _Arena._scratch.clear()
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -245,15 +265,18 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         invdepth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
-        arena = _Arena(dev)
-        st = _State()
         stream = torch.cuda.current_stream(dev).cuda_stream
+        arena = _Arena(dev, stream)
+        st = _State()
         hkey = (P, H, W, dev.index)
         hint = _capacity_hints.get(hkey, 0) if speculative_binning else 0
         rc = _C.gsb_forward(byref(cs), byref(ci), color.data_ptr(), radii.data_ptr(), invdepth.data_ptr(), hint,
                             arena.cb, None, byref(st), stream)
         _check(rc, arena)
-        _capacity_hints[hkey] = int(st.num_rendered * 1.25) + 65536
+        # next estimate: this count + 25 %, rounded up to 1 Mi instances and never shrinking, so that buffer sizes
+        # settle after the first few views instead of following every view's own count
+        want = ((int(st.num_rendered * 1.25) + 65536 + (1 << 20) - 1) >> 20) << 20
+        _capacity_hints[hkey] = max(want, _capacity_hints.get(hkey, 0))
     pack = dict(state=st, geom=arena.bufs.get(BUF_GEOM), binning=arena.bufs.get(BUF_BINNING),
                 image=arena.bufs.get(BUF_IMAGE), num_rendered=int(st.num_rendered), sh_coeffs=M)
     return color, radii, invdepth, pack
@@ -278,8 +301,8 @@ def _backward_impl(pack, rs, means3D, sh, colors_precomp, opacities, scales, rot
         g.dL_dopacities = _ptr(grads.get("opacities"))
         g.dL_dscales, g.dL_drotations = _ptr(grads.get("scales")), _ptr(grads.get("rotations"))
         g.dL_dcov3D = _ptr(grads.get("cov3D_precomp"))
-        arena = _Arena(dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
+        arena = _Arena(dev, stream)
         rc = _C.gsb_backward(byref(cs), byref(ci), byref(pack["state"]), out_color.data_ptr(), out_invdepth.data_ptr(),
                              grad_color.data_ptr(), _ptr(grad_invdepth), byref(g), int(bool(accumulate)), arena.cb,
                              None, stream)

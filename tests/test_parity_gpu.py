@@ -200,7 +200,7 @@ def test_speculative_capacity_repair_path():
     b = U.run_cuda(args, cam, wc, wd)                 # speculative path, estimate large enough
     dgr._capacity_hints[key] = 100                    # far too small: forces the repair
     c = U.run_cuda(args, cam, wc, wd)
-    assert dgr._capacity_hints[key] == big
+    assert dgr._capacity_hints[key] == big            # re-learned from the true count
     for other in (b, c):
         assert np.array_equal(a["color"], other["color"]) and np.array_equal(a["radii"], other["radii"])
         for k, v in a["grads"].items():
