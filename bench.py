@@ -311,20 +311,36 @@ def main():
     gt_dev = [g.to(dev) for g in gt_host]
     mpix_step = V * world * H * W / 1e6
 
-    class HostCams:
-        """e2e leg: a camera's tensors are uploaded from pinned host memory when the view comes up."""
+    # e2e leg: per-view host inputs.  The 24.9 MB target image of view i is copied from pinned memory on a side
+    # stream into one of two staging buffers when view i STARTS, so the copy overlaps that view's forward kernels;
+    # the loss kernel waits for it through an event.  Camera matrices (140 B) go on the compute stream.
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [torch.empty(3, H, W, device=dev) for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    for e in consumed:
+        e.record()
 
+    class HostCams:
         def __iter__(self):
-            for cam in cams:
+            for i, cam in enumerate(cams):
                 cam.upload(dev)
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[i % 2])          # the loss kernel two views ago is done with it
+                    stage[i % 2].copy_(gt_host[i], non_blocking=True)
+                    copied[i % 2].record(copy_stream)
                 yield cam
 
     def step(host_inputs: bool):
         bucket.zero_()
         if a.api == "views":
             def loss_fn(img, _invdepth, i):
-                gt = gt_host[i].to(dev, non_blocking=True) if host_inputs else gt_dev[i]
-                return dgr.l1_loss_and_grad(img, gt)      # fused L1 (train.py:120) + gradient, one kernel
+                if host_inputs:
+                    torch.cuda.current_stream(dev).wait_event(copied[i % 2])
+                    res = dgr.l1_loss_and_grad(img, stage[i % 2])   # fused L1 (train.py:120) + gradient, one kernel
+                    consumed[i % 2].record()
+                    return res
+                return dgr.l1_loss_and_grad(img, gt_dev[i])
             out = render_views_backward(HostCams() if host_inputs else cams, pc, pipe, bg, loss_fn, loss_returns_grad=True)
             total = out["losses"].sum()
         else:
