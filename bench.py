@@ -44,7 +44,7 @@ LOG_SCALE_MEAN = -5.3   # mean reference tiles-touched per visible gaussian ~= 7
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--views-per-rank", type=int, default=8)
@@ -360,19 +360,24 @@ def main():
             return float(total.item())   # device -> host read of the step's result
         return None
 
+    step_stats = {}
+
     def timed(host_inputs: bool, steps: int):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        marks[0].record()
+        for k in range(steps):
             step(host_inputs)
-        e1.record()
+            marks[k + 1].record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        per_step = [marks[k].elapsed_time(marks[k + 1]) for k in range(steps)]
+        step_stats[host_inputs] = {"min": round(min(per_step), 3), "median": round(statistics.median(per_step), 3),
+                                   "max": round(max(per_step), 3)}
+        ms = torch.tensor([marks[0].elapsed_time(marks[steps])], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
@@ -383,7 +388,7 @@ def main():
     if rank == 0:
         sampler.start()
     # untimed warm-up: at least 3 steps (contract) and at least 5 so that buffer sizes / the caching allocator settle
-    for _ in range(max(a.warmup, 5)):
+    for _ in range(max(a.warmup, 8)):
         step(False)
     torch.cuda.synchronize()
     if rank == 0:
@@ -491,7 +496,8 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": workload_config(a, world), "roofline": roofline,
             "cpu_baseline": cpu, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                                          "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
-            "gpu_launches": launches, "clocks": clocks, "scene_stats": stats, "kernel_ms_per_view": breakdown}
+            "gpu_launches": launches, "clocks": clocks,
+            "step_ms": {"resident": step_stats.get(False), "e2e": step_stats.get(True)}, "scene_stats": stats, "kernel_ms_per_view": breakdown}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
