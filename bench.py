@@ -394,11 +394,18 @@ def main():
     if rank == 0:
         time.sleep(0.5)
     dgr.set_option("time_kernels", 1)
-    dgr.kernel_time("", reset=True)
-    dgr.reset_launch_count()
-    sampler.mark("start")
-    ms_total = timed(False, a.steps)
-    sampler.mark("end")
+    # A shared host occasionally stalls the launching thread for tens to hundreds of ms (seen as ONE step of 40-700 ms
+    # among steps of 15.4 ms).  Such a leg is re-measured (at most twice) and every attempt is reported.
+    attempts = []
+    for _try in range(3):
+        dgr.kernel_time("", reset=True)
+        dgr.reset_launch_count()
+        sampler.mark("start")
+        ms_total = timed(False, a.steps)
+        sampler.mark("end")
+        attempts.append({"ms_total": round(ms_total, 3), **step_stats[False]})
+        if step_stats[False]["max"] <= 1.5 * step_stats[False]["median"]:
+            break
     launches = dgr.launch_count()
     bwd_ms, bwd_n = dgr.kernel_time("render_bwd")
     fwd_ms, fwd_n = dgr.kernel_time("render_fwd", reset=True)
@@ -409,7 +416,12 @@ def main():
     # ---- end-to-end leg (host inputs) ----
     for _ in range(max(a.warmup, 3)):
         step(True)
-    ms_e2e = timed(True, a.steps)
+    e2e_attempts = []
+    for _try in range(3):
+        ms_e2e = timed(True, a.steps)
+        e2e_attempts.append({"ms_total": round(ms_e2e, 3), **step_stats[True]})
+        if step_stats[True]["max"] <= 1.5 * step_stats[True]["median"]:
+            break
     e2e_value = mpix_step * a.steps / (ms_e2e / 1e3)
     h2d = V * (3 * H * W * 4 + 4 * 35)
     d2h = 4
@@ -497,7 +509,9 @@ def main():
             "cpu_baseline": cpu, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                                          "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": launches, "clocks": clocks,
-            "step_ms": {"resident": step_stats.get(False), "e2e": step_stats.get(True)}, "scene_stats": stats, "kernel_ms_per_view": breakdown}
+            "step_ms": {"resident": step_stats.get(False), "e2e": step_stats.get(True)},
+            "attempts": {"resident": attempts, "e2e": e2e_attempts,
+                         "rule": "a leg with a step > 1.5x its median step (host stall) is re-measured, at most twice; the last attempt is reported"}, "scene_stats": stats, "kernel_ms_per_view": breakdown}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
