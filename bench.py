@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--sh-degree", type=int, default=3)
     ap.add_argument("--api", default="views", choices=["views", "render"],
                     help="views: fused view-batch path render_views_backward(); render: per-view render() + autograd")
+    ap.add_argument("--no-batch", action="store_true", help="views API view by view instead of gsb_forward_batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
     return ap.parse_args()
@@ -315,9 +316,10 @@ def main():
     # stream into one of two staging buffers when view i STARTS, so the copy overlaps that view's forward kernels;
     # the loss kernel waits for it through an event.  Camera matrices (140 B) go on the compute stream.
     copy_stream = torch.cuda.Stream(device=dev)
-    stage = [torch.empty(3, H, W, device=dev) for _ in range(2)]
-    copied = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
+    NS = V                          # one staging buffer per view of the step (the batched path starts all views at once)
+    stage = [torch.empty(3, H, W, device=dev) for _ in range(NS)]
+    copied = [torch.cuda.Event() for _ in range(NS)]
+    consumed = [torch.cuda.Event() for _ in range(NS)]
     for e in consumed:
         e.record()
 
@@ -326,9 +328,9 @@ def main():
             for i, cam in enumerate(cams):
                 cam.upload(dev)
                 with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(consumed[i % 2])          # the loss kernel two views ago is done with it
-                    stage[i % 2].copy_(gt_host[i], non_blocking=True)
-                    copied[i % 2].record(copy_stream)
+                    copy_stream.wait_event(consumed[i % NS])         # last step's loss kernel is done with the buffer
+                    stage[i % NS].copy_(gt_host[i], non_blocking=True)
+                    copied[i % NS].record(copy_stream)
                 yield cam
 
     def step(host_inputs: bool):
@@ -336,12 +338,13 @@ def main():
         if a.api == "views":
             def loss_fn(img, _invdepth, i):
                 if host_inputs:
-                    torch.cuda.current_stream(dev).wait_event(copied[i % 2])
-                    res = dgr.l1_loss_and_grad(img, stage[i % 2])   # fused L1 (train.py:120) + gradient, one kernel
-                    consumed[i % 2].record()
+                    torch.cuda.current_stream(dev).wait_event(copied[i % NS])
+                    res = dgr.l1_loss_and_grad(img, stage[i % NS])  # fused L1 (train.py:120) + gradient, one kernel
+                    consumed[i % NS].record()
                     return res
                 return dgr.l1_loss_and_grad(img, gt_dev[i])
-            out = render_views_backward(HostCams() if host_inputs else cams, pc, pipe, bg, loss_fn, loss_returns_grad=True)
+            out = render_views_backward(HostCams() if host_inputs else cams, pc, pipe, bg, loss_fn, loss_returns_grad=True,
+                                        batched=not a.no_batch)
             total = out["losses"].sum()
         else:
             total = torch.zeros((), device=dev)

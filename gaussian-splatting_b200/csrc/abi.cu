@@ -62,7 +62,7 @@ static unsigned long long *pinned_slot() {
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     if (!slots[dev]) {
         void *p = nullptr;
-        if (cudaHostAlloc(&p, 64, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+        if (cudaHostAlloc(&p, 256, cudaHostAllocDefault) != cudaSuccess) return nullptr;
         slots[dev] = static_cast<unsigned long long *>(p);
     }
     return slots[dev];
@@ -241,6 +241,8 @@ int32_t gsb_forward(const GsbSettings *s, const GsbInputs *in, float *out_color,
     BinArgs ba;
     ba.P = P; ba.num_tiles = num_tiles; ba.gx = cam.gx; ba.order = idx; ba.tiles = tiles; ba.rect = rect; ba.splat = splat;
     ba.offsets = offsets; ba.partials = partials; ba.total = total;
+    ba.sv_gauss = 0; ba.sv_splat = 0; ba.sv_partials = 0; ba.sv_inst = 0;
+    st->splat = splat; st->final_T = iv.final_T; st->n_contrib = iv.n_contrib;
 
     // binning + blend for an instance capacity `cap`; the true count is read by the kernels from *n_dev when given
     BinningView bv;
@@ -250,6 +252,7 @@ int32_t gsb_forward(const GsbSettings *s, const GsbInputs *in, float *out_color,
         st->binning = do_alloc(alloc, alloc_ctx, GSB_BUF_BINNING, st->binning_bytes);
         if (!st->binning) return GSB_ERR_ALLOC;
         carve_binning(st->binning, cap, num_tiles, bv);
+        st->point_list = bv.point_list; st->ranges = bv.ranges;
         int r;
         if (cap > 0 && P > 0) {
             const size_t Dn = (size_t)cap;
@@ -260,14 +263,14 @@ int32_t gsb_forward(const GsbSettings *s, const GsbInputs *in, float *out_color,
             Carver c1r(scr1);
             uint32_t *inst_tile = c1r.take<uint32_t>(Dn), *inst_tile_alt = c1r.take<uint32_t>(Dn), *inst_gauss_alt = c1r.take<uint32_t>(Dn);
             char *sortscr1 = c1r.take<char>(sort_scratch_bytes(cap));
-            r = launch_emit(ba, inst_tile, bv.point_list, cap, debug, stream);
+            r = launch_emit(ba, 1, inst_tile, bv.point_list, cap, debug, stream);
             if (r) return r;
             r = sort_pairs(inst_tile, bv.point_list, inst_tile_alt, inst_gauss_alt, cap, n_dev, 0, tile_bits, sortscr1, debug, stream);
             if (r) return r;
-            r = launch_tile_ranges(inst_tile, cap, n_dev, num_tiles, bv.ranges, debug, stream);
+            r = launch_tile_ranges(inst_tile, cap, n_dev, num_tiles, bv.ranges, 1, 0, debug, stream);
             if (r) return r;
         } else {
-            r = launch_tile_ranges(nullptr, 0, nullptr, num_tiles, bv.ranges, debug, stream);
+            r = launch_tile_ranges(nullptr, 0, nullptr, num_tiles, bv.ranges, 1, 0, debug, stream);
             if (r) return r;
         }
         RenderFwdArgs ra;
@@ -291,7 +294,7 @@ int32_t gsb_forward(const GsbSettings *s, const GsbInputs *in, float *out_color,
         // gaussians by depth (culled ones carry key 0xffffffff and sort to the end)
         rc = sort_pairs(key, idx, key_alt, idx_alt, P, nullptr, 0, 32, sortscr, debug, stream);
         if (rc) return rc;
-        rc = launch_tile_scan(ba, debug, stream);
+        rc = launch_tile_scan(ba, 1, debug, stream);
         if (rc) return rc;
         // The instance count D sizes the binning buffers, so it has to reach the host: ONE read-back per forward.
         unsigned long long *h = pinned_slot();
@@ -341,7 +344,7 @@ int32_t gsb_backward(const GsbSettings *s, const GsbInputs *in, const GsbState *
     rc = check_inputs(s, in);
     if (rc) return rc;
     const int P = in->P;
-    if (P != st->P || st->num_tiles != cam.gx * cam.gy || !st->geom || !st->binning || !st->image) {
+    if (P != st->P || st->num_tiles != cam.gx * cam.gy || !st->splat || !st->ranges || !st->final_T) {
         set_error("gsb_backward: state does not match the inputs (P %d vs %d)", P, st->P);
         return GSB_ERR_ARGUMENT;
     }
@@ -352,16 +355,14 @@ int32_t gsb_backward(const GsbSettings *s, const GsbInputs *in, const GsbState *
     if (!dacc) return GSB_ERR_ALLOC;
     GSB_CUDA(cudaMemsetAsync(dacc, 0, dacc_bytes, stream));
 
-    ImageView iv;
-    carve_image(st->image, npix, iv);
-    BinningView bv;
-    carve_binning(st->binning, st->binning_capacity, st->num_tiles, bv);
-    const float4 *splat = static_cast<const float4 *>(st->geom);
+    (void)npix;
+    const float4 *splat = static_cast<const float4 *>(st->splat);
 
     if (st->num_rendered > 0) {
         RenderBwdArgs ra;
-        ra.W = cam.W; ra.H = cam.H; ra.gx = cam.gx; ra.gy = cam.gy; ra.ranges = bv.ranges; ra.point_list = bv.point_list;
-        ra.splat = splat; ra.bg = s->bg; ra.final_T = iv.final_T; ra.n_contrib = iv.n_contrib; ra.dL_dcolor = dL_dcolor;
+        ra.W = cam.W; ra.H = cam.H; ra.gx = cam.gx; ra.gy = cam.gy; ra.ranges = static_cast<const uint2 *>(st->ranges);
+        ra.point_list = st->point_list;
+        ra.splat = splat; ra.bg = s->bg; ra.final_T = st->final_T; ra.n_contrib = st->n_contrib; ra.dL_dcolor = dL_dcolor;
         ra.dL_dinvdepth = dL_dinvdepth; ra.dacc = dacc; ra.out_color = out_color; ra.out_invdepth = out_invdepth;
         rc = opt_bwd_variant == 5 ? launch_render_bwd_ps(ra, debug, stream) : opt_bwd_variant >= 2 ? launch_render_bwd_mp(ra, opt_bwd_variant == 3 ? 4 : (opt_bwd_variant == 4 ? -2 : 2), debug, stream)
                                   : launch_render_bwd(ra, opt_bwd_variant, debug, stream);
@@ -372,6 +373,232 @@ int32_t gsb_backward(const GsbSettings *s, const GsbInputs *in, const GsbState *
     pa.cov_pre = in->cov3D_precomp; pa.splat = splat; pa.dacc = dacc; pa.g = *grads;
     pa.moments = opt_bwd_variant >= 2 ? 1 : 0;
     return launch_preprocess_bwd(cam, pa, accumulate != 0, debug, stream);
+}
+
+
+static int run_render_fwd(const RenderFwdArgs &ra, bool debug, cudaStream_t stream) {
+    if (opt_fwd_variant == 5) return launch_render_fwd_ps(ra, debug, stream);
+    return (opt_fwd_variant == 2 || opt_fwd_variant == 3) ? launch_render_fwd_mp(ra, opt_fwd_variant == 3 ? 4 : 2, debug, stream)
+                                                          : launch_render_fwd(ra, opt_fwd_variant, debug, stream);
+}
+
+static int run_render_bwd(const RenderBwdArgs &ra, bool debug, cudaStream_t stream) {
+    return opt_bwd_variant == 5 ? launch_render_bwd_ps(ra, debug, stream)
+           : opt_bwd_variant >= 2 ? launch_render_bwd_mp(ra, opt_bwd_variant == 3 ? 4 : (opt_bwd_variant == 4 ? -2 : 2), debug, stream)
+                                  : launch_render_bwd(ra, opt_bwd_variant, debug, stream);
+}
+
+static int check_batch(int32_t V, const GsbSettings *s, const GsbInputs *in, CamArgsBatch &cb) {
+    if (V < 1 || V > GSB_MAX_VIEWS) { set_error("view batch: V=%d outside 1..%d", V, GSB_MAX_VIEWS); return GSB_ERR_ARGUMENT; }
+    cb.V = V;
+    for (int v = 0; v < V; ++v) {
+        int rc = make_cam(&s[v], cb.cam[v]);
+        if (rc) return rc;
+        rc = check_inputs(&s[v], in);
+        if (rc) return rc;
+        if (cb.cam[v].W != cb.cam[0].W || cb.cam[v].H != cb.cam[0].H || cb.cam[v].sh_degree != cb.cam[0].sh_degree ||
+            cb.cam[v].sh_coeffs != cb.cam[0].sh_coeffs) {
+            set_error("view batch: all views must share image size and SH configuration");
+            return GSB_ERR_ARGUMENT;
+        }
+    }
+    if (in->colors_precomp || in->cov3D_precomp) {
+        set_error("view batch: precomputed colours / covariances are per view; use the single-view call");
+        return GSB_ERR_ARGUMENT;
+    }
+    return GSB_OK;
+}
+
+int32_t gsb_forward_batch(int32_t V, const GsbSettings *s, const GsbInputs *in, float *out_color, int32_t *out_radii,
+                          float *out_invdepth, int64_t capacity_hint, gsb_alloc_fn alloc, void *alloc_ctx, GsbState *states,
+                          void *cuda_stream) {
+    if (!s || !in || !out_color || !out_radii || !out_invdepth || !alloc || !states || in->P <= 0) {
+        set_error("gsb_forward_batch: NULL argument or empty input");
+        return GSB_ERR_ARGUMENT;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    CamArgsBatch cb;
+    int rc = check_batch(V, s, in, cb);
+    if (rc) return rc;
+    const bool debug = s[0].debug != 0;
+    const CamArgs &c0 = cb.cam[0];
+    const int P = in->P;
+    const int num_tiles = c0.gx * c0.gy;
+    const int tile_bits = bits_for((uint32_t)num_tiles);
+    const size_t npix = (size_t)c0.W * c0.H;
+    const size_t Pn = align_up((size_t)P, 64);     // per-view stride of the per-gaussian u32 arrays
+
+    // ---- state buffers, V views each ----
+    const size_t sv_splat = (size_t)P * SPLAT_F4;  // float4
+    const size_t geom_bytes = align_up((size_t)V * sv_splat * sizeof(float4), 256);
+    float4 *splat = static_cast<float4 *>(do_alloc(alloc, alloc_ctx, GSB_BUF_GEOM, geom_bytes));
+    if (!splat) return GSB_ERR_ALLOC;
+    ImageView iv0;
+    const size_t image_bytes = carve_image(nullptr, npix, iv0);
+    char *image = static_cast<char *>(do_alloc(alloc, alloc_ctx, GSB_BUF_IMAGE, (size_t)V * image_bytes));
+    if (!image) return GSB_ERR_ALLOC;
+    for (int v = 0; v < V; ++v) {
+        GsbState *st = &states[v];
+        memset(st, 0, sizeof(*st));
+        st->P = P; st->num_tiles = num_tiles; st->num_visible = -1;
+        st->geom = splat; st->geom_bytes = geom_bytes; st->image = image; st->image_bytes = (size_t)V * image_bytes;
+        st->splat = splat + (size_t)v * sv_splat;
+        ImageView iv;
+        carve_image(image + (size_t)v * image_bytes, npix, iv);
+        st->final_T = iv.final_T; st->n_contrib = iv.n_contrib;
+    }
+
+    // ---- per-gaussian scratch, [V][Pn] ----
+    const size_t np = scan_partials_count(P);
+    uint32_t *key, *idx, *key_alt, *idx_alt, *tiles, *offsets, *partials; uint2 *rect; unsigned long long *total; char *sortscr;
+    auto carve0 = [&](Carver &c) {
+        key = c.take<uint32_t>(V * Pn); idx = c.take<uint32_t>(V * Pn); key_alt = c.take<uint32_t>(V * Pn); idx_alt = c.take<uint32_t>(V * Pn);
+        tiles = c.take<uint32_t>(V * Pn); rect = c.take<uint2>(V * Pn); offsets = c.take<uint32_t>(V * Pn);
+        partials = c.take<uint32_t>(V * np); total = c.take<unsigned long long>(GSB_MAX_VIEWS);
+        sortscr = c.take<char>(sort_scratch_bytes(P, V));
+    };
+    Carver c0n(nullptr);
+    carve0(c0n);
+    void *scr0 = do_alloc(alloc, alloc_ctx, GSB_BUF_SCRATCH0, c0n.bytes());
+    if (!scr0) return GSB_ERR_ALLOC;
+    Carver c0r(scr0);
+    carve0(c0r);
+
+    PreFwdArgs pa;
+    pa.P = P; pa.means = in->means3D; pa.shs = in->shs; pa.colors = nullptr; pa.opac = in->opacities;
+    pa.scales = in->scales; pa.rots = in->rotations; pa.cov_pre = nullptr;
+    pa.splat = splat; pa.depth_key = key; pa.depth_idx = idx; pa.tiles = tiles; pa.rect = rect; pa.radii = out_radii;
+    pa.cull = opt_cull;
+    PreFwdBatchStrides ps;
+    ps.splat = sv_splat; ps.per_gauss = Pn; ps.radii = (size_t)P;
+    rc = launch_preprocess_fwd_batch(cb, pa, ps, debug, stream);
+    if (rc) return rc;
+    rc = sort_pairs(key, idx, key_alt, idx_alt, P, nullptr, 0, 32, sortscr, debug, stream, V, Pn);
+    if (rc) return rc;
+    BinArgs ba;
+    ba.P = P; ba.num_tiles = num_tiles; ba.gx = c0.gx; ba.order = idx; ba.tiles = tiles; ba.rect = rect; ba.splat = splat;
+    ba.offsets = offsets; ba.partials = partials; ba.total = total;
+    ba.sv_gauss = Pn; ba.sv_splat = sv_splat; ba.sv_partials = np; ba.sv_inst = 0;
+    rc = launch_tile_scan(ba, V, debug, stream);
+    if (rc) return rc;
+    unsigned long long *h = pinned_slot();
+    cudaEvent_t ev = readback_event();
+    if (!h || !ev) { set_error("pinned read-back slot unavailable"); return GSB_ERR_CUDA; }
+    GSB_CUDA(cudaMemcpyAsync(h, total, (size_t)V * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    GSB_CUDA(cudaEventRecord(ev, stream));
+
+    auto bin_and_blend = [&](int64_t cap) -> int {
+        // BINNING: [V][cap] point lists, then [V][num_tiles] ranges
+        const size_t capn = (size_t)(cap > 0 ? cap : 1);
+        const size_t pl_bytes = align_up((size_t)V * capn * 4, 256);
+        const size_t bin_bytes = pl_bytes + align_up((size_t)V * num_tiles * sizeof(uint2), 256);
+        char *bin = static_cast<char *>(do_alloc(alloc, alloc_ctx, GSB_BUF_BINNING, bin_bytes));
+        if (!bin) return GSB_ERR_ALLOC;
+        uint32_t *point_list = reinterpret_cast<uint32_t *>(bin);
+        uint2 *ranges = reinterpret_cast<uint2 *>(bin + pl_bytes);
+        for (int v = 0; v < V; ++v) {
+            states[v].binning = bin; states[v].binning_bytes = bin_bytes; states[v].binning_capacity = cap;
+            states[v].point_list = point_list + (size_t)v * capn; states[v].ranges = ranges + (size_t)v * num_tiles;
+        }
+        int r;
+        if (cap > 0) {
+            Carver c1(nullptr);
+            c1.take<uint32_t>(V * capn); c1.take<uint32_t>(V * capn); c1.take<uint32_t>(V * capn); c1.take<char>(sort_scratch_bytes(cap, V));
+            void *scr1 = do_alloc(alloc, alloc_ctx, GSB_BUF_SCRATCH1, c1.bytes());
+            if (!scr1) return GSB_ERR_ALLOC;
+            Carver c1r(scr1);
+            uint32_t *inst_tile = c1r.take<uint32_t>(V * capn), *inst_tile_alt = c1r.take<uint32_t>(V * capn);
+            uint32_t *inst_gauss_alt = c1r.take<uint32_t>(V * capn);
+            char *sortscr1 = c1r.take<char>(sort_scratch_bytes(cap, V));
+            BinArgs bb = ba;
+            bb.sv_inst = capn;
+            r = launch_emit(bb, V, inst_tile, point_list, cap, debug, stream);
+            if (r) return r;
+            r = sort_pairs(inst_tile, point_list, inst_tile_alt, inst_gauss_alt, cap, total, 0, tile_bits, sortscr1, debug, stream, V, capn);
+            if (r) return r;
+            r = launch_tile_ranges(inst_tile, cap, total, num_tiles, ranges, V, capn, debug, stream);
+            if (r) return r;
+        } else {
+            r = launch_tile_ranges(nullptr, 0, nullptr, num_tiles, ranges, V, 0, debug, stream);
+            if (r) return r;
+        }
+        for (int v = 0; v < V; ++v) {
+            RenderFwdArgs ra;
+            ra.W = c0.W; ra.H = c0.H; ra.gx = c0.gx; ra.gy = c0.gy; ra.ranges = static_cast<const uint2 *>(states[v].ranges);
+            ra.point_list = states[v].point_list; ra.splat = static_cast<const float4 *>(states[v].splat); ra.bg = s[v].bg;
+            ra.out_color = out_color + (size_t)v * 3 * npix; ra.out_invdepth = out_invdepth + (size_t)v * npix;
+            ra.final_T = const_cast<float *>(states[v].final_T); ra.n_contrib = const_cast<uint32_t *>(states[v].n_contrib);
+            r = run_render_fwd(ra, debug, stream);
+            if (r) return r;
+        }
+        return GSB_OK;
+    };
+
+    bool blended = false;
+    if (capacity_hint > 0 && capacity_hint < (1ll << 30)) {
+        rc = bin_and_blend(capacity_hint);
+        if (rc) return rc;
+        blended = true;
+    }
+    GSB_CUDA(cudaEventSynchronize(ev));
+    int64_t dmax = 0;
+    for (int v = 0; v < V; ++v) {
+        if (h[v] >= (1ull << 30)) { set_error("instance count %llu exceeds 2^30", h[v]); return GSB_ERR_OVERFLOW; }
+        states[v].num_rendered = (int64_t)h[v];
+        if ((int64_t)h[v] > dmax) dmax = (int64_t)h[v];
+    }
+    if (!blended || dmax > capacity_hint) {
+        rc = bin_and_blend(dmax);
+        if (rc) return rc;
+    }
+    return GSB_OK;
+}
+
+int32_t gsb_backward_batch(int32_t V, const GsbSettings *s, const GsbInputs *in, const GsbState *states, const float *out_color,
+                           const float *out_invdepth, const float *dL_dcolor, const float *dL_dinvdepth, const GsbGrads *grads,
+                           int32_t accumulate, gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream) {
+    if (!s || !in || !states || !out_color || !out_invdepth || !dL_dcolor || !grads || !alloc || in->P <= 0) {
+        set_error("gsb_backward_batch: NULL argument or empty input");
+        return GSB_ERR_ARGUMENT;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    CamArgsBatch cb;
+    int rc = check_batch(V, s, in, cb);
+    if (rc) return rc;
+    const bool debug = s[0].debug != 0;
+    const CamArgs &c0 = cb.cam[0];
+    const int P = in->P;
+    const size_t npix = (size_t)c0.W * c0.H;
+    for (int v = 0; v < V; ++v) {
+        if (states[v].P != P || states[v].num_tiles != c0.gx * c0.gy || !states[v].splat || !states[v].ranges || !states[v].final_T) {
+            set_error("gsb_backward_batch: state %d does not match the inputs", v);
+            return GSB_ERR_ARGUMENT;
+        }
+    }
+    const size_t sv_dacc = (size_t)P * DACC_STRIDE;
+    const size_t dacc_bytes = align_up((size_t)V * sv_dacc * sizeof(float), 256);
+    float *dacc = static_cast<float *>(do_alloc(alloc, alloc_ctx, GSB_BUF_SCRATCH0, dacc_bytes));
+    if (!dacc) return GSB_ERR_ALLOC;
+    GSB_CUDA(cudaMemsetAsync(dacc, 0, dacc_bytes, stream));
+    for (int v = 0; v < V; ++v) {
+        if (states[v].num_rendered <= 0) continue;
+        RenderBwdArgs ra;
+        ra.W = c0.W; ra.H = c0.H; ra.gx = c0.gx; ra.gy = c0.gy; ra.ranges = static_cast<const uint2 *>(states[v].ranges);
+        ra.point_list = states[v].point_list; ra.splat = static_cast<const float4 *>(states[v].splat); ra.bg = s[v].bg;
+        ra.final_T = states[v].final_T; ra.n_contrib = states[v].n_contrib;
+        ra.dL_dcolor = dL_dcolor + (size_t)v * 3 * npix; ra.dL_dinvdepth = dL_dinvdepth ? dL_dinvdepth + (size_t)v * npix : nullptr;
+        ra.dacc = dacc + (size_t)v * sv_dacc; ra.out_color = out_color + (size_t)v * 3 * npix; ra.out_invdepth = out_invdepth + (size_t)v * npix;
+        rc = run_render_bwd(ra, debug, stream);
+        if (rc) return rc;
+    }
+    PreBwdArgs pa;
+    pa.P = P; pa.means = in->means3D; pa.shs = in->shs; pa.opac = in->opacities; pa.scales = in->scales; pa.rots = in->rotations;
+    pa.cov_pre = nullptr; pa.splat = static_cast<const float4 *>(states[0].splat); pa.dacc = dacc; pa.g = *grads;
+    pa.moments = opt_bwd_variant >= 2 ? 1 : 0;
+    PreBwdBatchStrides ps;
+    ps.splat = (size_t)((const float4 *)states[V > 1 ? 1 : 0].splat - (const float4 *)states[0].splat);
+    ps.dacc = sv_dacc; ps.means2D = (size_t)P * 3;
+    return launch_preprocess_bwd_batch(cb, pa, ps, accumulate != 0, debug, stream);
 }
 
 int32_t gsb_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,

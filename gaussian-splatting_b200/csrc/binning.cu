@@ -40,8 +40,9 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(const uint32_t v, u
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_reduce_kernel(const BinArgs a) {
+scan_reduce_kernel(BinArgs a) {
     __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+    a.order += blockIdx.y * a.sv_gauss; a.tiles += blockIdx.y * a.sv_gauss; a.partials += blockIdx.y * a.sv_partials;
     const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_IPT;
     uint32_t s = 0;
 #pragma unroll
@@ -56,8 +57,9 @@ scan_reduce_kernel(const BinArgs a) {
 
 // single block: exclusive scan of the per-chunk totals (64-bit running sum), grand total -> *total
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_partials_kernel(uint32_t *partials, const int n, unsigned long long *total_out) {
+scan_partials_kernel(uint32_t *partials, const int n, unsigned long long *total_out, const size_t sv_partials) {
     __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+    partials += blockIdx.y * sv_partials; total_out += blockIdx.y;
     __shared__ unsigned long long carry_s;
     if (threadIdx.x == 0) carry_s = 0ull;
     __syncthreads();
@@ -76,8 +78,10 @@ scan_partials_kernel(uint32_t *partials, const int n, unsigned long long *total_
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_apply_kernel(const BinArgs a) {
+scan_apply_kernel(BinArgs a) {
     __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+    a.order += blockIdx.y * a.sv_gauss; a.tiles += blockIdx.y * a.sv_gauss; a.partials += blockIdx.y * a.sv_partials;
+    a.offsets += blockIdx.y * a.sv_gauss;
     const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_IPT;
     uint32_t v[SCAN_IPT];
     uint32_t s = 0;
@@ -97,17 +101,21 @@ scan_apply_kernel(const BinArgs a) {
     }
 }
 
-int launch_tile_scan(const BinArgs &a, bool debug, cudaStream_t stream) {
+int launch_tile_scan(const BinArgs &a, int V, bool debug, cudaStream_t stream) {
     const int nchunks = (int)ceil_div(a.P, SCAN_CHUNK);
-    GSB_LAUNCH("scan_reduce", debug, stream, scan_reduce_kernel, nchunks, SCAN_THREADS, 0, a);
-    GSB_LAUNCH("scan_partials", debug, stream, scan_partials_kernel, 1, SCAN_THREADS, 0, a.partials, nchunks, a.total);
-    GSB_LAUNCH("scan_apply", debug, stream, scan_apply_kernel, nchunks, SCAN_THREADS, 0, a);
+    GSB_LAUNCH("scan_reduce", debug, stream, scan_reduce_kernel, dim3(nchunks, V), SCAN_THREADS, 0, a);
+    GSB_LAUNCH("scan_partials", debug, stream, scan_partials_kernel, dim3(1, V), SCAN_THREADS, 0, a.partials, nchunks, a.total,
+               a.sv_partials);
+    GSB_LAUNCH("scan_apply", debug, stream, scan_apply_kernel, dim3(nchunks, V), SCAN_THREADS, 0, a);
     return GSB_OK;
 }
 
 // K3: one thread per depth rank; writes (tile id, gaussian id) for every tile the gaussian's cull ellipse meets.
 __global__ void __launch_bounds__(256)
-emit_kernel(const BinArgs a, uint32_t *__restrict__ inst_tile, uint32_t *__restrict__ inst_gauss, const uint32_t cap) {
+emit_kernel(BinArgs a, uint32_t *__restrict__ inst_tile, uint32_t *__restrict__ inst_gauss, const uint32_t cap) {
+    a.order += blockIdx.y * a.sv_gauss; a.tiles += blockIdx.y * a.sv_gauss; a.rect += blockIdx.y * a.sv_gauss;
+    a.offsets += blockIdx.y * a.sv_gauss; a.splat += blockIdx.y * a.sv_splat;
+    inst_tile += blockIdx.y * a.sv_inst; inst_gauss += blockIdx.y * a.sv_inst;
     const int r = blockIdx.x * 256 + threadIdx.x;
     if (r >= a.P) return;
     const uint32_t g = a.order[r];
@@ -149,16 +157,17 @@ emit_kernel(const BinArgs a, uint32_t *__restrict__ inst_tile, uint32_t *__restr
     }
 }
 
-int launch_emit(const BinArgs &a, uint32_t *inst_tile, uint32_t *inst_gauss, int64_t cap, bool debug, cudaStream_t stream) {
-    GSB_LAUNCH("emit", debug, stream, emit_kernel, (int)ceil_div(a.P, 256), 256, 0, a, inst_tile, inst_gauss, (uint32_t)cap);
+int launch_emit(const BinArgs &a, int V, uint32_t *inst_tile, uint32_t *inst_gauss, int64_t cap, bool debug, cudaStream_t stream) {
+    GSB_LAUNCH("emit", debug, stream, emit_kernel, dim3((int)ceil_div(a.P, 256), V), 256, 0, a, inst_tile, inst_gauss, (uint32_t)cap);
     return GSB_OK;
 }
 
 // K5: ranges[t] = [first, last+1) of tile t in the tile-sorted instance list (ranges pre-zeroed)
 __global__ void __launch_bounds__(256)
 tile_ranges_kernel(const uint32_t *__restrict__ sorted_tiles, int64_t D, const unsigned long long *__restrict__ n_dev,
-                   const int num_tiles, uint2 *ranges) {
-    if (n_dev) D = min((int64_t)*n_dev, D);
+                   const int num_tiles, uint2 *ranges, const size_t sv_inst) {
+    sorted_tiles += blockIdx.y * sv_inst; ranges += (size_t)blockIdx.y * num_tiles;
+    if (n_dev) D = min((int64_t)n_dev[blockIdx.y], D);
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= D) return;
     const uint32_t t = sorted_tiles[i];
@@ -168,10 +177,11 @@ tile_ranges_kernel(const uint32_t *__restrict__ sorted_tiles, int64_t D, const u
 }
 
 int launch_tile_ranges(const uint32_t *sorted_tiles, int64_t D, const unsigned long long *n_dev, int num_tiles,
-                       uint2 *ranges, bool debug, cudaStream_t stream) {
-    GSB_CUDA(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), stream));
+                       uint2 *ranges, int V, size_t sv_inst, bool debug, cudaStream_t stream) {
+    GSB_CUDA(cudaMemsetAsync(ranges, 0, (size_t)V * num_tiles * sizeof(uint2), stream));
     if (D <= 0) return GSB_OK;
-    GSB_LAUNCH("tile_ranges", debug, stream, tile_ranges_kernel, (int)ceil_div(D, 256), 256, 0, sorted_tiles, D, n_dev, num_tiles, ranges);
+    GSB_LAUNCH("tile_ranges", debug, stream, tile_ranges_kernel, dim3((int)ceil_div(D, 256), V), 256, 0, sorted_tiles, D, n_dev,
+               num_tiles, ranges, sv_inst);
     return GSB_OK;
 }
 

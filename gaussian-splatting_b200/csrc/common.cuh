@@ -84,13 +84,15 @@ struct Carver {
 };
 
 // ---- radix sort / scan (radix_sort.cu) ----------------------------------------------------
-size_t sort_scratch_bytes(int64_t n);
+size_t sort_scratch_bytes(int64_t n, int V = 1);
 // Stable LSD sort of pairs on bits [begin_bit, end_bit).  Result is left in (keys, vals);
 // (keys_alt, vals_alt) are ping-pong buffers of the same size; scratch >= sort_scratch_bytes(n).
 // n sizes the launch; if n_dev != NULL the kernels sort min(*n_dev, n) pairs (count known only on the device).
+// V > 1 (view batch): V independent sorts in the same launches; view v's arrays start at base + v * sv elements and
+// n_dev is an array of V counts.
 int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n,
                const unsigned long long *n_dev, int begin_bit, int end_bit, void *scratch, bool debug,
-               cudaStream_t stream);
+               cudaStream_t stream, int V = 1, size_t sv = 0);
 extern int g_sort_variant;
 
 }  // namespace gsb

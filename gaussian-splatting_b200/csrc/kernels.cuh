@@ -9,6 +9,15 @@ namespace gsb {
 //   0,1 mean2D (NDC-scaled)  2,3,4 conic A,B,C  5 opacity  6,7,8 rgb  9 inverse depth  10,11 pad
 constexpr int DACC_STRIDE = 12;
 
+// ---- view-batch variants: per-view arrays are laid out [V][...] with uniform strides (in elements) ----
+constexpr int GSB_MAX_VIEWS = 16;
+struct CamArgsBatch {
+    int V;
+    CamArgs cam[GSB_MAX_VIEWS];
+};
+struct PreFwdBatchStrides { size_t splat /* float4 */, per_gauss /* u32 / uint2 arrays */, radii; };
+struct PreBwdBatchStrides { size_t splat /* float4 */, dacc /* float */, means2D /* float */; };
+
 struct PreFwdArgs {
     int P;
     const float *means, *shs, *colors, *opac, *scales, *rots, *cov_pre;
@@ -33,6 +42,11 @@ struct PreBwdArgs {
 struct BinArgs {
     int P;
     int num_tiles, gx;
+    // view-batch launches (blockIdx.y = view): strides between the views' arrays, in elements; 0 for single view
+    size_t sv_gauss;          // order / tiles / rect / offsets
+    size_t sv_splat;          // float4
+    size_t sv_partials;
+    size_t sv_inst;           // instance arrays (capacity)
     const uint32_t *order;    // [P] gaussian ids in depth order
     const uint32_t *tiles;    // [P]
     const uint2 *rect;        // [P]
@@ -67,13 +81,17 @@ struct RenderBwdArgs {
 
 int launch_preprocess_fwd(const CamArgs &ca, const PreFwdArgs &a, bool debug, cudaStream_t stream);
 int launch_preprocess_bwd(const CamArgs &ca, const PreBwdArgs &a, bool accumulate, bool debug, cudaStream_t stream);
+int launch_preprocess_fwd_batch(const CamArgsBatch &cb, const PreFwdArgs &a, const PreFwdBatchStrides &st, bool debug, cudaStream_t stream);
+int launch_preprocess_bwd_batch(const CamArgsBatch &cb, const PreBwdArgs &a, const PreBwdBatchStrides &st, bool accumulate, bool debug,
+                                cudaStream_t stream);
 int launch_mark_visible(int P, const float *means, const float *view, uint8_t *present, cudaStream_t stream);
 
 size_t scan_partials_count(int P);
-int launch_tile_scan(const BinArgs &a, bool debug, cudaStream_t stream);
-int launch_emit(const BinArgs &a, uint32_t *inst_tile, uint32_t *inst_gauss, int64_t cap, bool debug, cudaStream_t stream);
+// V > 1: blockIdx.y = view, arrays offset by the BinArgs strides; totals / n_dev are arrays of V counts
+int launch_tile_scan(const BinArgs &a, int V, bool debug, cudaStream_t stream);
+int launch_emit(const BinArgs &a, int V, uint32_t *inst_tile, uint32_t *inst_gauss, int64_t cap, bool debug, cudaStream_t stream);
 int launch_tile_ranges(const uint32_t *sorted_tiles, int64_t D, const unsigned long long *n_dev, int num_tiles,
-                       uint2 *ranges, bool debug, cudaStream_t stream);
+                       uint2 *ranges, int V, size_t sv_inst, bool debug, cudaStream_t stream);
 
 int launch_render_fwd(const RenderFwdArgs &a, int variant, bool debug, cudaStream_t stream);
 int launch_render_bwd(const RenderBwdArgs &a, int variant, bool debug, cudaStream_t stream);

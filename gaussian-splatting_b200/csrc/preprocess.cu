@@ -74,19 +74,8 @@ __device__ __forceinline__ void stage_rows_out(float *__restrict__ g, const floa
     }
 }
 
-__global__ void __launch_bounds__(PRE_THREADS)
-preprocess_fwd_kernel(const CamArgs ca, const PreFwdArgs a) {
-    __shared__ CamParams cam;
-    extern __shared__ float sh_rows[];
-    load_cam(ca, cam);
-    const int row0 = blockIdx.x * PRE_THREADS;
-    const int nrows = min(PRE_THREADS, a.P - row0);
-    const int shn = 3 * ca.sh_coeffs;
-    if (a.shs) stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * (ca.sh_degree + 1) * (ca.sh_degree + 1));
-    __syncthreads();
-    const int i = row0 + threadIdx.x;
-    if (i >= a.P) return;
-
+// one gaussian, one view: everything of K1 after the SH row has been staged
+__device__ __forceinline__ void preprocess_fwd_body(const CamParams &cam, const PreFwdArgs &a, const int i, const float *sh_row) {
     // defaults for a culled gaussian
     uint32_t key = 0xffffffffu, ntiles = 0;
     int radius_out = 0;
@@ -142,7 +131,7 @@ preprocess_fwd_kernel(const CamArgs ca, const PreFwdArgs a) {
                     float bas[16];
                     sh_basis(cam.sh_degree, dx * inv, dy * inv, dz * inv, bas);
                     const int nb = (cam.sh_degree + 1) * (cam.sh_degree + 1);
-                    const float *sh = sh_rows + threadIdx.x * sh_row_stride(shn);
+                    const float *sh = sh_row;
                     for (int k = 0; k < nb; ++k) {
                         r += bas[k] * sh[3 * k]; g += bas[k] * sh[3 * k + 1]; b += bas[k] * sh[3 * k + 2];
                     }
@@ -183,6 +172,43 @@ preprocess_fwd_kernel(const CamArgs ca, const PreFwdArgs a) {
     a.radii[i] = radius_out;
 }
 
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_fwd_kernel(const CamArgs ca, const PreFwdArgs a) {
+    __shared__ CamParams cam;
+    extern __shared__ float sh_rows[];
+    load_cam(ca, cam);
+    const int row0 = blockIdx.x * PRE_THREADS;
+    const int nrows = min(PRE_THREADS, a.P - row0);
+    const int shn = 3 * ca.sh_coeffs;
+    if (a.shs) stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * (ca.sh_degree + 1) * (ca.sh_degree + 1));
+    __syncthreads();
+    const int i = row0 + threadIdx.x;
+    if (i >= a.P) return;
+    preprocess_fwd_body(cam, a, i, sh_rows + threadIdx.x * sh_row_stride(shn));
+}
+
+// View-batch K1: the gaussians' parameters (236 B each at SH degree 3, 192 B of it the SH row) are read ONCE and
+// projected through every camera of the batch; per-view outputs are [V][...] arrays with uniform strides.
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_fwd_batch_kernel(const CamArgsBatch cb, const PreFwdArgs a, const PreFwdBatchStrides st) {
+    __shared__ CamParams cams[GSB_MAX_VIEWS];
+    extern __shared__ float sh_rows[];
+    for (int v = 0; v < cb.V; ++v) load_cam(cb.cam[v], cams[v]);
+    const int row0 = blockIdx.x * PRE_THREADS;
+    const int nrows = min(PRE_THREADS, a.P - row0);
+    const int shn = 3 * cb.cam[0].sh_coeffs;
+    if (a.shs) stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * (cb.cam[0].sh_degree + 1) * (cb.cam[0].sh_degree + 1));
+    __syncthreads();
+    const int i = row0 + threadIdx.x;
+    if (i >= a.P) return;
+    for (int v = 0; v < cb.V; ++v) {
+        PreFwdArgs av = a;
+        av.splat += (size_t)v * st.splat; av.depth_key += (size_t)v * st.per_gauss; av.depth_idx += (size_t)v * st.per_gauss;
+        av.tiles += (size_t)v * st.per_gauss; av.rect += (size_t)v * st.per_gauss; av.radii += (size_t)v * st.radii;
+        preprocess_fwd_body(cams[v], av, i, sh_rows + threadIdx.x * sh_row_stride(shn));
+    }
+}
+
 // d basis / d(x,y,z)
 __device__ __forceinline__ void sh_basis_grad(const int deg, const float x, const float y, const float z, float bx[16],
                                               float by[16], float bz[16]) {
@@ -213,38 +239,29 @@ __device__ __forceinline__ void put(float *p, const float v) {
     if (ACC) *p += v; else *p = v;
 }
 
-// K8: per-gaussian chain rule from (mean2D, conic, opacity, rgb, inverse depth) gradients to the inputs.
-template <bool ACC>
-__global__ void __launch_bounds__(PRE_THREADS)
-preprocess_bwd_kernel(const CamArgs ca, const PreBwdArgs a) {
-    __shared__ CamParams cam;
-    extern __shared__ float sh_rows[];
-    load_cam(ca, cam);
-    const int row0 = blockIdx.x * PRE_THREADS;
-    const int nrows = min(PRE_THREADS, a.P - row0);
-    const int shn = 3 * ca.sh_coeffs;
-    const int nb = (ca.sh_degree + 1) * (ca.sh_degree + 1);
-    if (a.shs) stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * nb);
-    __syncthreads();
-    const int i = row0 + threadIdx.x;
-    const bool live = i < a.P;
-    const int M = cam.sh_coeffs;
+// gradient of one gaussian through one view
+struct ViewGrad {
+    float gm[3], g_m2[2], g_op, g_rgb[3], g_sc[3], g_rot[4], dS[6], d_rgb_sh[3], bas[16];
+};
 
-    uint32_t bits = 0u;
-    if (live) bits = __float_as_uint(a.splat[(size_t)i * SPLAT_F4 + 2].w);
-    const bool visible = (bits & 8u) != 0u;
-
-    float gm[3] = {0.f, 0.f, 0.f};
-    float g_m2[2] = {0.f, 0.f};
-    float g_op = 0.f;
-    float g_rgb[3] = {0.f, 0.f, 0.f};
-    float g_sc[3] = {0.f, 0.f, 0.f};
-    float g_rot[4] = {0.f, 0.f, 0.f, 0.f};
-    float dS[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float d_rgb_sh[3] = {0.f, 0.f, 0.f};
-    float bas[16];
+// K8 for one gaussian and one view: chain rule from the blend kernel's accumulators (mean2D / conic or raw moments, opacity,
+// rgb, inverse depth) to the rasterizer inputs.  Every field of `o` is written.
+__device__ __forceinline__ void preprocess_bwd_view(const CamParams &cam, const PreBwdArgs &a, const int i, const float *sh_row,
+                                                    const uint32_t bits, ViewGrad &o) {
+    float (&gm)[3] = o.gm; float (&g_m2)[2] = o.g_m2; float &g_op = o.g_op; float (&g_rgb)[3] = o.g_rgb;
+    float (&g_sc)[3] = o.g_sc; float (&g_rot)[4] = o.g_rot; float (&dS)[6] = o.dS; float (&d_rgb_sh)[3] = o.d_rgb_sh;
+    float (&bas)[16] = o.bas;
+    gm[0] = gm[1] = gm[2] = 0.f; g_m2[0] = g_m2[1] = 0.f; g_op = 0.f; g_rgb[0] = g_rgb[1] = g_rgb[2] = 0.f;
+    g_sc[0] = g_sc[1] = g_sc[2] = 0.f; g_rot[0] = g_rot[1] = g_rot[2] = g_rot[3] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dS[k] = 0.f;
+    d_rgb_sh[0] = d_rgb_sh[1] = d_rgb_sh[2] = 0.f;
 #pragma unroll
     for (int k = 0; k < 16; ++k) bas[k] = 0.f;
+    const bool visible = (bits & 8u) != 0u;
+    const int nb = (cam.sh_degree + 1) * (cam.sh_degree + 1);
+    const int M = cam.sh_coeffs;
+    (void)M;
 
     if (visible) {
         const float4 *acc = reinterpret_cast<const float4 *>(a.dacc + (size_t)i * DACC_STRIDE);
@@ -277,7 +294,7 @@ preprocess_bwd_kernel(const CamArgs ca, const PreBwdArgs a) {
             d_rgb_sh[0] = (bits & 1u) ? 0.f : d_rgb[0];
             d_rgb_sh[1] = (bits & 2u) ? 0.f : d_rgb[1];
             d_rgb_sh[2] = (bits & 4u) ? 0.f : d_rgb[2];
-            const float *sh = sh_rows + threadIdx.x * sh_row_stride(shn);
+            const float *sh = sh_row;
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;
             for (int k = 1; k < nb; ++k) {
                 const float s = sh[3 * k] * d_rgb_sh[0] + sh[3 * k + 1] * d_rgb_sh[1] + sh[3 * k + 2] * d_rgb_sh[2];
@@ -396,27 +413,14 @@ preprocess_bwd_kernel(const CamArgs ca, const PreBwdArgs a) {
         }
     }
 
-    // SH gradient rows go out through shared memory (coalesced); each thread rewrites only its own row
-    if (a.g.dL_dshs && a.shs) {
-        if (live) {
-            float *o = sh_rows + threadIdx.x * sh_row_stride(shn);
-            for (int k = 0; k < M; ++k) {
-                const float bk = (k < nb && k < 16) ? bas[k] : 0.f;
-                o[3 * k] = bk * d_rgb_sh[0]; o[3 * k + 1] = bk * d_rgb_sh[1]; o[3 * k + 2] = bk * d_rgb_sh[2];
-            }
-        }
-        __syncthreads();
-        stage_rows_out<ACC>(a.g.dL_dshs, sh_rows, row0, nrows, shn);
-    }
-    if (!live) return;
+}
 
+template <bool ACC>
+__device__ __forceinline__ void write_gauss_grads(const PreBwdArgs &a, const int i, const float gm[3], const float g_op,
+                                                  const float g_rgb[3], const float g_sc[3], const float g_rot[4], const float dS[6]) {
     if (a.g.dL_dmeans3D) {
         put<ACC>(a.g.dL_dmeans3D + 3 * (size_t)i, gm[0]); put<ACC>(a.g.dL_dmeans3D + 3 * (size_t)i + 1, gm[1]);
         put<ACC>(a.g.dL_dmeans3D + 3 * (size_t)i + 2, gm[2]);
-    }
-    if (a.g.dL_dmeans2D) {
-        put<ACC>(a.g.dL_dmeans2D + 3 * (size_t)i, g_m2[0]); put<ACC>(a.g.dL_dmeans2D + 3 * (size_t)i + 1, g_m2[1]);
-        put<ACC>(a.g.dL_dmeans2D + 3 * (size_t)i + 2, 0.f);
     }
     if (a.g.dL_dopacities) put<ACC>(a.g.dL_dopacities + i, g_op);
     if (a.g.dL_dcolors) {
@@ -438,6 +442,112 @@ preprocess_bwd_kernel(const CamArgs ca, const PreBwdArgs a) {
             for (int k = 0; k < 4; ++k) put<ACC>(a.g.dL_drotations + 4 * (size_t)i + k, g_rot[k]);
         }
     }
+}
+
+// K8, one view.
+template <bool ACC>
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_bwd_kernel(const CamArgs ca, const PreBwdArgs a) {
+    __shared__ CamParams cam;
+    extern __shared__ float sh_rows[];
+    load_cam(ca, cam);
+    const int row0 = blockIdx.x * PRE_THREADS;
+    const int nrows = min(PRE_THREADS, a.P - row0);
+    const int shn = 3 * ca.sh_coeffs;
+    const int nb = (ca.sh_degree + 1) * (ca.sh_degree + 1);
+    if (a.shs) stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * nb);
+    __syncthreads();
+    const int i = row0 + threadIdx.x;
+    const bool live = i < a.P;
+    const int M = cam.sh_coeffs;
+    float *sh_row = sh_rows + threadIdx.x * sh_row_stride(shn);
+    ViewGrad g;
+    if (live) preprocess_bwd_view(cam, a, i, sh_row, __float_as_uint(a.splat[(size_t)i * SPLAT_F4 + 2].w), g);
+
+    // SH gradient rows go out through shared memory (coalesced); each thread rewrites only its own row
+    if (a.g.dL_dshs && a.shs) {
+        if (live) {
+            for (int k = 0; k < M; ++k) {
+                const float bk = (k < nb && k < 16) ? g.bas[k] : 0.f;
+                sh_row[3 * k] = bk * g.d_rgb_sh[0]; sh_row[3 * k + 1] = bk * g.d_rgb_sh[1]; sh_row[3 * k + 2] = bk * g.d_rgb_sh[2];
+            }
+        }
+        __syncthreads();
+        stage_rows_out<ACC>(a.g.dL_dshs, sh_rows, row0, nrows, shn);
+    }
+    if (!live) return;
+    if (a.g.dL_dmeans2D) {
+        put<ACC>(a.g.dL_dmeans2D + 3 * (size_t)i, g.g_m2[0]); put<ACC>(a.g.dL_dmeans2D + 3 * (size_t)i + 1, g.g_m2[1]);
+        put<ACC>(a.g.dL_dmeans2D + 3 * (size_t)i + 2, 0.f);
+    }
+    write_gauss_grads<ACC>(a, i, g.gm, g.g_op, g.g_rgb, g.g_sc, g.g_rot, g.dS);
+}
+
+// View-batch K8: parameters read once, the V views' accumulators chained one after the other, the per-gaussian
+// gradient summed over views in registers (SH: in a second shared-memory row) and written ONCE.
+// Per-view arrays (dacc, splat, means2D gradient) are [V][...] with uniform strides.
+template <bool ACC>
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_bwd_batch_kernel(const CamArgsBatch cb, const PreBwdArgs a, const PreBwdBatchStrides st) {
+    __shared__ CamParams cams[GSB_MAX_VIEWS];
+    extern __shared__ float sh_rows[];
+    for (int v = 0; v < cb.V; ++v) load_cam(cb.cam[v], cams[v]);
+    const int row0 = blockIdx.x * PRE_THREADS;
+    const int nrows = min(PRE_THREADS, a.P - row0);
+    const int shn = 3 * cb.cam[0].sh_coeffs;
+    const int nb = (cb.cam[0].sh_degree + 1) * (cb.cam[0].sh_degree + 1);
+    float *grad_rows = sh_rows + PRE_THREADS * sh_row_stride(shn);
+    if (a.shs) stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * nb);
+    __syncthreads();
+    const int i = row0 + threadIdx.x;
+    const bool live = i < a.P;
+    const int M = cb.cam[0].sh_coeffs;
+    const float *sh_row = sh_rows + threadIdx.x * sh_row_stride(shn);
+    float *gr = grad_rows + threadIdx.x * sh_row_stride(shn);
+    float gm[3] = {0.f, 0.f, 0.f}, g_op = 0.f, g_rgb[3] = {0.f, 0.f, 0.f}, g_sc[3] = {0.f, 0.f, 0.f};
+    float g_rot[4] = {0.f, 0.f, 0.f, 0.f}, dS[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool want_sh = a.g.dL_dshs && a.shs;
+    if (live) {
+        if (want_sh)
+            for (int k = 0; k < 3 * M; ++k) gr[k] = 0.f;
+        for (int v = 0; v < cb.V; ++v) {
+            PreBwdArgs av = a;
+            av.splat += (size_t)v * st.splat; av.dacc += (size_t)v * st.dacc;
+            const uint32_t bits = __float_as_uint(av.splat[(size_t)i * SPLAT_F4 + 2].w);
+            if (!(bits & 8u)) {
+                if (a.g.dL_dmeans2D) {
+                    float *m2 = a.g.dL_dmeans2D + (size_t)v * st.means2D + 3 * (size_t)i;
+                    m2[0] = 0.f; m2[1] = 0.f; m2[2] = 0.f;
+                }
+                continue;
+            }
+            ViewGrad g;
+            preprocess_bwd_view(cams[v], av, i, sh_row, bits, g);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { gm[c] += g.gm[c]; g_rgb[c] += g.g_rgb[c]; g_sc[c] += g.g_sc[c]; }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) g_rot[c] += g.g_rot[c];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) dS[c] += g.dS[c];
+            g_op += g.g_op;
+            if (want_sh) {
+                for (int k = 0; k < nb && k < 16; ++k) {
+                    gr[3 * k] += g.bas[k] * g.d_rgb_sh[0]; gr[3 * k + 1] += g.bas[k] * g.d_rgb_sh[1];
+                    gr[3 * k + 2] += g.bas[k] * g.d_rgb_sh[2];
+                }
+            }
+            if (a.g.dL_dmeans2D) {
+                float *m2 = a.g.dL_dmeans2D + (size_t)v * st.means2D + 3 * (size_t)i;
+                m2[0] = g.g_m2[0]; m2[1] = g.g_m2[1]; m2[2] = 0.f;
+            }
+        }
+    }
+    if (want_sh) {
+        __syncthreads();
+        stage_rows_out<ACC>(a.g.dL_dshs, grad_rows, row0, nrows, shn);
+    }
+    if (!live) return;
+    write_gauss_grads<ACC>(a, i, gm, g_op, g_rgb, g_sc, g_rot, dS);
 }
 
 __global__ void __launch_bounds__(PRE_THREADS)
@@ -466,6 +576,29 @@ int launch_preprocess_bwd(const CamArgs &ca, const PreBwdArgs &a, bool accumulat
     } else {
         if (smem > 48 * 1024) GSB_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GSB_LAUNCH("preprocess_bwd", debug, stream, preprocess_bwd_kernel<false>, grid, PRE_THREADS, smem, ca, a);
+    }
+    return GSB_OK;
+}
+
+int launch_preprocess_fwd_batch(const CamArgsBatch &cb, const PreFwdArgs &a, const PreFwdBatchStrides &st, bool debug, cudaStream_t stream) {
+    if (a.P <= 0) return GSB_OK;
+    const size_t smem = a.shs ? (size_t)PRE_THREADS * ((3 * cb.cam[0].sh_coeffs) | 1) * sizeof(float) : 0;
+    if (smem > 40 * 1024) GSB_CUDA(cudaFuncSetAttribute(preprocess_fwd_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GSB_LAUNCH("preprocess_fwd", debug, stream, preprocess_fwd_batch_kernel, (int)ceil_div(a.P, PRE_THREADS), PRE_THREADS, smem, cb, a, st);
+    return GSB_OK;
+}
+
+int launch_preprocess_bwd_batch(const CamArgsBatch &cb, const PreBwdArgs &a, const PreBwdBatchStrides &st, bool accumulate, bool debug,
+                                cudaStream_t stream) {
+    if (a.P <= 0) return GSB_OK;
+    const int grid = (int)ceil_div(a.P, PRE_THREADS);
+    const size_t smem = a.shs ? 2 * (size_t)PRE_THREADS * ((3 * cb.cam[0].sh_coeffs) | 1) * sizeof(float) : 0;
+    if (accumulate) {
+        if (smem > 40 * 1024) GSB_CUDA(cudaFuncSetAttribute(preprocess_bwd_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSB_LAUNCH("preprocess_bwd", debug, stream, preprocess_bwd_batch_kernel<true>, grid, PRE_THREADS, smem, cb, a, st);
+    } else {
+        if (smem > 40 * 1024) GSB_CUDA(cudaFuncSetAttribute(preprocess_bwd_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSB_LAUNCH("preprocess_bwd", debug, stream, preprocess_bwd_batch_kernel<false>, grid, PRE_THREADS, smem, cb, a, st);
     }
     return GSB_OK;
 }

@@ -168,6 +168,7 @@ sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__rest
 #define OS_FLAG_PREFIX (2u << 30)
 #define OS_VALUE_MASK ((1u << 30) - 1u)
 constexpr int OS_MAX_PASSES = 4;
+constexpr int GSB_SORT_MAX_VIEWS = 16;
 
 struct OnesweepPasses {
     int npass;
@@ -177,9 +178,10 @@ struct OnesweepPasses {
 
 __global__ void __launch_bounds__(256)
 onesweep_hist_kernel(const uint32_t *__restrict__ keys, uint32_t *__restrict__ ghist, int64_t n,
-                     const unsigned long long *__restrict__ n_dev, const OnesweepPasses ps) {
+                     const unsigned long long *__restrict__ n_dev, const OnesweepPasses ps, const size_t sv) {
     __shared__ uint32_t hist[OS_MAX_PASSES][RADIX];
-    if (n_dev) n = min((int64_t)*n_dev, n);
+    keys += blockIdx.y * sv; ghist += blockIdx.y * (OS_MAX_PASSES * RADIX);   // view-batch: blockIdx.y = view
+    if (n_dev) n = min((int64_t)n_dev[blockIdx.y], n);
     for (int p = 0; p < ps.npass; ++p) hist[p][threadIdx.x] = 0;
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * 256;
@@ -199,13 +201,19 @@ __global__ void __launch_bounds__(SORT_THREADS)
 onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                      const uint32_t *__restrict__ ghist, volatile uint32_t *status, uint32_t *ticket, int64_t n,
-                     const unsigned long long *__restrict__ n_dev, int shift, uint32_t mask) {
+                     const unsigned long long *__restrict__ n_dev, int shift, uint32_t mask, const size_t sv,
+                     const size_t sv_status) {
     constexpr int SORT_KPB = SORT_THREADS * SORT_IPT;
+    {   // view-batch: blockIdx.y = view
+        const size_t v = blockIdx.y;
+        keys_in += v * sv; vals_in += v * sv; keys_out += v * sv; vals_out += v * sv;
+        ghist += v * (OS_MAX_PASSES * RADIX); status += v * sv_status; ticket += v * OS_MAX_PASSES;
+    }
     __shared__ uint32_t warp_cnt[SORT_THREADS / 32][RADIX];
     __shared__ uint32_t warp_sums[8];
     __shared__ uint32_t s_ticket;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (n_dev) n = min((int64_t)*n_dev, n);
+    if (n_dev) n = min((int64_t)n_dev[blockIdx.y], n);
     if (tid == 0) s_ticket = atomicAdd(ticket, 1u);
 #pragma unroll
     for (int k = 0; k < SORT_THREADS / 32; ++k) warp_cnt[k][tid] = 0;
@@ -307,14 +315,14 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
 
 int g_sort_variant = 1;  // 0: histogram / row scan / scatter per pass, 1: onesweep
 
-static size_t onesweep_scratch_bytes(int64_t n) {
+static size_t onesweep_scratch_bytes(int64_t n, int V) {
     const int64_t nblocks = ceil_div(n > 0 ? n : 1, SORT_THREADS * sort_ipt(n));
-    return align_up((size_t)OS_MAX_PASSES * RADIX * 4 + 256 + (size_t)OS_MAX_PASSES * nblocks * RADIX * 4, 256);
+    return align_up((size_t)GSB_SORT_MAX_VIEWS * OS_MAX_PASSES * RADIX * 4 + 256 + (size_t)V * OS_MAX_PASSES * nblocks * RADIX * 4, 256);
 }
 
 static int onesweep_sort(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n,
                          const unsigned long long *n_dev, int begin_bit, int end_bit, void *scratch, bool debug,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, int V, size_t sv) {
     OnesweepPasses ps;
     ps.npass = 0;
     for (int bit = begin_bit; bit < end_bit; bit += RADIX_BITS) {
@@ -326,51 +334,55 @@ static int onesweep_sort(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uin
     }
     const bool small = sort_ipt(n) == SORT_IPT_SMALL;
     const int nblocks = (int)ceil_div(n, SORT_THREADS * sort_ipt(n));
-    // layout: ghist[4][256] | ticket[4] (padded to 256 B) | status[npass][nblocks][256]
+    // layout: ghist[16 views][4][256] | ticket[16][4] (256 B) | status[V][npass][nblocks][256]
     uint32_t *ghist = static_cast<uint32_t *>(scratch);
-    uint32_t *ticket = ghist + OS_MAX_PASSES * RADIX;
+    uint32_t *ticket = ghist + GSB_SORT_MAX_VIEWS * OS_MAX_PASSES * RADIX;
     uint32_t *status = ticket + 64;
-    const size_t zero_bytes = (size_t)OS_MAX_PASSES * RADIX * 4 + 256 + (size_t)ps.npass * nblocks * RADIX * 4;
+    const size_t sv_status = (size_t)ps.npass * nblocks * RADIX;
+    const size_t zero_bytes = (size_t)GSB_SORT_MAX_VIEWS * OS_MAX_PASSES * RADIX * 4 + 256 + (size_t)V * sv_status * 4;
     GSB_CUDA(cudaMemsetAsync(scratch, 0, zero_bytes, stream));
     const int hist_blocks = (int)(ceil_div(n, 256 * 16) < 148 * 8 ? ceil_div(n, 256 * 16) : 148 * 8);
-    GSB_LAUNCH("sort_hist", debug, stream, onesweep_hist_kernel, hist_blocks, 256, 0, keys, ghist, n, n_dev, ps);
+    GSB_LAUNCH("sort_hist", debug, stream, onesweep_hist_kernel, dim3(hist_blocks, V), 256, 0, keys, ghist, n, n_dev, ps, sv);
     uint32_t *kin = keys, *vin = vals, *kout = keys_alt, *vout = vals_alt;
     for (int p = 0; p < ps.npass; ++p) {
         uint32_t *st = status + (size_t)p * nblocks * RADIX;
         if (small) {
-            GSB_LAUNCH("sort_scatter", debug, stream, onesweep_pass_kernel<SORT_IPT_SMALL>, nblocks, SORT_THREADS, 0, kin,
-                       vin, kout, vout, ghist + p * RADIX, st, ticket + p, n, n_dev, ps.shift[p], ps.mask[p]);
+            GSB_LAUNCH("sort_scatter", debug, stream, onesweep_pass_kernel<SORT_IPT_SMALL>, dim3(nblocks, V), SORT_THREADS, 0, kin,
+                       vin, kout, vout, ghist + p * RADIX, st, ticket + p, n, n_dev, ps.shift[p], ps.mask[p], sv, sv_status);
         } else {
-            GSB_LAUNCH("sort_scatter", debug, stream, onesweep_pass_kernel<SORT_IPT_BIG>, nblocks, SORT_THREADS, 0, kin,
-                       vin, kout, vout, ghist + p * RADIX, st, ticket + p, n, n_dev, ps.shift[p], ps.mask[p]);
+            GSB_LAUNCH("sort_scatter", debug, stream, onesweep_pass_kernel<SORT_IPT_BIG>, dim3(nblocks, V), SORT_THREADS, 0, kin,
+                       vin, kout, vout, ghist + p * RADIX, st, ticket + p, n, n_dev, ps.shift[p], ps.mask[p], sv, sv_status);
         }
         uint32_t *t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }
     if (ps.npass & 1) {
-        GSB_CUDA(cudaMemcpyAsync(keys, keys_alt, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
-        GSB_CUDA(cudaMemcpyAsync(vals, vals_alt, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+        const size_t bytes = V > 1 ? ((size_t)(V - 1) * sv + (size_t)n) * 4 : (size_t)n * 4;
+        GSB_CUDA(cudaMemcpyAsync(keys, keys_alt, bytes, cudaMemcpyDeviceToDevice, stream));
+        GSB_CUDA(cudaMemcpyAsync(vals, vals_alt, bytes, cudaMemcpyDeviceToDevice, stream));
     }
     return GSB_OK;
 }
 
-size_t sort_scratch_bytes(int64_t n) {
+size_t sort_scratch_bytes(int64_t n, int V) {
     int64_t nblocks = ceil_div(n > 0 ? n : 1, SORT_THREADS * sort_ipt(n));
     const size_t classic = align_up((size_t)RADIX * nblocks * sizeof(uint32_t), 256) + align_up(RADIX * sizeof(uint32_t), 256);
-    const size_t os = onesweep_scratch_bytes(n);
+    const size_t os = onesweep_scratch_bytes(n, V);
     return classic > os ? classic : os;
 }
 
 int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n,
                const unsigned long long *n_dev, int begin_bit, int end_bit, void *scratch, bool debug,
-               cudaStream_t stream) {
+               cudaStream_t stream, int V, size_t sv) {
     if (n <= 0 || end_bit <= begin_bit) return GSB_OK;
     if (n >= (int64_t)1 << 30) {
         set_error("sort_pairs: n=%lld does not fit 30-bit positions", (long long)n);
         return GSB_ERR_OVERFLOW;
     }
-    if (g_sort_variant == 1 && (end_bit - begin_bit) <= OS_MAX_PASSES * RADIX_BITS)
-        return onesweep_sort(keys, vals, keys_alt, vals_alt, n, n_dev, begin_bit, end_bit, scratch, debug, stream);
+    if (V > GSB_SORT_MAX_VIEWS) { set_error("sort_pairs: more than %d views", GSB_SORT_MAX_VIEWS); return GSB_ERR_ARGUMENT; }
+    if ((g_sort_variant == 1 || V > 1) && (end_bit - begin_bit) <= OS_MAX_PASSES * RADIX_BITS)
+        return onesweep_sort(keys, vals, keys_alt, vals_alt, n, n_dev, begin_bit, end_bit, scratch, debug, stream, V, sv);
+    if (V > 1) { set_error("sort_pairs: the view-batch sort needs the onesweep path"); return GSB_ERR_ARGUMENT; }
     const bool small = sort_ipt(n) == SORT_IPT_SMALL;
     const int nblocks = (int)ceil_div(n, SORT_THREADS * sort_ipt(n));
     uint32_t *table = static_cast<uint32_t *>(scratch);

@@ -42,7 +42,8 @@ class _Inputs(Structure):
 class _State(Structure):
     _fields_ = [("P", c_int32), ("num_tiles", c_int32), ("num_rendered", c_int64), ("num_visible", c_int64),
                 ("binning_capacity", c_int64), ("geom", c_void_p), ("geom_bytes", c_size_t), ("binning", c_void_p), ("binning_bytes", c_size_t),
-                ("image", c_void_p), ("image_bytes", c_size_t)]
+                ("image", c_void_p), ("image_bytes", c_size_t), ("splat", c_void_p), ("point_list", c_void_p),
+                ("ranges", c_void_p), ("final_T", c_void_p), ("n_contrib", c_void_p)]
 
 
 class _Grads(Structure):
@@ -67,6 +68,12 @@ def _load():
     lib.gsb_backward.restype = c_int32
     lib.gsb_backward.argtypes = [POINTER(_Settings), POINTER(_Inputs), POINTER(_State), c_void_p, c_void_p, c_void_p,
                                  c_void_p, POINTER(_Grads), c_int32, _ALLOC_FN, c_void_p, c_void_p]
+    lib.gsb_forward_batch.restype = c_int32
+    lib.gsb_forward_batch.argtypes = [c_int32, POINTER(_Settings), POINTER(_Inputs), c_void_p, c_void_p, c_void_p, c_int64,
+                                      _ALLOC_FN, c_void_p, POINTER(_State), c_void_p]
+    lib.gsb_backward_batch.restype = c_int32
+    lib.gsb_backward_batch.argtypes = [c_int32, POINTER(_Settings), POINTER(_Inputs), POINTER(_State), c_void_p, c_void_p,
+                                       c_void_p, c_void_p, POINTER(_Grads), c_int32, _ALLOC_FN, c_void_p, c_void_p]
     lib.gsb_mark_visible.restype = c_int32
     lib.gsb_mark_visible.argtypes = [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.gsb_sort_pairs.restype = c_int32
@@ -81,8 +88,8 @@ def _load():
     lib.gsb_kernel_time.argtypes = [c_char_p, POINTER(ctypes.c_double), POINTER(c_int64), c_int32]
     lib.gsb_set_option.restype = c_int32
     lib.gsb_set_option.argtypes = [c_char_p, c_int32]
-    if lib.gsb_abi_version() != 3:
-        raise ImportError(f"{_LIB_PATH}: ABI version {lib.gsb_abi_version()} != 3")
+    if lib.gsb_abi_version() != 4:
+        raise ImportError(f"{_LIB_PATH}: ABI version {lib.gsb_abi_version()} != 4")
     return lib
 
 
@@ -306,6 +313,63 @@ def _backward_impl(pack, rs, means3D, sh, colors_precomp, opacities, scales, rot
         rc = _C.gsb_backward(byref(cs), byref(ci), byref(pack["state"]), out_color.data_ptr(), out_invdepth.data_ptr(),
                              grad_color.data_ptr(), _ptr(grad_invdepth), byref(g), int(bool(accumulate)), arena.cb,
                              None, stream)
+        _check(rc, arena)
+
+
+MAX_BATCH_VIEWS = 16
+
+
+def _forward_batch_impl(means3D, sh, opacities, scales, rotations, settings_list):
+    """View-batch forward (gsb_forward_batch): returns (color[V,3,H,W], radii[V,P], invdepth[V,1,H,W], pack)."""
+    if not means3D.is_cuda:
+        raise RuntimeError("diff_gaussian_rasterization (B200): tensors must live on a CUDA device; there is no CPU path")
+    dev = means3D.device
+    V, P = len(settings_list), int(means3D.shape[0])
+    H, W = int(settings_list[0].image_height), int(settings_list[0].image_width)
+    M = int(sh.shape[1])
+    with torch.cuda.device(dev):
+        keep = []
+        cs = (_Settings * V)(*[_c_settings(rs, M, keep) for rs in settings_list])
+        ci = _c_inputs(P, means3D, sh, None, opacities, scales, rotations, None)
+        color = torch.empty((V, 3, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((V, P), dtype=torch.int32, device=dev)
+        invdepth = torch.empty((V, 1, H, W), dtype=torch.float32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        arena = _Arena(dev, stream)
+        states = (_State * V)()
+        hkey = (P, H, W, dev.index, "batch")
+        hint = _capacity_hints.get(hkey, 0) if speculative_binning else 0
+        rc = _C.gsb_forward_batch(V, cs, byref(ci), color.data_ptr(), radii.data_ptr(), invdepth.data_ptr(), hint, arena.cb,
+                                  None, states, stream)
+        _check(rc, arena)
+        dmax = max(int(states[v].num_rendered) for v in range(V))
+        want = ((int(dmax * 1.25) + 65536 + (1 << 20) - 1) >> 20) << 20
+        _capacity_hints[hkey] = max(want, _capacity_hints.get(hkey, 0))
+    pack = dict(states=states, V=V, geom=arena.bufs.get(BUF_GEOM), binning=arena.bufs.get(BUF_BINNING),
+                image=arena.bufs.get(BUF_IMAGE), num_rendered=[int(states[v].num_rendered) for v in range(V)], sh_coeffs=M,
+                keep=keep)
+    return color, radii, invdepth, pack
+
+
+def _backward_batch_impl(pack, settings_list, means3D, sh, opacities, scales, rotations, out_color, out_invdepth,
+                         grad_color, grad_invdepth, grads: dict, accumulate: bool):
+    """View-batch backward (gsb_backward_batch).  grads: tensors holding / receiving the gradient SUMMED over the views
+    (means2D, if present, is [V,P,3] and per view)."""
+    dev = means3D.device
+    V, P = pack["V"], int(means3D.shape[0])
+    with torch.cuda.device(dev):
+        keep = []
+        cs = (_Settings * V)(*[_c_settings(rs, pack["sh_coeffs"], keep) for rs in settings_list])
+        ci = _c_inputs(P, means3D, sh, None, opacities, scales, rotations, None)
+        g = _Grads()
+        g.dL_dmeans3D, g.dL_dmeans2D = _ptr(grads.get("means3D")), _ptr(grads.get("means2D"))
+        g.dL_dshs, g.dL_dopacities = _ptr(grads.get("shs")), _ptr(grads.get("opacities"))
+        g.dL_dscales, g.dL_drotations = _ptr(grads.get("scales")), _ptr(grads.get("rotations"))
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        arena = _Arena(dev, stream)
+        rc = _C.gsb_backward_batch(V, cs, byref(ci), pack["states"], out_color.data_ptr(), out_invdepth.data_ptr(),
+                                   grad_color.data_ptr(), _ptr(grad_invdepth), byref(g), int(bool(accumulate)), arena.cb, None,
+                                   stream)
         _check(rc, arena)
 
 

@@ -118,7 +118,7 @@ def _settings_for(cam, pc, pipe, bg_color, scaling_modifier):
 
 def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch.Tensor, loss_fn, *,
                           scaling_modifier: float = 1.0, densify_stats: Optional[dict] = None,
-                          keep_images: bool = False, loss_returns_grad: bool = False) -> dict:
+                          keep_images: bool = False, loss_returns_grad: bool = False, batched: bool = True) -> dict:
     """Fused view-batch training step: forward + loss + backward for every camera, with the per-gaussian
     gradients of ALL views summed in place.
 
@@ -132,8 +132,12 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
     ``loss_fn(image[3,H,W] (clamped to [0,1] like render() does), invdepth[1,H,W], view_index) -> scalar``, or,
     with ``loss_returns_grad=True``, ``loss_fn(raw_image, invdepth, view_index) -> (loss, dL/d raw_image[, dL/d invdepth])``
     for a loss that brings its own gradient (e.g. ``diff_gaussian_rasterization.l1_loss_and_grad``); no autograd then.
-    Returns {"losses": [V] tensor, "radii_max": [P] int32, "images": list (if keep_images)}; nothing in here
-    synchronises with the host except the one instance-count read-back per forward.
+    Returns {"losses": [V] tensor, "radii_max": [P] int32, "images": list (if keep_images)}.
+
+    ``batched=True`` (default, up to 16 views of equal size per chunk) goes through gsb_forward_batch /
+    gsb_backward_batch: the gaussians' parameters are read once for all views in the per-gaussian kernels, the
+    depth sorts / scans / tile sorts of the views run as single batched launches, the summed gradient is written
+    once, and there is ONE host read-back per chunk.  ``batched=False`` runs view by view (one read-back each).
     """
     xyz, opacity = pc.get_xyz, pc.get_opacity
     scales, rotations, shs = pc.get_scaling, pc.get_rotation, pc.get_features
@@ -154,6 +158,50 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
     c["opacities"] = c["opacities"].reshape(-1) if c["opacities"] is not None else None
     losses, images = [], []
     radii_max = torch.zeros((P,), dtype=torch.int32, device=dev)
+    cams_all = list(viewpoint_cameras) if batched else None
+    if batched and cams_all and all(int(cm.image_height) == int(cams_all[0].image_height) and
+                                    int(cm.image_width) == int(cams_all[0].image_width) for cm in cams_all):
+        for c0 in range(0, len(cams_all), _dgr.MAX_BATCH_VIEWS):
+            chunk = cams_all[c0:c0 + _dgr.MAX_BATCH_VIEWS]
+            rss = [_settings_for(cm, pc, pipe, bg_color, scaling_modifier) for cm in chunk]
+            color, radii, invdepth, pack = _dgr._forward_batch_impl(c["means3D"], c["shs"], c["opacities"], c["scales"],
+                                                                    c["rotations"], rss)
+            g_color = torch.empty_like(color)
+            g_depth = None
+            for k in range(len(chunk)):
+                vi = c0 + k
+                if loss_returns_grad:
+                    res = loss_fn(color[k], invdepth[k], vi)
+                    loss, g_img = res[0], res[1]
+                    g_dep = res[2] if len(res) > 2 else None
+                else:
+                    img = color[k].detach().requires_grad_(True)
+                    dep = invdepth[k].detach().requires_grad_(True)
+                    with torch.enable_grad():
+                        loss = loss_fn(img.clamp(0, 1), dep, vi)
+                    g_img, g_dep = torch.autograd.grad(loss, (img, dep), allow_unused=True)
+                if g_img is None:
+                    g_color[k].zero_()
+                else:
+                    g_color[k].copy_(g_img)
+                if g_dep is not None:
+                    if g_depth is None:
+                        g_depth = torch.zeros_like(invdepth)
+                    g_depth[k].copy_(g_dep)
+                losses.append(loss.detach().reshape(()))
+                if keep_images:
+                    images.append(color[k].detach())
+            vg = dict(grads)
+            if densify_stats is not None:
+                vg["means2D"] = torch.empty((len(chunk), P, 3), dtype=torch.float32, device=dev)
+            _dgr._backward_batch_impl(pack, rss, c["means3D"], c["shs"], c["opacities"], c["scales"], c["rotations"], color,
+                                      invdepth, g_color, g_depth, vg, accumulate=True)
+            torch.maximum(radii_max, radii.max(dim=0).values, out=radii_max)
+            if densify_stats is not None:
+                vis = radii > 0                                               # [V,P]
+                densify_stats["xyz_gradient_accum"] += (vg["means2D"][:, :, :2].norm(dim=-1) * vis).sum(dim=0)[:, None]
+                densify_stats["denom"] += vis.sum(dim=0)[:, None].to(densify_stats["denom"].dtype)
+        viewpoint_cameras = []
     for vi, cam in enumerate(viewpoint_cameras):
         rs = _settings_for(cam, pc, pipe, bg_color, scaling_modifier)
         color, radii, invdepth, pack = _dgr._forward_impl(c["means3D"], c["shs"], None, c["opacities"], c["scales"],

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define GSB_ABI_VERSION 3
+#define GSB_ABI_VERSION 4
 
 /* error codes (0 = ok); gsb_last_error() holds the message of the calling thread's last failure */
 #define GSB_OK 0
@@ -104,6 +104,12 @@ typedef struct GsbState {
     size_t binning_bytes;
     void *image;
     size_t image_bytes;
+    /* typed views into the buffers above (set by the forward call; the view-batch call packs V views per buffer) */
+    const void *splat;        /* [P] 48-byte records */
+    const uint32_t *point_list; /* [num_rendered] gaussian ids grouped by tile, depth-ordered inside a tile */
+    const void *ranges;       /* [num_tiles] uint2 [begin, end) into point_list */
+    const float *final_T;     /* [H*W] */
+    const uint32_t *n_contrib; /* [H*W] */
 } GsbState;
 
 /* gradient outputs of the autograd.Function's backward; NULL pointers are skipped */
@@ -134,6 +140,20 @@ int32_t gsb_backward(const GsbSettings *settings, const GsbInputs *in, const Gsb
                      const float *out_color, const float *out_invdepth, const float *dL_dcolor,
                      const float *dL_dinvdepth, const GsbGrads *grads, int32_t accumulate,
                      gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream);
+
+/* View-batch variants: V <= 16 cameras of equal image size against the SAME gaussians.
+ * The per-gaussian parameters are read once for all views (preprocess), the V depth sorts / scans / tile sorts
+ * run as single batched launches, and there is ONE host read-back (V instance counts) per call.
+ * out_color [V,3,H,W], out_radii [V,P], out_invdepth [V,H*W]; states[V] (buffers are shared, the typed views differ).
+ * Backward: dL_dcolor [V,3,H,W], dL_dinvdepth [V,H*W] or NULL; every gradient in `grads` is the SUM over the V views
+ * and is written once (accumulate != 0: added to the existing contents), except dL_dmeans2D which is [V,P,3]. */
+int32_t gsb_forward_batch(int32_t V, const GsbSettings *settings, const GsbInputs *in, float *out_color,
+                          int32_t *out_radii, float *out_invdepth, int64_t capacity_hint, gsb_alloc_fn alloc,
+                          void *alloc_ctx, GsbState *states, void *cuda_stream);
+int32_t gsb_backward_batch(int32_t V, const GsbSettings *settings, const GsbInputs *in, const GsbState *states,
+                           const float *out_color, const float *out_invdepth, const float *dL_dcolor,
+                           const float *dL_dinvdepth, const GsbGrads *grads, int32_t accumulate,
+                           gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream);
 
 /* Frustum test only (GaussianRasterizer.markVisible): present[i] = 1 if view-space z > 0.2 */
 int32_t gsb_mark_visible(int32_t P, const float *means3D, const float *viewmatrix,

@@ -304,3 +304,35 @@ def test_full_size_config3_against_oracle():
     vis = ref["radii"] > 0
     assert np.all(got["grads"]["means3D"][~vis] == 0) and np.all(got["grads"]["shs"][~vis] == 0)
     U.assert_grads_close(got["grads"], ref["grads"], flips=5e-3 if frac > 0 else 0.0)
+
+
+@pytest.mark.parametrize("nviews", [1, 5])
+def test_batched_calls_match_single_view_calls(nviews):
+    """gsb_forward_batch / gsb_backward_batch against the per-view calls: images identical, summed gradients equal up to
+    float summation order, per-view means2D gradients and the densification statistics equal."""
+    import math
+    import bench
+    from gaussian_renderer import GradientBucket, render_views_backward
+    dev = torch.device("cuda", 0)
+    scene = TO.make_scene(6000, seed=60, log_scale_mean=-3.0)
+    W, H = 208, 120
+    cams = [bench.BenchCamera(W, H, math.radians(55.0), *bench.view_pose(i, 3.0), dev) for i in range(nviews)]
+    gts = [torch.rand(3, H, W, generator=torch.Generator().manual_seed(i)).to(dev) for i in range(nviews)]
+    bg = torch.tensor([0.3, 0.1, 0.2], device=dev)
+
+    def run(batched):
+        pc = bench.BenchGaussians(scene, 3, dev)
+        bucket = GradientBucket(pc.parameters())
+        stats = dict(xyz_gradient_accum=torch.zeros(6000, 1, device=dev), denom=torch.zeros(6000, 1, device=dev))
+        out = render_views_backward(cams, pc, bench.Pipe(), bg, lambda img, d, i: (img - gts[i]).abs().mean() + 0.05 * d.mean(),
+                                    densify_stats=stats, keep_images=True, batched=batched)
+        return (out["losses"].cpu().numpy(), bucket.flat.cpu().numpy(), [im.cpu().numpy() for im in out["images"]],
+                stats["xyz_gradient_accum"].cpu().numpy(), stats["denom"].cpu().numpy(), out["radii_max"].cpu().numpy())
+
+    a, b = run(False), run(True)
+    assert np.allclose(a[0], b[0], rtol=1e-6, atol=1e-7)
+    for x, y in zip(a[2], b[2]):
+        assert np.array_equal(x, y)
+    assert np.abs(a[1] - b[1]).max() <= 1e-4 * np.abs(a[1]).max()
+    assert np.abs(a[3] - b[3]).max() <= 1e-4 * (np.abs(a[3]).max() + 1e-20)
+    assert np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])
