@@ -9,8 +9,7 @@
 // records they point to are gathered from the L2-resident record table (P * 48 B) into shared
 // memory 256 at a time.  One 16x16 tile per CTA; a warp owns an 8x4 pixel patch so that a gaussian
 // which misses the patch is skipped by the whole warp.
-#include "kernels.cuh"
-#include "patch_cull.cuh"
+#include "blend_common.cuh"
 
 namespace gsb {
 
@@ -111,9 +110,11 @@ render_fwd_pc_kernel(const RenderFwdArgs a) {
         if (idx < todo) {
             const uint32_t g = a.point_list[range.x + idx];
             const float4 *rec = a.splat + (size_t)g * SPLAT_F4;
-            const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
-            s0[threadIdx.x] = q0; s1[threadIdx.x] = q1; s2[threadIdx.x] = make_float2(q2.x, q2.y);
+            float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
+            const float4 q2 = __ldg(rec + 2);
             smask[threadIdx.x] = (uint8_t)patch_mask(q0.x, q0.y, q0.z, q0.w, q1.x, q2.z, ox, oy);
+            stage_scale(q0, q1);   // conic pre-scaled for the log2-domain exponent (blend_common.cuh)
+            s0[threadIdx.x] = q0; s1[threadIdx.x] = q1; s2[threadIdx.x] = make_float2(q2.x, q2.y);
         }
         __syncthreads();
         const int n = min(RB, todo - rd * RB);
@@ -123,16 +124,17 @@ render_fwd_pc_kernel(const RenderFwdArgs a) {
             const float4 q0 = s0[j];
             const float4 q1 = s1[j];
             const float dx = q0.x - fx, dy = q0.y - fy;
-            const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
+            // same operation order as render_mp.cu / render_ps.cu, so forward and backward agree bit for bit on alpha
+            const float power = power2_at(__fmul_rn(__fmul_rn(q0.z, dx), dx), __fmul_rn(__fmul_rn(q1.x, dy), dy), __fmul_rn(q0.w, dx), dy);
             if (power > 0.0f) continue;
-            const float alpha = fminf(ALPHA_MAX, q1.y * __expf(power));
+            const float alpha = fminf(ALPHA_MAX, __fmul_rn(q1.y, ex2_approx(power)));
             if (alpha < ALPHA_MIN) continue;
-            const float test_T = T * (1.0f - alpha);
+            const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
             if (test_T < T_STOP) { done = true; continue; }
             const float2 q2 = s2[j];
-            const float wgt = alpha * T;
-            C0 += q1.z * wgt; C1 += q1.w * wgt; C2 += q2.x * wgt;
-            Dp += q2.y * wgt;
+            const float wgt = __fmul_rn(alpha, T);
+            C0 = __fmaf_rn(q1.z, wgt, C0); C1 = __fmaf_rn(q1.w, wgt, C1); C2 = __fmaf_rn(q2.x, wgt, C2);
+            Dp = __fmaf_rn(q2.y, wgt, Dp);
             T = test_T;
             last = (uint32_t)(rd * RB + j + 1);
         }

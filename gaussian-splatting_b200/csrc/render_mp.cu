@@ -166,10 +166,11 @@ render_bwd_mp_kernel(const RenderBwdArgs a) {
     }
     if (t == 0) s_max = 0;
     __syncthreads();
-    my_max = __reduce_max_sync(0xffffffffu, my_max);
+    my_max = __reduce_max_sync(0xffffffffu, my_max);   // deepest list position this warp's pixels blended
     if ((t & 31) == 0) atomicMax(&s_max, my_max);
     __syncthreads();
     const int todo = (int)s_max;  // the deepest list position any pixel of the tile blended
+    const int my_todo = (int)my_max;
 
     for (int base = 0; base < todo; base += MP_R) {
         __syncthreads();
@@ -184,7 +185,8 @@ render_bwd_mp_kernel(const RenderBwdArgs a) {
             s0[k] = q0; s1[k] = q1; s2[k] = make_float2(q2.x, q2.y); sid[k] = g;
         }
         __syncthreads();
-        const int cnt = CULL ? compact_hits(smask, n, want, slist[CULL ? (t >> 5) : 0]) : n;
+        const int nw = max(0, min(n, my_todo - base));   // nothing behind this warp's own deepest pixel matters to it
+        const int cnt = CULL ? compact_hits(smask, nw, want, slist[CULL ? (t >> 5) : 0]) : nw;
         for (int kk = 0; kk < cnt; ++kk) {
             const int j = CULL ? (int)slist[CULL ? (t >> 5) : 0][kk] : kk;
             const float4 q0 = s0[j];
