@@ -236,31 +236,15 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
     for (int k = 0; k < 8; ++k)
         if (k < w) digit_base += warp_sums[k];
 
-    // keys of this block (block order = (warp, round, lane)) and the block's digit histogram.  The histogram is
-    // published as this block's AGGREGATE before the (long) ranking phase, so that by the time successors look back
-    // most predecessors already show an inclusive prefix and the walk is short.
-    __shared__ uint32_t block_hist[RADIX];
-    block_hist[tid] = 0;
-    __syncthreads();
+    // stable local ranks, block order = (warp, round, lane)
     const int64_t seg = (int64_t)b * SORT_KPB + (int64_t)w * (32 * SORT_IPT);
     uint32_t key[SORT_IPT], rank[SORT_IPT];
-#pragma unroll
-    for (int r = 0; r < SORT_IPT; ++r) {
-        const int64_t idx = seg + r * 32 + lane;
-        key[r] = idx < n ? keys_in[idx] : 0xffffffffu;
-        if (idx < n) atomicAdd(&block_hist[(key[r] >> shift) & mask], 1u);
-    }
-    __syncthreads();
-    const uint32_t cnt = block_hist[tid];
-    volatile uint32_t *my = status + (size_t)b * RADIX + tid;
-    *my = cnt | (b == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG);
-
-    // stable local ranks
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int r = 0; r < SORT_IPT; ++r) {
         const int64_t idx = seg + r * 32 + lane;
         const bool valid = idx < n;
+        key[r] = valid ? keys_in[idx] : 0xffffffffu;
         const uint32_t d = valid ? ((key[r] >> shift) & mask) : (uint32_t)RADIX;
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
         const int leader = __ffs(peers) - 1;
@@ -275,19 +259,23 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
     }
     __syncthreads();
 
-    // warp_cnt becomes the exclusive prefix over warps
-    {
-        uint32_t acc = 0;
+    // per-digit block count; warp_cnt becomes the exclusive prefix over warps
+    uint32_t cnt = 0;
 #pragma unroll
-        for (int k = 0; k < SORT_THREADS / 32; ++k) {
-            const uint32_t c = warp_cnt[k][tid];
-            warp_cnt[k][tid] = acc;
-            acc += c;
-        }
+    for (int k = 0; k < SORT_THREADS / 32; ++k) {
+        const uint32_t c = warp_cnt[k][tid];
+        warp_cnt[k][tid] = cnt;
+        cnt += c;
     }
-    // decoupled look-back for digit `tid`, eight status words in flight at a time
+    // decoupled look-back for digit `tid`
+    volatile uint32_t *my = status + (size_t)b * RADIX + tid;
     uint32_t excl = 0;
-    if (b != 0) {
+    if (b == 0) {
+        *my = cnt | OS_FLAG_PREFIX;
+    } else {
+        *my = cnt | OS_FLAG_AGG;
+        // Walk back over the predecessors' status words, eight loads in flight at a time: with ~300 blocks resident
+        // most predecessors only show an aggregate, so the walk is long and must not be one L2 round trip per step.
         int64_t pb = (int64_t)b - 1;
         bool found = false;
         while (!found) {
