@@ -54,4 +54,19 @@ __device__ __forceinline__ float reduce2_transposed(const float v0, const float 
     return r;
 }
 
+// ---- packed FP32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot for two lanes' worth of FP32) ----
+// tools/micro/ffma2_bench.cu: FFMA2 runs at half the FFMA issue rate (same FLOP/s), so it frees issue slots for
+// the ALU / MUFU / shuffle work around it -- what the issue-bound blend kernels need.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(const float lo, const float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 pk1(const float v) { return pk(v, v); }
+__device__ __forceinline__ void unpk(const f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ float lo_of(const f32x2 v) { float a, b; unpk(v, a, b); return a; }
+__device__ __forceinline__ float hi_of(const f32x2 v) { float a, b; unpk(v, a, b); return b; }
+__device__ __forceinline__ f32x2 fma2(const f32x2 a, const f32x2 b, const f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 mul2(const f32x2 a, const f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2(const f32x2 a, const f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 sub2(const f32x2 a, const f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ float hsum(const f32x2 v) { float a, b; unpk(v, a, b); return a + b; }
+
 }  // namespace gsb

@@ -82,7 +82,8 @@ render_fwd_kernel(const RenderFwdArgs a) {
 
 // forward with sub-tile culling: each warp (8x4 patch) walks only the staged gaussians whose cull ellipse
 // meets its patch (patch_cull.cuh).  Blend arithmetic identical to render_fwd_kernel.
-__global__ void __launch_bounds__(256)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 render_fwd_pc_kernel(const RenderFwdArgs a) {
     __shared__ float4 s0[RB], s1[RB];
     __shared__ float2 s2[RB];
@@ -296,7 +297,11 @@ int launch_render_fwd(const RenderFwdArgs &a, int variant, bool debug, cudaStrea
     const int tiles = a.gx * a.gy;
     if (tiles <= 0) return GSB_OK;
     if (variant == 4) {
-        GSB_LAUNCH("render_fwd", debug, stream, render_fwd_pc_kernel, tiles, 256, 0, a);
+        GSB_LAUNCH("render_fwd", debug, stream, render_fwd_pc_kernel<1>, tiles, 256, 0, a);
+    } else if (variant == 6) {   // register budget for 6 CTAs (48 warps) per SM
+        GSB_LAUNCH("render_fwd", debug, stream, render_fwd_pc_kernel<6>, tiles, 256, 0, a);
+    } else if (variant == 8) {   // 8 CTAs (64 warps) per SM
+        GSB_LAUNCH("render_fwd", debug, stream, render_fwd_pc_kernel<8>, tiles, 256, 0, a);
     } else {
         GSB_LAUNCH("render_fwd", debug, stream, render_fwd_kernel, tiles, 256, 0, a);
     }
