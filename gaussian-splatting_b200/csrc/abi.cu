@@ -36,7 +36,7 @@ void timer_end(void *token, cudaStream_t stream) {
 
 static int opt_cull = 1;
 static int opt_fwd_variant = 4;  // one pixel per thread + sub-tile patch culling (tools/sweep.py: 0.33 ms vs 0.42)
-static int opt_bwd_variant = 6;  // 2x2 px/thread, sub-tile culling, 12 CTAs/SM register budget  // render_mp.cu, 2x2 pixels per thread (tools/sweep.py: 0.74 ms vs 1.41 / 1.03)
+static int opt_bwd_variant = 8;  // 2x2 px/thread, sub-tile culling, packed f32x2 (FFMA2) arithmetic  // render_mp.cu, 2x2 pixels per thread (tools/sweep.py: 0.74 ms vs 1.41 / 1.03)
 
 void set_error(const char *fmt, ...) {
     va_list ap;

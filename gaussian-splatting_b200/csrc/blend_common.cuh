@@ -14,6 +14,13 @@ __device__ __forceinline__ float ex2_approx(const float x) {
     return y;
 }
 
+// 1/x, one MUFU.RCP (<= 1 ulp); x = 1 - alpha is in [0.01, 1], no special cases to handle
+__device__ __forceinline__ float rcp_approx(const float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // staged record: q0 = {x, y, A', B'}, q1 = {C', opacity, r, g} with A' = -0.5 log2e A, B' = -log2e B, C' = -0.5 log2e C
 __device__ __forceinline__ void stage_scale(float4 &q0, float4 &q1) {
     q0.z = __fmul_rn(q0.z, -0.5f * LOG2E);

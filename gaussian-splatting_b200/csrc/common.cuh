@@ -35,6 +35,14 @@ __device__ constexpr float SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f,
 //   q2 = { b, 1/depth, depth, bits }     bits: low 3 = SH clamp flags
 constexpr int SPLAT_F4 = 3;
 
+// ---- single-instruction approximate math (MUFU), for CULLING GEOMETRY ONLY ------------------------------------
+// The culling tests are conservative by construction (padded limits and spans), so <= 2 ulp approximations are
+// fine there, and as inline PTX they are evaluated identically wherever they appear (the counting and the emitting
+// pass must agree bit for bit).  Projection / covariance / blending arithmetic never uses these.
+__device__ __forceinline__ float sqrt_apx(const float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float div_apx(const float a, const float b) { float y; asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(y) : "f"(a), "f"(b)); return y; }
+__device__ __forceinline__ float rcp_apx(const float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
 // ---- host-side plumbing -------------------------------------------------------------------
 void set_error(const char *fmt, ...);
 extern int64_t g_launch_count;

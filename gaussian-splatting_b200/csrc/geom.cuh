@@ -132,8 +132,9 @@ __device__ __forceinline__ void sh_basis(const int deg, const float x, const flo
 //
 // Per tile row the hit columns are one contiguous span (convexity), found in O(1): the ellipse's
 // x-extent over the band dy in [y0,y1] is attained at the band point closest to the ellipse's
-// extreme point (x_r(dy) is concave).  All arithmetic uses round-to-nearest intrinsics so that the
-// counting pass (preprocess) and the emitting pass (binning) see bit-identical spans.
+// extreme point (x_r(dy) is concave).  All arithmetic is pinned (round-to-nearest intrinsics, MUFU approximations
+// through inline PTX: common.cuh) so that the counting pass (preprocess) and the emitting pass (binning) see
+// bit-identical spans.
 // ------------------------------------------------------------------------------------------
 struct CullGeom {
     float cx, cy;      // pixel-space mean
@@ -155,10 +156,10 @@ __device__ __forceinline__ void cull_rows(const CullGeom &g, int &ty0, int &ty1)
     if (g.lim < 0.0f) return;
     const float detc = __fmaf_rn(g.A, g.C, -__fmul_rn(g.B, g.B));
     if (!(detc > 0.0f)) { ty1 = g.ry1; return; }
-    const float ey = __fmaf_rn(__fsqrt_rn(__fdiv_rn(__fmul_rn(g.lim, g.A), detc)), 1.002f, 0.05f);
+    const float ey = __fmaf_rn(sqrt_apx(div_apx(__fmul_rn(g.lim, g.A), detc)), 1.002f, 0.05f);
     // rows whose pixel-centre band [16t, 16t+15] meets [cy-ey, cy+ey]
-    const float lo = __fdiv_rn(__fsub_rn(__fsub_rn(g.cy, ey), 15.0f), 16.0f);
-    const float hi = __fdiv_rn(__fadd_rn(g.cy, ey), 16.0f);
+    const float lo = div_apx(__fsub_rn(__fsub_rn(g.cy, ey), 15.0f), 16.0f);
+    const float hi = div_apx(__fadd_rn(g.cy, ey), 16.0f);
     const int a = (int)fminf(fmaxf(ceilf(lo), -1.0f), 65536.0f);
     const int b = (int)fminf(fmaxf(floorf(hi), -1.0f), 65536.0f) + 1;
     ty0 = max(g.ry0, a);
@@ -171,33 +172,33 @@ __device__ __forceinline__ void cull_span(const CullGeom &g, const int ty, int &
     tx0 = g.rx0; tx1 = g.rx1;
     const float detc = __fmaf_rn(g.A, g.C, -__fmul_rn(g.B, g.B));
     if (!(detc > 0.0f)) return;
-    const float ey = __fsqrt_rn(__fdiv_rn(__fmul_rn(g.lim, g.A), detc));
-    const float ex = __fsqrt_rn(__fdiv_rn(__fmul_rn(g.lim, g.C), detc));
+    const float ey = sqrt_apx(div_apx(__fmul_rn(g.lim, g.A), detc));
+    const float ex = sqrt_apx(div_apx(__fmul_rn(g.lim, g.C), detc));
     const float y0 = __fsub_rn((float)(ty * TILE), g.cy), y1 = __fadd_rn(y0, 15.0f);
     const float ylo = fmaxf(y0, -ey), yhi = fminf(y1, ey);
     const float m = __fmaf_rn(ex, 0.002f, 0.05f);
     if (ylo > yhi) {
         // band misses the ellipse by less than the row padding: keep the nearest point's span
         const float yc = (y0 > 0.0f) ? ey : -ey;
-        const float xc = __fdiv_rn(-__fmul_rn(g.B, yc), g.A);
-        const float l = __fdiv_rn(__fsub_rn(__fsub_rn(__fadd_rn(g.cx, xc), m), 15.0f), 16.0f);
-        const float h = __fdiv_rn(__fadd_rn(__fadd_rn(g.cx, xc), m), 16.0f);
+        const float xc = div_apx(-__fmul_rn(g.B, yc), g.A);
+        const float l = div_apx(__fsub_rn(__fsub_rn(__fadd_rn(g.cx, xc), m), 15.0f), 16.0f);
+        const float h = div_apx(__fadd_rn(__fadd_rn(g.cx, xc), m), 16.0f);
         tx0 = max(g.rx0, (int)fminf(fmaxf(ceilf(l), -1.0f), 65536.0f));
         tx1 = min(g.rx1, (int)fminf(fmaxf(floorf(h), -1.0f), 65536.0f) + 1);
         if (tx1 < tx0) tx1 = tx0;
         return;
     }
     // extreme points of the ellipse: x = +-ex at dy = -+(B/C) ex
-    const float dyR = __fmul_rn(__fdiv_rn(-g.B, g.C), ex);
+    const float dyR = __fmul_rn(div_apx(-g.B, g.C), ex);
     const float yr = fminf(fmaxf(dyR, ylo), yhi);
     const float yl = fminf(fmaxf(-dyR, ylo), yhi);
     const float Alim = __fmul_rn(g.A, g.lim);
     const float dr = fmaxf(__fmaf_rn(-detc, __fmul_rn(yr, yr), Alim), 0.0f);
     const float dl = fmaxf(__fmaf_rn(-detc, __fmul_rn(yl, yl), Alim), 0.0f);
-    const float xr = __fdiv_rn(__fadd_rn(-__fmul_rn(g.B, yr), __fsqrt_rn(dr)), g.A);
-    const float xl = __fdiv_rn(__fsub_rn(-__fmul_rn(g.B, yl), __fsqrt_rn(dl)), g.A);
-    const float l = __fdiv_rn(__fsub_rn(__fsub_rn(__fadd_rn(g.cx, xl), m), 15.0f), 16.0f);
-    const float h = __fdiv_rn(__fadd_rn(__fadd_rn(g.cx, xr), m), 16.0f);
+    const float xr = div_apx(__fadd_rn(-__fmul_rn(g.B, yr), sqrt_apx(dr)), g.A);
+    const float xl = div_apx(__fsub_rn(-__fmul_rn(g.B, yl), sqrt_apx(dl)), g.A);
+    const float l = div_apx(__fsub_rn(__fsub_rn(__fadd_rn(g.cx, xl), m), 15.0f), 16.0f);
+    const float h = div_apx(__fadd_rn(__fadd_rn(g.cx, xr), m), 16.0f);
     tx0 = max(g.rx0, (int)fminf(fmaxf(ceilf(l), -1.0f), 65536.0f));
     tx1 = min(g.rx1, (int)fminf(fmaxf(floorf(h), -1.0f), 65536.0f) + 1);
     if (tx1 < tx0) tx1 = tx0;

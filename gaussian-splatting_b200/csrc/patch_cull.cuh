@@ -17,11 +17,11 @@ __device__ __forceinline__ uint32_t patch_mask(const float cx, const float cy, c
     if (lim < 0.0f) return 0u;
     const float detc = A * C - B * B;
     if (!(detc > 0.0f)) return 0xffu;
-    const float inv_det = 1.0f / detc;
-    const float ex = sqrtf(lim * C * inv_det), ey = sqrtf(lim * A * inv_det);
+    const float inv_det = rcp_apx(detc);
+    const float ex = sqrt_apx(lim * C * inv_det), ey = sqrt_apx(lim * A * inv_det);
     const float m = fmaf(ex, 0.002f, 0.05f), my = fmaf(ey, 0.002f, 0.05f);
-    const float dyR = -B / C * ex;
-    const float Alim = A * lim, invA = 1.0f / A;
+    const float dyR = -B * rcp_apx(C) * ex;
+    const float Alim = A * lim, invA = rcp_apx(A);
     const float xa = ox - cx;   // tile origin relative to the mean
     uint32_t mask = 0;
 #pragma unroll
@@ -30,8 +30,8 @@ __device__ __forceinline__ uint32_t patch_mask(const float cx, const float cy, c
         const float ylo = fmaxf(y0, -ey - my), yhi = fminf(y1, ey + my);
         if (ylo > yhi) continue;
         const float yr = fminf(fmaxf(dyR, ylo), yhi), yl = fminf(fmaxf(-dyR, ylo), yhi);
-        const float xr = (-B * yr + sqrtf(fmaxf(Alim - detc * yr * yr, 0.0f))) * invA + m;
-        const float xl = (-B * yl - sqrtf(fmaxf(Alim - detc * yl * yl, 0.0f))) * invA - m;
+        const float xr = (-B * yr + sqrt_apx(fmaxf(Alim - detc * yr * yr, 0.0f))) * invA + m;
+        const float xl = (-B * yl - sqrt_apx(fmaxf(Alim - detc * yl * yl, 0.0f))) * invA - m;
         // columns: pixels [xa, xa+7] and [xa+8, xa+15] relative to the mean
         const bool c0 = (xr >= xa) && (xl <= xa + 7.0f);
         const bool c1 = (xr >= xa + 8.0f) && (xl <= xa + 15.0f);

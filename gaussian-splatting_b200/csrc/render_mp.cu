@@ -227,7 +227,7 @@ render_bwd_mp_kernel(const RenderBwdArgs a) {
                 g_r = __fmaf_rn(w, dL0[i], g_r); g_g = __fmaf_rn(w, dL1[i], g_g);
                 g_b = __fmaf_rn(w, dL2[i], g_b); g_d = __fmaf_rn(w, dLd[i], g_d);
                 const float om = __fsub_rn(1.0f, ai);
-                float dLda = T[i] * g - (S[i] - F[i]) * __frcp_rn(om);
+                float dLda = T[i] * g - (S[i] - F[i]) * rcp_approx(om);
                 T[i] = __fmul_rn(T[i], om);
                 dLda = valid[i] ? dLda : 0.0f;
                 g_o = __fmaf_rn(G[i], dLda, g_o);
@@ -369,7 +369,7 @@ render_bwd_mp2x_kernel(const RenderBwdArgs a) {
                 const f32x2 om = sub2(one2, ai);
                 float om0, om1;
                 unpk(om, om0, om1);
-                const f32x2 rcp = pk(__frcp_rn(om0), __frcp_rn(om1));
+                const f32x2 rcp = pk(rcp_approx(om0), rcp_approx(om1));
                 // dL/dalpha = T g - (S - F) / (1 - alpha); multiplied by G (0 for invalid lanes) wherever it is used
                 const f32x2 dLda = sub2(mul2(T[r], g), mul2(sub2(S[r], F[r]), rcp));
                 T[r] = mul2(T[r], om);

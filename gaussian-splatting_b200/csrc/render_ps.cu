@@ -224,7 +224,7 @@ render_bwd_ps_kernel(const RenderBwdArgs a) {
                 g_r = __fmaf_rn(wgt, dL0[i], g_r); g_g = __fmaf_rn(wgt, dL1[i], g_g); g_b = __fmaf_rn(wgt, dL2[i], g_b);
                 if (DEPTH) g_d = __fmaf_rn(wgt, dLd[i], g_d);
                 const float om = __fsub_rn(1.0f, ai);
-                float dLda = T[i] * g - (S[i] - F[i]) * __frcp_rn(om);
+                float dLda = T[i] * g - (S[i] - F[i]) * rcp_approx(om);
                 T[i] = __fmul_rn(T[i], om);
                 dLda = valid[i] ? dLda : 0.0f;
                 g_o = __fmaf_rn(G[i], dLda, g_o);
