@@ -296,6 +296,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    for kv in os.environ.get("GS_OPTS", "").split(","):      # tuning knobs for A/B runs, e.g. GS_OPTS=sort_small=1
+        if "=" in kv:
+            dgr.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     if world != a.gpus and rank == 0:
         print(f"# note: --gpus {a.gpus} but WORLD_SIZE {world}; using {world}", file=sys.stderr)
 

@@ -102,5 +102,6 @@ int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *val
                const unsigned long long *n_dev, int begin_bit, int end_bit, void *scratch, bool debug,
                cudaStream_t stream, int V = 1, size_t sv = 0);
 extern int g_sort_variant;
+extern int g_sort_force_small;
 
 }  // namespace gsb

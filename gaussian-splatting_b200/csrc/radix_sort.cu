@@ -22,8 +22,9 @@ constexpr int SORT_THREADS = 256;
 // 148 SMs with several blocks each (the first version ran 245 blocks of 4096 keys: latency bound)
 constexpr int SORT_IPT_BIG = 16;
 constexpr int SORT_IPT_SMALL = 4;
-constexpr int64_t SORT_SMALL_LIMIT = 148 * 4 * 4096;
-static inline int sort_ipt(int64_t n) { return n < SORT_SMALL_LIMIT ? SORT_IPT_SMALL : SORT_IPT_BIG; }
+constexpr int64_t SORT_SMALL_LIMIT = 148 * 4 * 1024;   // below ~0.6 M keys: 1024-key blocks to fill the SMs
+int g_sort_force_small = 0;   // option "sort_small": 1 = 4 keys per thread for every size (A/B)
+static inline int sort_ipt(int64_t n) { return (g_sort_force_small || n < SORT_SMALL_LIMIT) ? SORT_IPT_SMALL : SORT_IPT_BIG; }
 
 template <int SORT_IPT>
 __global__ void __launch_bounds__(SORT_THREADS)
@@ -259,7 +260,7 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
     }
     __syncthreads();
 
-    // per-digit block count; warp_cnt becomes the exclusive prefix over warps
+    // per-digit block count; warp_cnt becomes the exclusive prefix over warps (position inside the block's digit run)
     uint32_t cnt = 0;
 #pragma unroll
     for (int k = 0; k < SORT_THREADS / 32; ++k) {
@@ -297,19 +298,49 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
         }
         *my = ((excl + cnt) & OS_VALUE_MASK) | OS_FLAG_PREFIX;
     }
-    const uint32_t run = digit_base + excl;
+
+    // Local reorder: the block's pairs are first put in digit order in shared memory, then written out so that
+    // consecutive threads write consecutive addresses inside each digit's run.  A direct scatter writes one 4-byte
+    // element per 32-byte sector (12.5 % sector efficiency); runs of KPB/256 keys fill whole sectors.
+    __shared__ uint32_t sk[SORT_KPB], svals[SORT_KPB];
+    __shared__ uint32_t loff[RADIX], gpos[RADIX];
+    {   // exclusive scan of cnt over the 256 digits -> local start of each digit's run
+        uint32_t inc = cnt;
 #pragma unroll
-    for (int k = 0; k < SORT_THREADS / 32; ++k) warp_cnt[k][tid] += run;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t2 = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t2;
+        }
+        __syncthreads();                 // warp_sums is reused: everyone has finished reading it for digit_base
+        if (lane == 31) warp_sums[w] = inc;
+        __syncthreads();
+        uint32_t lo = inc - cnt;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < w) lo += warp_sums[k];
+        loff[tid] = lo;
+        gpos[tid] = digit_base + excl;
+    }
     __syncthreads();
+    const int64_t block_start = (int64_t)b * SORT_KPB;
+    const int block_n = (int)min((int64_t)SORT_KPB, n - block_start);
 #pragma unroll
     for (int r = 0; r < SORT_IPT; ++r) {
         const int64_t idx = seg + r * 32 + lane;
         if (idx < n) {
             const uint32_t d = (key[r] >> shift) & mask;
-            const uint32_t pos = warp_cnt[w][d] + rank[r];
-            keys_out[pos] = key[r];
-            vals_out[pos] = vals_in[idx];
+            const uint32_t lp = loff[d] + warp_cnt[w][d] + rank[r];
+            sk[lp] = key[r];
+            svals[lp] = vals_in[idx];
         }
+    }
+    __syncthreads();
+    for (int i = tid; i < block_n; i += SORT_THREADS) {
+        const uint32_t k2 = sk[i];
+        const uint32_t d = (k2 >> shift) & mask;
+        const uint32_t pos = gpos[d] + ((uint32_t)i - loff[d]);
+        keys_out[pos] = k2;
+        vals_out[pos] = svals[i];
     }
 }
 
