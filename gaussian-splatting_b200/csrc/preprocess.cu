@@ -132,8 +132,9 @@ __device__ __forceinline__ void preprocess_fwd_body(const CamParams &cam, const 
                     sh_basis(cam.sh_degree, dx * inv, dy * inv, dz * inv, bas);
                     const int nb = (cam.sh_degree + 1) * (cam.sh_degree + 1);
                     const float *sh = sh_row;
-                    for (int k = 0; k < nb; ++k) {
-                        r += bas[k] * sh[3 * k]; g += bas[k] * sh[3 * k + 1]; b += bas[k] * sh[3 * k + 2];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {   // compile-time bound: bas[] stays in registers
+                        if (k < nb) { r += bas[k] * sh[3 * k]; g += bas[k] * sh[3 * k + 1]; b += bas[k] * sh[3 * k + 2]; }
                     }
                     r += 0.5f; g += 0.5f; b += 0.5f;
                     if (r < 0.f) { bits |= 1u; r = 0.f; }
@@ -296,9 +297,12 @@ __device__ __forceinline__ void preprocess_bwd_view(const CamParams &cam, const 
             d_rgb_sh[2] = (bits & 4u) ? 0.f : d_rgb[2];
             const float *sh = sh_row;
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;
-            for (int k = 1; k < nb; ++k) {
-                const float s = sh[3 * k] * d_rgb_sh[0] + sh[3 * k + 1] * d_rgb_sh[1] + sh[3 * k + 2] * d_rgb_sh[2];
-                ddx += bx[k] * s; ddy += by[k] * s; ddz += bz[k] * s;
+#pragma unroll
+            for (int k = 1; k < 16; ++k) {   // compile-time bound: bx/by/bz stay in registers
+                if (k < nb) {
+                    const float s = sh[3 * k] * d_rgb_sh[0] + sh[3 * k + 1] * d_rgb_sh[1] + sh[3 * k + 2] * d_rgb_sh[2];
+                    ddx += bx[k] * s; ddy += by[k] * s; ddz += bz[k] * s;
+                }
             }
             const float dot = ux * ddx + uy * ddy + uz * ddz;
             gm[0] += (ddx - ux * dot) * inv; gm[1] += (ddy - uy * dot) * inv; gm[2] += (ddz - uz * dot) * inv;
@@ -467,10 +471,14 @@ preprocess_bwd_kernel(const CamArgs ca, const PreBwdArgs a) {
     // SH gradient rows go out through shared memory (coalesced); each thread rewrites only its own row
     if (a.g.dL_dshs && a.shs) {
         if (live) {
-            for (int k = 0; k < M; ++k) {
-                const float bk = (k < nb && k < 16) ? g.bas[k] : 0.f;
-                sh_row[3 * k] = bk * g.d_rgb_sh[0]; sh_row[3 * k + 1] = bk * g.d_rgb_sh[1]; sh_row[3 * k + 2] = bk * g.d_rgb_sh[2];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (k < M) {
+                    const float bk = k < nb ? g.bas[k] : 0.f;
+                    sh_row[3 * k] = bk * g.d_rgb_sh[0]; sh_row[3 * k + 1] = bk * g.d_rgb_sh[1]; sh_row[3 * k + 2] = bk * g.d_rgb_sh[2];
+                }
             }
+            for (int k = 16; k < M; ++k) { sh_row[3 * k] = 0.f; sh_row[3 * k + 1] = 0.f; sh_row[3 * k + 2] = 0.f; }
         }
         __syncthreads();
         stage_rows_out<ACC>(a.g.dL_dshs, sh_rows, row0, nrows, shn);
@@ -531,9 +539,12 @@ preprocess_bwd_batch_kernel(const CamArgsBatch cb, const PreBwdArgs a, const Pre
             for (int c = 0; c < 6; ++c) dS[c] += g.dS[c];
             g_op += g.g_op;
             if (want_sh) {
-                for (int k = 0; k < nb && k < 16; ++k) {
-                    gr[3 * k] += g.bas[k] * g.d_rgb_sh[0]; gr[3 * k + 1] += g.bas[k] * g.d_rgb_sh[1];
-                    gr[3 * k + 2] += g.bas[k] * g.d_rgb_sh[2];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (k < nb) {
+                        gr[3 * k] += g.bas[k] * g.d_rgb_sh[0]; gr[3 * k + 1] += g.bas[k] * g.d_rgb_sh[1];
+                        gr[3 * k + 2] += g.bas[k] * g.d_rgb_sh[2];
+                    }
                 }
             }
             if (a.g.dL_dmeans2D) {
