@@ -151,6 +151,101 @@ render_fwd_pc_kernel(const RenderFwdArgs a) {
     }
 }
 
+// Forward, two pixels per lane: a warp owns one 16x4 band of the tile (both 8x4 patches of that band); lane l
+// blends pixels (l & 7, l >> 3) of the left and of the right patch, i.e. two pixels 8 columns apart that share dy and
+// every per-gaussian operand, so their FP32 arithmetic runs as packed f32x2 instructions (FFMA2).  Culling stays at
+// patch granularity through the staged 8-bit mask: a warp walks the gaussians that reach either of its two patches.
+__global__ void __launch_bounds__(128)
+render_fwd_pc2_kernel(const RenderFwdArgs a) {
+    constexpr int NT = 128;
+    __shared__ float4 s0[RB], s1[RB];
+    __shared__ float2 s2[RB];
+    __shared__ uint8_t smask[RB];
+    __shared__ uint8_t slist[4][RB];
+    const int tile = blockIdx.x;
+    const int tile_x = tile % a.gx, tile_y = tile / a.gx;
+    const int t = threadIdx.x, w = t >> 5, l = t & 31;
+    const int px0 = tile_x * TILE + (l & 7), py = tile_y * TILE + 4 * w + (l >> 3);
+    const float fx0 = (float)px0, fy = (float)py;
+    const float ox = (float)(tile_x * TILE), oy = (float)(tile_y * TILE);
+    const uint2 range = a.ranges[tile];
+    const int todo = (int)(range.y - range.x);
+    const int rounds = (todo + RB - 1) / RB;
+
+    bool done0 = !(px0 < a.W && py < a.H), done1 = !(px0 + 8 < a.W && py < a.H);
+    f32x2 T = pk1(1.0f), C0 = pk1(0.f), C1 = C0, C2 = C0, Dp = C0;
+    uint32_t last0 = 0, last1 = 0;
+    const f32x2 one2 = pk1(1.0f);
+
+    for (int rd = 0; rd < rounds; ++rd) {
+        if (__syncthreads_and(done0 && done1)) break;
+        const int n = min(RB, todo - rd * RB);
+        for (int k = t; k < n; k += NT) {
+            const uint32_t g = a.point_list[range.x + rd * RB + k];
+            const float4 *rec = a.splat + (size_t)g * SPLAT_F4;
+            float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
+            const float4 q2 = __ldg(rec + 2);
+            smask[k] = (uint8_t)patch_mask(q0.x, q0.y, q0.z, q0.w, q1.x, q2.z, ox, oy);
+            stage_scale(q0, q1);
+            s0[k] = q0; s1[k] = q1; s2[k] = make_float2(q2.x, q2.y);
+        }
+        __syncthreads();
+        const int cnt = compact_hits(smask, n, 3u << (2 * w), slist[w]);
+        for (int k = 0; k < cnt; ++k) {
+            if (done0 && done1) break;
+            const int j = slist[w][k];
+            const float4 q0 = s0[j];
+            const float4 q1 = s1[j];
+            const f32x2 dx2 = pk(q0.x - fx0, q0.x - (fx0 + 8.0f));
+            const float dy = q0.y - fy;
+            const float Cyy = __fmul_rn(__fmul_rn(q1.x, dy), dy);
+            const f32x2 Axx2 = mul2(mul2(pk1(q0.z), dx2), dx2);
+            const f32x2 p2 = fma2(mul2(pk1(q0.w), dx2), pk1(dy), add2(Axx2, pk1(Cyy)));   // power2_at, both columns
+            float p0, p1;
+            unpk(p2, p0, p1);
+            const float al0 = fminf(ALPHA_MAX, __fmul_rn(q1.y, ex2_approx(p0)));
+            const float al1 = fminf(ALPHA_MAX, __fmul_rn(q1.y, ex2_approx(p1)));
+            const bool v0 = (p0 <= 0.0f) && (al0 >= ALPHA_MIN) && !done0;
+            const bool v1 = (p1 <= 0.0f) && (al1 >= ALPHA_MIN) && !done1;
+            if (!__any_sync(0xffffffffu, v0 || v1)) continue;
+            const f32x2 al2 = pk(al0, al1);
+            const f32x2 tT = mul2(T, sub2(one2, al2));
+            float t0, t1;
+            unpk(tT, t0, t1);
+            const bool stop0 = v0 && (t0 < T_STOP), stop1 = v1 && (t1 < T_STOP);
+            done0 = done0 || stop0; done1 = done1 || stop1;
+            const bool u0 = v0 && !stop0, u1 = v1 && !stop1;
+            const f32x2 wgt = mul2(pk(u0 ? al0 : 0.0f, u1 ? al1 : 0.0f), T);
+            const float2 q2 = s2[j];
+            C0 = fma2(pk1(q1.z), wgt, C0); C1 = fma2(pk1(q1.w), wgt, C1); C2 = fma2(pk1(q2.x), wgt, C2);
+            Dp = fma2(pk1(q2.y), wgt, Dp);
+            float T0, T1;
+            unpk(T, T0, T1);
+            T = pk(u0 ? t0 : T0, u1 ? t1 : T1);
+            const uint32_t pos = (uint32_t)(rd * RB + j + 1);
+            last0 = u0 ? pos : last0; last1 = u1 ? pos : last1;
+        }
+    }
+    const float bg0 = __ldg(a.bg), bg1 = __ldg(a.bg + 1), bg2 = __ldg(a.bg + 2);
+    const size_t HW = (size_t)a.W * a.H;
+    float Tl, Th, c0l, c0h, c1l, c1h, c2l, c2h, dl, dh;
+    unpk(T, Tl, Th); unpk(C0, c0l, c0h); unpk(C1, c1l, c1h); unpk(C2, c2l, c2h); unpk(Dp, dl, dh);
+    if (py < a.H) {
+        if (px0 < a.W) {
+            const size_t pid = (size_t)py * a.W + px0;
+            a.final_T[pid] = Tl; a.n_contrib[pid] = last0;
+            a.out_color[pid] = c0l + Tl * bg0; a.out_color[HW + pid] = c1l + Tl * bg1; a.out_color[2 * HW + pid] = c2l + Tl * bg2;
+            a.out_invdepth[pid] = dl;
+        }
+        if (px0 + 8 < a.W) {
+            const size_t pid = (size_t)py * a.W + px0 + 8;
+            a.final_T[pid] = Th; a.n_contrib[pid] = last1;
+            a.out_color[pid] = c0h + Th * bg0; a.out_color[HW + pid] = c1h + Th * bg1; a.out_color[2 * HW + pid] = c2h + Th * bg2;
+            a.out_invdepth[pid] = dh;
+        }
+    }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -298,6 +393,8 @@ int launch_render_fwd(const RenderFwdArgs &a, int variant, bool debug, cudaStrea
     if (tiles <= 0) return GSB_OK;
     if (variant == 4) {
         GSB_LAUNCH("render_fwd", debug, stream, render_fwd_pc_kernel<1>, tiles, 256, 0, a);
+    } else if (variant == 9) {   // two pixels per lane, packed f32x2 arithmetic
+        GSB_LAUNCH("render_fwd", debug, stream, render_fwd_pc2_kernel, tiles, 128, 0, a);
     } else if (variant == 6) {   // register budget for 6 CTAs (48 warps) per SM
         GSB_LAUNCH("render_fwd", debug, stream, render_fwd_pc_kernel<6>, tiles, 256, 0, a);
     } else if (variant == 8) {   // 8 CTAs (64 warps) per SM
