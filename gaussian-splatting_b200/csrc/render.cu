@@ -192,7 +192,8 @@ render_fwd_pc2_kernel(const RenderFwdArgs a) {
         __syncthreads();
         const int cnt = compact_hits(smask, n, 3u << (2 * w), slist[w]);
         for (int k = 0; k < cnt; ++k) {
-            if (done0 && done1) break;
+            // warp-uniform exit: the vote below needs all 32 lanes, so a lane may not leave on its own
+            if (__all_sync(0xffffffffu, done0 && done1)) break;
             const int j = slist[w][k];
             const float4 q0 = s0[j];
             const float4 q1 = s1[j];
