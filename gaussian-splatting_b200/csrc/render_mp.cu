@@ -251,8 +251,8 @@ render_bwd_mp_kernel(const RenderBwdArgs a) {
 // Packed variant of render_bwd_mp_kernel<2, CULL>: the two pixels of a row of the thread's 2x2 block share every
 // per-gaussian operand, so their FP32 mul / add / fma run as f32x2 instructions (FFMA2): ~20 % fewer issue slots.
 // Arithmetic per lane is IEEE round-to-nearest exactly as in the scalar kernel.
-template <bool CULL, bool DEPTH>
-__global__ void __launch_bounds__(64)
+template <bool CULL, bool DEPTH, int MINB>
+__global__ void __launch_bounds__(64, MINB)
 render_bwd_mp2x_kernel(const RenderBwdArgs a) {
     constexpr int NT = 64;
     __shared__ float4 s0[MP_R], s1[MP_R];
@@ -418,9 +418,17 @@ int launch_render_bwd_mp(const RenderBwdArgs &a, int qh, bool debug, cudaStream_
         GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp_kernel<2, false, 1>), tiles, 64, 0, a);
     } else if (qh == -20) {   // packed f32x2 arithmetic (FFMA2), sub-tile culling
         if (a.dL_dinvdepth) {
-            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, true>), tiles, 64, 0, a);
+            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, true, 1>), tiles, 64, 0, a);
         } else {
-            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, false>), tiles, 64, 0, a);
+            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, false, 1>), tiles, 64, 0, a);
+        }
+    } else if (qh == -21 || qh == -22) {   // same, register budget for 12 / 16 CTAs per SM
+        if (a.dL_dinvdepth) {
+            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, true, 12>), tiles, 64, 0, a);
+        } else if (qh == -21) {
+            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, false, 12>), tiles, 64, 0, a);
+        } else {
+            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, false, 16>), tiles, 64, 0, a);
         }
     } else if (qh == -12) {   // as -2, register budget for 12 CTAs / SM
         GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp_kernel<2, true, 12>), tiles, 64, 0, a);
