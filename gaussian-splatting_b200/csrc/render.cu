@@ -82,7 +82,7 @@ render_fwd_kernel(const RenderFwdArgs a) {
 
 // forward with sub-tile culling: each warp (8x4 patch) walks only the staged gaussians whose cull ellipse
 // meets its patch (patch_cull.cuh).  Blend arithmetic identical to render_fwd_kernel.
-template <int MINB>
+template <int MINB, bool PREFETCH>
 __global__ void __launch_bounds__(256, MINB)
 render_fwd_pc_kernel(const RenderFwdArgs a) {
     __shared__ float4 s0[RB], s1[RB];
@@ -120,10 +120,19 @@ render_fwd_pc_kernel(const RenderFwdArgs a) {
         __syncthreads();
         const int n = min(RB, todo - rd * RB);
         const int cnt = compact_hits(smask, n, 1u << w, slist[w]);
+        // PREFETCH: the next list entry's record is read from shared memory while the current one is blended
+        int jn = 0;
+        float4 q0n = make_float4(0.f, 0.f, 0.f, 0.f), q1n = q0n;
+        if (PREFETCH && cnt > 0) { jn = slist[w][0]; q0n = s0[jn]; q1n = s1[jn]; }
         for (int k = 0; !done && k < cnt; ++k) {
-            const int j = slist[w][k];
-            const float4 q0 = s0[j];
-            const float4 q1 = s1[j];
+            int j;
+            float4 q0, q1;
+            if (PREFETCH) {
+                j = jn; q0 = q0n; q1 = q1n;
+                if (k + 1 < cnt) { jn = slist[w][k + 1]; q0n = s0[jn]; q1n = s1[jn]; }
+            } else {
+                j = slist[w][k]; q0 = s0[j]; q1 = s1[j];
+            }
             const float dx = q0.x - fx, dy = q0.y - fy;
             // same operation order as render_mp.cu / render_ps.cu, so forward and backward agree bit for bit on alpha
             const float power = power2_at(__fmul_rn(__fmul_rn(q0.z, dx), dx), __fmul_rn(__fmul_rn(q1.x, dy), dy), __fmul_rn(q0.w, dx), dy);
@@ -393,13 +402,15 @@ int launch_render_fwd(const RenderFwdArgs &a, int variant, bool debug, cudaStrea
     const int tiles = a.gx * a.gy;
     if (tiles <= 0) return GSB_OK;
     if (variant == 4) {
-        GSB_LAUNCH("render_fwd", debug, stream, render_fwd_pc_kernel<1>, tiles, 256, 0, a);
+        GSB_LAUNCH("render_fwd", debug, stream, (render_fwd_pc_kernel<1, false>), tiles, 256, 0, a);
+    } else if (variant == 7) {   // 6 CTAs/SM + shared-memory prefetch of the next record
+        GSB_LAUNCH("render_fwd", debug, stream, (render_fwd_pc_kernel<6, true>), tiles, 256, 0, a);
     } else if (variant == 9) {   // two pixels per lane, packed f32x2 arithmetic
         GSB_LAUNCH("render_fwd", debug, stream, render_fwd_pc2_kernel, tiles, 128, 0, a);
     } else if (variant == 6) {   // register budget for 6 CTAs (48 warps) per SM
-        GSB_LAUNCH("render_fwd", debug, stream, render_fwd_pc_kernel<6>, tiles, 256, 0, a);
+        GSB_LAUNCH("render_fwd", debug, stream, (render_fwd_pc_kernel<6, false>), tiles, 256, 0, a);
     } else if (variant == 8) {   // 8 CTAs (64 warps) per SM
-        GSB_LAUNCH("render_fwd", debug, stream, render_fwd_pc_kernel<8>, tiles, 256, 0, a);
+        GSB_LAUNCH("render_fwd", debug, stream, (render_fwd_pc_kernel<8, false>), tiles, 256, 0, a);
     } else {
         GSB_LAUNCH("render_fwd", debug, stream, render_fwd_kernel, tiles, 256, 0, a);
     }

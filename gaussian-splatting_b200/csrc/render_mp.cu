@@ -251,7 +251,7 @@ render_bwd_mp_kernel(const RenderBwdArgs a) {
 // Packed variant of render_bwd_mp_kernel<2, CULL>: the two pixels of a row of the thread's 2x2 block share every
 // per-gaussian operand, so their FP32 mul / add / fma run as f32x2 instructions (FFMA2): ~20 % fewer issue slots.
 // Arithmetic per lane is IEEE round-to-nearest exactly as in the scalar kernel.
-template <bool CULL, bool DEPTH, int MINB>
+template <bool CULL, bool DEPTH, int MINB, bool PREFETCH>
 __global__ void __launch_bounds__(64, MINB)
 render_bwd_mp2x_kernel(const RenderBwdArgs a) {
     constexpr int NT = 64;
@@ -317,10 +317,18 @@ render_bwd_mp2x_kernel(const RenderBwdArgs a) {
         __syncthreads();
         const int nw = max(0, min(n, my_todo - base));
         const int cnt = CULL ? compact_hits(smask, nw, want, slist[CULL ? (t >> 5) : 0]) : nw;
+        int jn = 0;
+        float4 q0n = make_float4(0.f, 0.f, 0.f, 0.f), q1n = q0n;
+        if (PREFETCH && cnt > 0) { jn = CULL ? (int)slist[CULL ? (t >> 5) : 0][0] : 0; q0n = s0[jn]; q1n = s1[jn]; }
         for (int kk = 0; kk < cnt; ++kk) {
-            const int j = CULL ? (int)slist[CULL ? (t >> 5) : 0][kk] : kk;
-            const float4 q0 = s0[j];
-            const float4 q1 = s1[j];
+            int j;
+            float4 q0, q1;
+            if (PREFETCH) {   // next record read from shared memory while this one is processed
+                j = jn; q0 = q0n; q1 = q1n;
+                if (kk + 1 < cnt) { jn = CULL ? (int)slist[CULL ? (t >> 5) : 0][kk + 1] : kk + 1; q0n = s0[jn]; q1n = s1[jn]; }
+            } else {
+                j = CULL ? (int)slist[CULL ? (t >> 5) : 0][kk] : kk; q0 = s0[j]; q1 = s1[j];
+            }
             const uint32_t pos = (uint32_t)(base + j + 1);
             // column-packed terms (shared by both rows): dx, A' dx^2, B' dx
             const f32x2 dx2 = pk(q0.x - fx0, q0.x - (fx0 + 1.0f));   // same rounding as the one-pixel kernels
@@ -418,17 +426,23 @@ int launch_render_bwd_mp(const RenderBwdArgs &a, int qh, bool debug, cudaStream_
         GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp_kernel<2, false, 1>), tiles, 64, 0, a);
     } else if (qh == -20) {   // packed f32x2 arithmetic (FFMA2), sub-tile culling
         if (a.dL_dinvdepth) {
-            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, true, 1>), tiles, 64, 0, a);
+            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, true, 1, false>), tiles, 64, 0, a);
         } else {
-            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, false, 1>), tiles, 64, 0, a);
+            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, false, 1, false>), tiles, 64, 0, a);
         }
     } else if (qh == -21 || qh == -22) {   // same, register budget for 12 / 16 CTAs per SM
         if (a.dL_dinvdepth) {
-            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, true, 12>), tiles, 64, 0, a);
+            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, true, 12, false>), tiles, 64, 0, a);
         } else if (qh == -21) {
-            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, false, 12>), tiles, 64, 0, a);
+            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, false, 12, false>), tiles, 64, 0, a);
         } else {
-            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, false, 16>), tiles, 64, 0, a);
+            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, false, 16, false>), tiles, 64, 0, a);
+        }
+    } else if (qh == -23) {   // 16 CTAs/SM + shared-memory prefetch of the next record
+        if (a.dL_dinvdepth) {
+            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, true, 12, true>), tiles, 64, 0, a);
+        } else {
+            GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp2x_kernel<true, false, 16, true>), tiles, 64, 0, a);
         }
     } else if (qh == -12) {   // as -2, register budget for 12 CTAs / SM
         GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_mp_kernel<2, true, 12>), tiles, 64, 0, a);
