@@ -247,7 +247,8 @@ struct ViewGrad {
 
 // K8 for one gaussian and one view: chain rule from the blend kernel's accumulators (mean2D / conic or raw moments, opacity,
 // rgb, inverse depth) to the rasterizer inputs.  Every field of `o` is written.
-__device__ __forceinline__ void preprocess_bwd_view(const CamParams &cam, const PreBwdArgs &a, const int i, const float *sh_row,
+// Returns false when the gaussian received no gradient in this view (all fields of `o` are zero then).
+__device__ __forceinline__ bool preprocess_bwd_view(const CamParams &cam, const PreBwdArgs &a, const int i, const float *sh_row,
                                                     const uint32_t bits, ViewGrad &o) {
     float (&gm)[3] = o.gm; float (&g_m2)[2] = o.g_m2; float &g_op = o.g_op; float (&g_rgb)[3] = o.g_rgb;
     float (&g_sc)[3] = o.g_sc; float (&g_rot)[4] = o.g_rot; float (&dS)[6] = o.dS; float (&d_rgb_sh)[3] = o.d_rgb_sh;
@@ -267,6 +268,11 @@ __device__ __forceinline__ void preprocess_bwd_view(const CamParams &cam, const 
     if (visible) {
         const float4 *acc = reinterpret_cast<const float4 *>(a.dacc + (size_t)i * DACC_STRIDE);
         const float4 A0 = acc[0], A1 = acc[1], A2 = acc[2];
+        // A gaussian no pixel blended in this view (occluded, or behind every pixel's stopping point) has an all-zero
+        // accumulator row: every gradient below would be an exact zero, so the chain rule is skipped.
+        if (A0.x == 0.f && A0.y == 0.f && A0.z == 0.f && A0.w == 0.f && A1.x == 0.f && A1.y == 0.f && A1.z == 0.f && A1.w == 0.f &&
+            A2.x == 0.f && A2.y == 0.f)
+            return false;
         float d_m2x = A0.x, d_m2y = A0.y;
         float dA = A0.z, dB = A0.w, dC = A1.x;
         if (a.moments) {
@@ -417,6 +423,7 @@ __device__ __forceinline__ void preprocess_bwd_view(const CamParams &cam, const 
         }
     }
 
+    return visible;
 }
 
 template <bool ACC>
@@ -530,7 +537,13 @@ preprocess_bwd_batch_kernel(const CamArgsBatch cb, const PreBwdArgs a, const Pre
                 continue;
             }
             ViewGrad g;
-            preprocess_bwd_view(cams[v], av, i, sh_row, bits, g);
+            if (!preprocess_bwd_view(cams[v], av, i, sh_row, bits, g)) {
+                if (a.g.dL_dmeans2D) {
+                    float *m2 = a.g.dL_dmeans2D + (size_t)v * st.means2D + 3 * (size_t)i;
+                    m2[0] = 0.f; m2[1] = 0.f; m2[2] = 0.f;
+                }
+                continue;
+            }
 #pragma unroll
             for (int c = 0; c < 3; ++c) { gm[c] += g.gm[c]; g_rgb[c] += g.g_rgb[c]; g_sc[c] += g.g_sc[c]; }
 #pragma unroll
