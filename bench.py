@@ -341,7 +341,8 @@ def main():
     step_counter = [0]
 
     def step(host_inputs: bool):
-        bucket.zero_()
+        if a.api != "views":
+            bucket.zero_()
         if a.api == "views":
             def loss_fn(img, _invdepth, i):
                 if host_inputs:
@@ -351,7 +352,7 @@ def main():
                     return res
                 return dgr.l1_loss_and_grad(img, gt_dev[i])
             out = render_views_backward(HostCams() if host_inputs else cams, pc, pipe, bg, loss_fn, loss_returns_grad=True,
-                                        batched=not a.no_batch)
+                                        batched=not a.no_batch, overwrite=True)   # first chunk writes the bucket: no zeroing pass
             total = out["losses"].sum()
         else:
             total = torch.zeros((), device=dev)

@@ -5,7 +5,7 @@
 
 namespace gsb {
 
-constexpr int MP_R = 128;           // gaussians staged per round
+constexpr int MP_R = 128;           // gaussians staged per round (256 measured 2 % slower)
 constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ float ex2_approx(const float x) {

@@ -118,7 +118,8 @@ def _settings_for(cam, pc, pipe, bg_color, scaling_modifier):
 
 def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch.Tensor, loss_fn, *,
                           scaling_modifier: float = 1.0, densify_stats: Optional[dict] = None,
-                          keep_images: bool = False, loss_returns_grad: bool = False, batched: bool = True) -> dict:
+                          keep_images: bool = False, loss_returns_grad: bool = False, batched: bool = True,
+                          overwrite: bool = False) -> dict:
     """Fused view-batch training step: forward + loss + backward for every camera, with the per-gaussian
     gradients of ALL views summed in place.
 
@@ -133,6 +134,9 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
     with ``loss_returns_grad=True``, ``loss_fn(raw_image, invdepth, view_index) -> (loss, dL/d raw_image[, dL/d invdepth])``
     for a loss that brings its own gradient (e.g. ``diff_gaussian_rasterization.l1_loss_and_grad``); no autograd then.
     Returns {"losses": [V] tensor, "radii_max": [P] int32, "images": list (if keep_images)}.
+
+    ``overwrite=True``: the gradient buffers are WRITTEN by the first chunk of views instead of added to, so the
+    caller does not have to zero them first (saves one memset and one read pass over the 59 floats/gaussian).
 
     ``batched=True`` (default, up to 16 views of equal size per chunk) goes through gsb_forward_batch /
     gsb_backward_batch: the gaussians' parameters are read once for all views in the per-gaussian kernels, the
@@ -195,7 +199,7 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
             if densify_stats is not None:
                 vg["means2D"] = torch.empty((len(chunk), P, 3), dtype=torch.float32, device=dev)
             _dgr._backward_batch_impl(pack, rss, c["means3D"], c["shs"], c["opacities"], c["scales"], c["rotations"], color,
-                                      invdepth, g_color, g_depth, vg, accumulate=True)
+                                      invdepth, g_color, g_depth, vg, accumulate=not (overwrite and c0 == 0))
             torch.maximum(radii_max, radii.max(dim=0).values, out=radii_max)
             if densify_stats is not None:
                 vis = radii > 0                                               # [V,P]
@@ -223,7 +227,7 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
             vg["means2D"] = m2d
         _dgr._backward_impl(pack, rs, c["means3D"], c["shs"], None, c["opacities"], c["scales"], c["rotations"], None,
                             color.detach(), invdepth.detach(), _dgr._f32c(g_img), _dgr._f32c(g_dep), vg,
-                            accumulate=True, accumulate_means2D=False)
+                            accumulate=not (overwrite and vi == 0), accumulate_means2D=False)
         torch.maximum(radii_max, radii, out=radii_max)
         if densify_stats is not None:
             # add_densification_stats (gaussian_model.py:471-473) + max_radii2D update (train.py:166), sync-free

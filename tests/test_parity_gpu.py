@@ -335,6 +335,12 @@ def test_batched_calls_match_single_view_calls(nviews):
     assert np.allclose(a[0], b[0], rtol=1e-6, atol=1e-7)
     for x, y in zip(a[2], b[2]):
         assert np.array_equal(x, y)
+    # overwrite=True: the first chunk WRITES the gradient buffers, whatever they held
+    pc = bench.BenchGaussians(scene, 3, dev)
+    bucket = GradientBucket(pc.parameters())
+    bucket.flat.fill_(123.0)
+    render_views_backward(cams, pc, bench.Pipe(), bg, lambda img, d, i: (img - gts[i]).abs().mean() + 0.05 * d.mean(), overwrite=True)
+    assert np.abs(bucket.flat.cpu().numpy() - b[1]).max() <= 1e-4 * np.abs(b[1]).max()
     assert np.abs(a[1] - b[1]).max() <= 1e-4 * np.abs(a[1]).max()
     assert np.abs(a[3] - b[3]).max() <= 1e-4 * (np.abs(a[3]).max() + 1e-20)
     assert np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])
