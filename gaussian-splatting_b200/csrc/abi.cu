@@ -365,7 +365,7 @@ int32_t gsb_backward(const GsbSettings *s, const GsbInputs *in, const GsbState *
         ra.point_list = st->point_list;
         ra.splat = splat; ra.bg = s->bg; ra.final_T = st->final_T; ra.n_contrib = st->n_contrib; ra.dL_dcolor = dL_dcolor;
         ra.dL_dinvdepth = dL_dinvdepth; ra.dacc = dacc; ra.out_color = out_color; ra.out_invdepth = out_invdepth;
-        rc = opt_bwd_variant == 5 ? launch_render_bwd_ps(ra, debug, stream) : opt_bwd_variant >= 2 ? launch_render_bwd_mp(ra, opt_bwd_variant == 3 ? 4 : (opt_bwd_variant == 4 ? -2 : (opt_bwd_variant == 6 ? -12 : (opt_bwd_variant == 7 ? -16 : (opt_bwd_variant == 8 ? -20 : (opt_bwd_variant == 9 ? -21 : (opt_bwd_variant == 10 ? -22 : (opt_bwd_variant == 11 ? -23 : 2))))))), debug, stream)
+        rc = opt_bwd_variant == 5 ? launch_render_bwd_ps(ra, debug, stream) : opt_bwd_variant >= 2 ? launch_render_bwd_mp(ra, opt_bwd_variant == 3 ? 4 : (opt_bwd_variant == 4 ? -2 : (opt_bwd_variant == 6 ? -12 : (opt_bwd_variant == 7 ? -16 : (opt_bwd_variant == 8 ? -20 : (opt_bwd_variant == 9 ? -21 : (opt_bwd_variant == 10 ? -22 : (opt_bwd_variant == 11 ? -23 : (opt_bwd_variant == 12 ? -24 : 2)))))))), debug, stream)
                                   : launch_render_bwd(ra, opt_bwd_variant, debug, stream);
         if (rc) return rc;
     }
@@ -385,7 +385,7 @@ static int run_render_fwd(const RenderFwdArgs &ra, bool debug, cudaStream_t stre
 
 static int run_render_bwd(const RenderBwdArgs &ra, bool debug, cudaStream_t stream) {
     return opt_bwd_variant == 5 ? launch_render_bwd_ps(ra, debug, stream)
-           : opt_bwd_variant >= 2 ? launch_render_bwd_mp(ra, opt_bwd_variant == 3 ? 4 : (opt_bwd_variant == 4 ? -2 : (opt_bwd_variant == 6 ? -12 : (opt_bwd_variant == 7 ? -16 : (opt_bwd_variant == 8 ? -20 : (opt_bwd_variant == 9 ? -21 : (opt_bwd_variant == 10 ? -22 : (opt_bwd_variant == 11 ? -23 : 2))))))), debug, stream)
+           : opt_bwd_variant >= 2 ? launch_render_bwd_mp(ra, opt_bwd_variant == 3 ? 4 : (opt_bwd_variant == 4 ? -2 : (opt_bwd_variant == 6 ? -12 : (opt_bwd_variant == 7 ? -16 : (opt_bwd_variant == 8 ? -20 : (opt_bwd_variant == 9 ? -21 : (opt_bwd_variant == 10 ? -22 : (opt_bwd_variant == 11 ? -23 : (opt_bwd_variant == 12 ? -24 : 2)))))))), debug, stream)
                                   : launch_render_bwd(ra, opt_bwd_variant, debug, stream);
 }
 
