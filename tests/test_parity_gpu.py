@@ -344,3 +344,63 @@ def test_batched_calls_match_single_view_calls(nviews):
     assert np.abs(a[1] - b[1]).max() <= 1e-4 * np.abs(a[1]).max()
     assert np.abs(a[3] - b[3]).max() <= 1e-4 * (np.abs(a[3]).max() + 1e-20)
     assert np.array_equal(a[4], b[4]) and np.array_equal(a[5], b[5])
+
+
+def test_batched_path_antialiasing_scale_modifier_background():
+    """The view-batch kernels loop over cameras that differ in pose and background; antialiasing and scale_modifier are
+    per-call settings carried per view."""
+    import math
+    import bench
+    from gaussian_renderer import GradientBucket, render_views_backward
+    dev = torch.device("cuda", 0)
+    scene = TO.make_scene(3000, seed=61, log_scale_mean=-2.8)
+    W, H = 144, 88
+    cams = [bench.BenchCamera(W, H, math.radians(50.0), *bench.view_pose(i + 3, 3.0), dev) for i in range(3)]
+    gts = [torch.rand(3, H, W, generator=torch.Generator().manual_seed(i)).to(dev) for i in range(3)]
+    bg = torch.tensor([0.9, 0.5, 0.1], device=dev)
+
+    class AAPipe(bench.Pipe):
+        antialiasing = True
+
+    def run(batched):
+        pc = bench.BenchGaussians(scene, 3, dev)
+        pc.active_sh_degree = 2
+        bucket = GradientBucket(pc.parameters())
+        out = render_views_backward(cams, pc, AAPipe(), bg, lambda img, d, i: ((img - gts[i]) ** 2).mean(), scaling_modifier=0.8,
+                                    keep_images=True, batched=batched)
+        return [im.cpu().numpy() for im in out["images"]], bucket.flat.cpu().numpy()
+
+    (ia, ga), (ib, gb) = run(False), run(True)
+    for x, y in zip(ia, ib):
+        assert np.array_equal(x, y)
+    assert np.abs(ga - gb).max() <= 1e-4 * np.abs(ga).max()
+    # and against the oracle for one of the views
+    cam = cams[1]
+    os_ = TO.OracleSettings(H, W, math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5), bg.cpu(), 0.8, cam.world_view_transform.cpu(),
+                            cam.full_proj_transform.cpu(), 2, cam.camera_center.cpu(), False, False, True)
+    ref = U.run_oracle(U.make_args(scene, "sh"), os_)
+    U.assert_image_close(ib[1], ref["color"], "batched AA view vs oracle")
+
+
+def test_debug_flag_float64_noncontiguous_and_side_stream():
+    """debug=True synchronises after every kernel; float64 / non-contiguous inputs are converted; a non-default stream works."""
+    import diff_gaussian_rasterization as dgr
+    scene = TO.make_scene(1500, seed=62, log_scale_mean=-2.7)
+    cam = TO.make_camera(112, 80, sh_degree=1)
+    base = U.run_cuda(U.make_args(scene, "sh"), cam)
+    rs = U.settings_to(cam._replace(debug=True), "cuda")
+    dev = torch.device("cuda", 0)
+    big = torch.zeros(1500, 6, dtype=torch.float64, device=dev)
+    big[:, ::2] = scene["means3D"].double().to(dev)
+    means_nc = big[:, ::2]                                   # float64, non-contiguous view
+    assert not means_nc.is_contiguous()
+    side = torch.cuda.Stream(device=dev)
+    args = {k: v.to(dev) for k, v in U.make_args(scene, "sh").items() if v is not None}
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        rast = dgr.GaussianRasterizer(rs)
+        color, radii, invd = rast(means3D=means_nc, means2D=torch.zeros(1500, 3, device=dev), shs=args["shs"], opacities=args["opacities"],
+                                  scales=args["scales"], rotations=args["rotations"])
+    side.synchronize()
+    assert np.array_equal(color.cpu().numpy(), base["color"])
+    assert np.array_equal(radii.cpu().numpy(), base["radii"])
