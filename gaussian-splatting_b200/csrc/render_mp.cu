@@ -417,15 +417,20 @@ render_bwd_mp2x_kernel(const RenderBwdArgs a) {
                 __syncwarp();
                 continue;
             }
+            // both shuffle networks are issued before either atomic so that their (independent) chains overlap
             const float ra = reduce8_transposed(hsum(m_x), hsum(m_y), hsum(m_xx), hsum(m_xy), hsum(m_yy), hsum(g_o), hsum(g_r), hsum(g_g));
-            if ((lane & 3) == 0) atomicAdd(d + (lane >> 2), ra);
+            float rb;
             if (DEPTH) {
-                const float rb = reduce2_transposed(hsum(g_b), hsum(g_d));
-                if ((lane & 15) == 1) atomicAdd(d + 8 + (lane >> 4), rb);
+                rb = reduce2_transposed(hsum(g_b), hsum(g_d));
             } else {
-                float rb = hsum(g_b);
+                rb = hsum(g_b);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) rb += __shfl_xor_sync(0xffffffffu, rb, o);
+            }
+            if ((lane & 3) == 0) atomicAdd(d + (lane >> 2), ra);
+            if (DEPTH) {
+                if ((lane & 15) == 1) atomicAdd(d + 8 + (lane >> 4), rb);
+            } else {
                 if (lane == 1) atomicAdd(d + 8, rb);
             }
         }
