@@ -1,5 +1,7 @@
-// render.cu -- per-tile blend kernels: forward front-to-back alpha blend (K6) and backward
-// back-to-front gradient accumulation (K7).
+// render.cu -- one-pixel-per-thread blend kernels.  The DEFAULT forward kernel (K6) lives here:
+// render_fwd_pc_kernel (8x4 pixel patch per warp, sub-tile culling, log2-domain exponent; fwd variant 6).
+// render_fwd_kernel / render_bwd_kernel are the round's first versions (back-to-front recursion with butterfly
+// reductions), kept as the A/B baseline of DESIGN.md section 4; render_fwd_pc2_kernel is a rejected experiment.
 //
 // Replaces FORWARD::renderCUDA / BACKWARD::renderCUDA of the reference's
 // cuda_rasterizer/{forward,backward}.cu (named in BASELINE.json north_star; absent from

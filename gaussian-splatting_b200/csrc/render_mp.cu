@@ -1,4 +1,7 @@
-// render_mp.cu -- multi-pixel-per-thread blend kernels (forward K6 and backward K7).
+// render_mp.cu -- multi-pixel-per-thread blend kernels.  The DEFAULT backward kernel (K7) lives here:
+// render_bwd_mp2x_kernel (2x2 pixels per thread, packed f32x2 arithmetic, sub-tile culling; bwd variant 10).
+// render_bwd_mp_kernel is its scalar predecessor; render_fwd_mp_kernel (multi-pixel forward) measured slower than
+// the one-pixel forward of render.cu and is kept for A/B only.
 //
 // ncu on the one-pixel-per-thread kernels (profiles/r1_render_v0.md) shows both are bound by the SM
 // issue rate (issue active 81-87 %, DRAM 1-2 %): the cost is instructions per (pixel, gaussian) pair,

@@ -1,4 +1,7 @@
-// render_ps.cu -- "patch-slot" blend kernels: the default forward (K6) and backward (K7).
+// render_ps.cu -- "patch-slot" blend kernels (EXPERIMENT, measured slower, NOT the default; fwd/bwd variant 5).
+// Kept selectable through gsb_set_option so the A/B in DESIGN.md section 4 can be reproduced (tools/sweep.py):
+// forward 0.49 ms vs 0.33, backward 0.77 ms vs 0.73 at the time -- the per-slot warp-uniform branches serialise the
+// four slots and remove the instruction-level parallelism the 2x2 kernels get from evaluating them together.
 //
 // A 16x16 tile is one CTA of two warps.  Warp w owns rows [8w, 8w+8) = four 8x4 patches; lane l owns the SAME
 // in-patch position (l & 7, l >> 3) in each of the four patches, i.e. four pixels 8 columns / 4 rows apart
