@@ -525,6 +525,12 @@ preprocess_bwd_batch_kernel(const CamArgsBatch cb, const PreBwdArgs a, const Pre
     if (live) {
         if (want_sh)
             for (int k = 0; k < 3 * M; ++k) gr[k] = 0.f;
+#ifdef GSB_PRE_UNROLL
+        constexpr int kViewUnroll = GSB_PRE_UNROLL;
+#else
+        constexpr int kViewUnroll = 1;
+#endif
+#pragma unroll kViewUnroll
         for (int v = 0; v < cb.V; ++v) {
             PreBwdArgs av = a;
             av.splat += (size_t)v * st.splat; av.dacc += (size_t)v * st.dacc;

@@ -21,7 +21,8 @@ import torch.nn as nn
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians"]
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(os.path.dirname(_PKG_DIR), "libgs_b200.so")
+# GSB_LIBRARY: an alternative build of the same sources (A/B of compile-time knobs); default = the in-tree library
+_LIB_PATH = os.environ.get("GSB_LIBRARY") or os.path.join(os.path.dirname(_PKG_DIR), "libgs_b200.so")
 
 
 # ---------------------------------------------------------------------------------------------
