@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "kernels.cuh"
@@ -56,8 +57,11 @@ int check_launch(const char *what, bool debug, cudaStream_t stream) {
 }
 
 // pinned read-back slot for the instance count, one per device, created on first use
+static std::mutex g_slot_mutex;   // the tiny per-device caches below are shared by all host threads
+
 static unsigned long long *pinned_slot() {
     static unsigned long long *slots[64] = {nullptr};
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     if (!slots[dev]) {
@@ -70,6 +74,7 @@ static unsigned long long *pinned_slot() {
 
 static cudaEvent_t readback_event() {
     static cudaEvent_t evs[64] = {nullptr};
+    std::lock_guard<std::mutex> lock(g_slot_mutex);
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     if (!evs[dev] && cudaEventCreateWithFlags(&evs[dev], cudaEventDisableTiming) != cudaSuccess) return nullptr;

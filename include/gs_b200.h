@@ -1,8 +1,10 @@
 /*
  * gs_b200.h -- C ABI of libgs_b200.so, the B200 (sm_100a) differentiable 3D-Gaussian-splatting
  * rasterizer.  Plain C: raw device pointers, explicit sizes, explicit stream, int error codes.
- * No torch types, no exceptions, no hidden global state except a per-device pinned 16-byte
- * read-back slot and the launch counter.
+ * No torch types, no exceptions, no hidden global state except a per-device pinned read-back slot
+ * (+ its event), the launch counter, the kernel-timing records and the tuning options.
+ * Threading: one host thread per device at a time (the reference calls it from its single training
+ * thread, train.py); calls for DIFFERENT devices may come from different processes (one per GPU).
  *
  * What each entry point replaces in the reference (graphdeco-inria/gaussian-splatting):
  * the reference reaches this path ONLY through the python package imported at
