@@ -406,8 +406,6 @@ def main():
     for _ in range(max(a.warmup, 8)):
         step(False)
     torch.cuda.synchronize()
-    if rank == 0:
-        time.sleep(0.5)
     dgr.set_option("time_kernels", 1)
     # A shared host occasionally stalls the launching thread for tens to hundreds of ms (seen as ONE step of 40-700 ms
     # among steps of 15.4 ms).  Such a leg is re-measured (at most twice) and every attempt is reported.
