@@ -65,11 +65,11 @@ class BenchCamera:
     """The attributes render() reads from scene.cameras.Camera (/root/reference/scene/cameras.py:19-89)."""
 
     def __init__(self, width, height, fovx, R, T, device):
-        from oracle import torch_oracle as TO  # camera formulae only (cameras.py:80-89), no compute
+        from gaussian_renderer.synthetic import camera_matrices
         self.image_width, self.image_height = width, height
         self.FoVx = fovx
         self.FoVy = 2.0 * math.atan(math.tan(fovx / 2) * height / width)
-        wvt, full, center = TO.camera_matrices(R, T, self.FoVx, self.FoVy)
+        wvt, full, center = camera_matrices(R, T, self.FoVx, self.FoVy)
         self.host = dict(wvt=wvt.contiguous().pin_memory() if device != "cpu" else wvt,
                          full=full.contiguous().pin_memory() if device != "cpu" else full,
                          center=center.contiguous().pin_memory() if device != "cpu" else center)
@@ -88,13 +88,8 @@ class BenchCamera:
 
 def view_pose(global_index: int, radius: float):
     """Cameras on a sphere of radius 3R looking at the origin; golden-angle spiral."""
-    from oracle import torch_oracle as TO
-    k = global_index
-    phi = k * 2.399963229728653
-    y = 0.35 * math.sin(0.61803398875 * k * 2 * math.pi)
-    r = math.sqrt(max(0.0, 1 - y * y))
-    eye = (radius * r * math.sin(phi), radius * y, -radius * r * math.cos(phi))
-    return TO.look_at_camera(eye)
+    from gaussian_renderer.synthetic import sphere_pose
+    return sphere_pose(global_index, radius)
 
 
 class BenchGaussians:
@@ -229,6 +224,7 @@ def cpu_reference_pass(scene, cam_settings, repeats):
 
 
 def oracle_settings(cam: BenchCamera, sh_degree: int):
+    """Settings record for the CPU oracle (cpu_baseline / --impl reference legs only)."""
     import torch
     from oracle import torch_oracle as TO
     return TO.OracleSettings(image_height=cam.image_height, image_width=cam.image_width,
@@ -252,11 +248,11 @@ def workload_config(a, world):
 def run_reference(a):
     """--impl reference: the path's CPU implementation on the host cores, one view per step (bounded sample)."""
     import torch
-    from oracle import torch_oracle as TO
+    from gaussian_renderer.synthetic import make_scene
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    scene = TO.make_scene(a.gaussians, seed=0, log_scale_mean=LOG_SCALE_MEAN)
+    scene = make_scene(a.gaussians, seed=0, log_scale_mean=LOG_SCALE_MEAN)
     R, T = view_pose(0, 3.0)
     cam = BenchCamera(a.width, a.height, math.radians(60.0), R, T, "cpu")
     cs = oracle_settings(cam, a.sh_degree)
@@ -284,7 +280,7 @@ def main():
         return
     import torch
     import torch.distributed as dist
-    from oracle import torch_oracle as TO   # scene + camera generators (shared with the tests); no compute
+    from gaussian_renderer.synthetic import make_scene   # the oracle is only loaded by the cpu_baseline leg below
     import diff_gaussian_rasterization as dgr
     from gaussian_renderer import GradientBucket, render, render_views_backward
 
@@ -304,7 +300,7 @@ def main():
         print(f"# note: --gpus {a.gpus} but WORLD_SIZE {world}; using {world}", file=sys.stderr)
 
     torch.manual_seed(0)
-    scene = TO.make_scene(a.gaussians, seed=0, log_scale_mean=LOG_SCALE_MEAN)
+    scene = make_scene(a.gaussians, seed=0, log_scale_mean=LOG_SCALE_MEAN)
     pc = BenchGaussians(scene, a.sh_degree, dev)
     bucket = GradientBucket(pc.parameters())
     pipe = Pipe()

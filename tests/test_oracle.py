@@ -101,3 +101,21 @@ def test_c_oracle_empty_and_culled():
     sc["means3D"][:, 2] -= 100.0  # behind the camera
     co = COracle(sc["means3D"], sc["shs"], None, sc["opacities"], sc["scales"], sc["rotations"], None, cam)
     assert co.num_rendered == 0 and (co.radii == 0).all()
+
+
+def test_package_synthetic_generators_match_oracle_and_reference(golden):
+    """gaussian_renderer.synthetic (used by bench.py's GPU arm, which never imports the oracle) against the oracle's
+    generators and the reference-pinned camera golden vector."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gaussian-splatting_b200", "gaussian_renderer"))
+    import synthetic as SY
+    a, b = SY.make_scene(777, seed=5, log_scale_mean=-5.3), TO.make_scene(777, seed=5, log_scale_mean=-5.3)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    wvt, full, center = SY.camera_matrices(golden["cam_R"], golden["cam_T"], float(golden["fovx"]), float(golden["fovy"]))
+    assert np.abs(wvt.numpy() - golden["world_view"]).max() < 1e-6
+    assert np.abs(full.numpy() - golden["full_proj"]).max() < 1e-6
+    assert np.abs(center.numpy() - golden["cam_center"]).max() < 1e-6
+    R0, T0 = SY.look_at((0.3, -0.2, -3.0))
+    R1, T1 = TO.look_at_camera((0.3, -0.2, -3.0))
+    assert np.allclose(R0, R1) and np.allclose(T0, T1)
