@@ -485,9 +485,10 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-    traffic = None
+    traffic, prof = None, {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("render_bwd_dram_bytes_per_launch")
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = prof.get("render_bwd_dram_bytes_per_launch")
     except Exception:
         pass
     bwd_avg_ms = bwd_ms / max(1, bwd_n)
@@ -496,6 +497,12 @@ def main():
     roofline = {"kernel": "render_bwd", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                 "algorithmic_bytes_per_launch": bytes_bwd, "avg_launch_ms": bwd_avg_ms, "launches_timed": bwd_n,
+                # what actually bounds the blend kernels: warp instructions issued (ncu count of the
+                # committed capture) over the live launch time, against 148 SMs x 4 schedulers x the sampled SM clock
+                "issue": (lambda wi, ms, mhz: None if not (wi and ms and mhz) else
+                          {"warp_instructions_per_launch": wi, "achieved_ginstr_s": wi / ms / 1e6,
+                           "peak_ginstr_s": 148 * 4 * mhz / 1e3, "frac": (wi / ms / 1e6) / (148 * 4 * mhz / 1e3)})(
+                    prof.get("render_bwd_warp_instructions_per_launch"), bwd_avg_ms, (clocks or {}).get("sm_mhz")),
                 "render_fwd": {"avg_launch_ms": fwd_avg_ms, "algorithmic_bytes_per_launch": bytes_fwd,
                                "achieved": bytes_fwd / (fwd_avg_ms * 1e-3) / 1e9 if fwd_avg_ms > 0 else 0.0,
                                "frac": (bytes_fwd / (fwd_avg_ms * 1e-3) / 1e9 / peak) if fwd_avg_ms > 0 else 0.0}}
