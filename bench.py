@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--sh-degree", type=int, default=3)
     ap.add_argument("--api", default="views", choices=["views", "render"],
                     help="views: fused view-batch path render_views_backward(); render: per-view render() + autograd")
+    ap.add_argument("--loss", default="l1", choices=["l1", "l1_ssim"],
+                    help="l1: mean |clamp(image) - target| (default, comparable across rounds); l1_ssim: the reference step's "
+                         "0.8 L1 + 0.2 (1 - SSIM) (train.py:120-126), fused kernel")
     ap.add_argument("--no-batch", action="store_true", help="views API view by view instead of gsb_forward_batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
@@ -240,7 +243,7 @@ def workload_config(a, world):
             "gaussians": a.gaussians, "image": [a.width, a.height], "sh_degree": a.sh_degree,
             "views_per_rank": a.views_per_rank, "views_total": a.views_per_rank * world,
             "parallelism": f"view-parallel x{world}, gaussians replicated, one all-reduce of 59 floats/gaussian",
-            "api": a.api,
+            "api": a.api, "loss": a.loss,
             "l2": "inputs_exceed_l2 (236 MB parameters + 8 distinct views per step; no explicit flush)",
             "scene": f"xyz~U([-1,1]^3), log-scale~N({LOG_SCALE_MEAN},0.5), opacity=sigmoid(U(-2,4)), cameras on sphere r=3, seed 0"}
 
@@ -341,12 +344,13 @@ def main():
             bucket.zero_()
         if a.api == "views":
             def loss_fn(img, _invdepth, i):
+                fused = dgr.l1_loss_and_grad if a.loss == "l1" else (lambda x, y: dgr.photometric_loss_and_grad(x, y, 0.2)[:2])
                 if host_inputs:
                     torch.cuda.current_stream(dev).wait_event(copied[i % NS])
-                    res = dgr.l1_loss_and_grad(img, stage[i % NS])  # fused L1 (train.py:120) + gradient, one kernel
+                    res = fused(img, stage[i % NS])      # fused loss (train.py:120-126) + gradient
                     consumed[i % NS].record()
                     return res
-                return dgr.l1_loss_and_grad(img, gt_dev[i])
+                return fused(img, gt_dev[i])
             out = render_views_backward(HostCams() if host_inputs else cams, pc, pipe, bg, loss_fn, loss_returns_grad=True,
                                         batched=not a.no_batch, overwrite=True)   # first chunk writes the bucket: no zeroing pass
             total = out["losses"].sum()

@@ -626,6 +626,22 @@ int32_t gsb_l1_loss_grad(const float *image, const float *target, int64_t n, flo
     return launch_l1_loss_grad(image, target, n, scale, grad_out, loss_accum, static_cast<cudaStream_t>(cuda_stream));
 }
 
+int32_t gsb_photometric_loss_grad(const float *image, const float *target, int32_t channels, int32_t height, int32_t width,
+                                  float lambda_dssim, float *grad_out, float *loss_accum, gsb_alloc_fn alloc, void *alloc_ctx,
+                                  void *cuda_stream) {
+    if (channels < 0 || height < 0 || width < 0 || !alloc ||
+        ((size_t)channels * height * width > 0 && (!image || !target || !grad_out || !loss_accum))) {
+        set_error("gsb_photometric_loss_grad: bad argument");
+        return GSB_ERR_ARGUMENT;
+    }
+    const size_t n = (size_t)channels * height * width;
+    if (n == 0) return GSB_OK;
+    float *maps = static_cast<float *>(do_alloc(alloc, alloc_ctx, GSB_BUF_SCRATCH2, 3 * n * sizeof(float)));
+    if (!maps) return GSB_ERR_ALLOC;
+    return launch_photometric_loss_grad(image, target, channels, height, width, lambda_dssim, grad_out, loss_accum, maps,
+                                        static_cast<cudaStream_t>(cuda_stream));
+}
+
 int32_t gsb_sort_pairs(uint32_t *keys, uint32_t *vals, int64_t n, int32_t begin_bit, int32_t end_bit,
                        gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream) {
     if (n < 0 || (n > 0 && (!keys || !vals)) || !alloc || begin_bit < 0 || end_bit > 32 || begin_bit > end_bit) {

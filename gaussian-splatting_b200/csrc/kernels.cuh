@@ -99,6 +99,8 @@ int launch_render_fwd_mp(const RenderFwdArgs &a, int qh, bool debug, cudaStream_
 int launch_render_bwd_mp(const RenderBwdArgs &a, int qh, bool debug, cudaStream_t stream);
 int launch_l1_loss_grad(const float *img, const float *gt, int64_t n, float scale, float *grad, float *loss_accum,
                         cudaStream_t stream);
+int launch_photometric_loss_grad(const float *img, const float *gt, int C, int H, int W, float lambda_dssim, float *grad,
+                                 float *loss_accum, float *maps, cudaStream_t stream);
 int launch_render_fwd_ps(const RenderFwdArgs &a, bool debug, cudaStream_t stream);
 int launch_render_bwd_ps(const RenderBwdArgs &a, bool debug, cudaStream_t stream);
 

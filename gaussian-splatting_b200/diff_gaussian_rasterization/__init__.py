@@ -81,6 +81,9 @@ def _load():
     lib.gsb_sort_pairs.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, _ALLOC_FN, c_void_p, c_void_p]
     lib.gsb_l1_loss_grad.restype = c_int32
     lib.gsb_l1_loss_grad.argtypes = [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p]
+    lib.gsb_photometric_loss_grad.restype = c_int32
+    lib.gsb_photometric_loss_grad.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p,
+                                              _ALLOC_FN, c_void_p, c_void_p]
     lib.gsb_last_error.restype = c_char_p
     lib.gsb_abi_version.restype = c_int32
     lib.gsb_launch_count.restype = c_int64
@@ -147,6 +150,25 @@ def l1_loss_and_grad(image: torch.Tensor, target: torch.Tensor, loss_accum: Opti
                                  torch.cuda.current_stream(img.device).cuda_stream)
     _check(rc)
     return loss_accum, grad
+
+
+def photometric_loss_and_grad(image: torch.Tensor, target: torch.Tensor, lambda_dssim: float = 0.2):
+    """The reference training step's loss (train.py:120-126) fused with its gradient:
+    ``(1 - lambda) * mean|x - y| + lambda * (1 - SSIM(x, y))`` with ``x = clamp(image, 0, 1)``; image / target [C,H,W].
+    Returns (loss[1], dloss/dimage, parts) with parts = tensor [loss, mean L1, mean SSIM] (device, no sync)."""
+    img, gt = _f32c(image), _f32c(target)
+    C, H, W = (int(v) for v in img.shape[-3:])
+    grad = torch.empty_like(img)
+    acc = torch.tensor([float(lambda_dssim), 0.0, 0.0], dtype=torch.float32).to(img.device, non_blocking=True)
+    with torch.cuda.device(img.device):
+        stream = torch.cuda.current_stream(img.device).cuda_stream
+        arena = _Arena(img.device, stream)
+        rc = _C.gsb_photometric_loss_grad(img.data_ptr(), gt.data_ptr(), C, H, W, float(lambda_dssim), grad.data_ptr(),
+                                          acc.data_ptr(), arena.cb, None, stream)
+    _check(rc, arena)
+    n = float(C * H * W)
+    parts = acc / torch.tensor([1.0, n, n], dtype=torch.float32, device=img.device)
+    return acc[:1], grad, parts
 
 
 class _Arena:

@@ -173,6 +173,15 @@ int32_t gsb_sort_pairs(uint32_t *keys, uint32_t *vals, int64_t n, int32_t begin_
 int32_t gsb_l1_loss_grad(const float *image, const float *target, int64_t n, float scale, float *grad_out,
                          float *loss_accum, void *cuda_stream);
 
+/* The reference training step's photometric loss fused with its gradient:
+ *   loss = (1 - lambda) * mean|x - y| + lambda * (1 - SSIM(x, y)),  x = clamp(image, 0, 1)
+ * (train.py:120-126, utils/loss_utils.py:40-86; 11x11 gaussian window, sigma 1.5, zero padding).  image / target are
+ * [channels, height, width]; grad_out = d loss / d image; loss_accum[0] += loss - lambda (add lambda on the host side,
+ * or pre-load it), loss_accum[1] += sum|x - y| * (1-lambda > 0), loss_accum[2] += sum of the SSIM map. */
+int32_t gsb_photometric_loss_grad(const float *image, const float *target, int32_t channels, int32_t height,
+                                  int32_t width, float lambda_dssim, float *grad_out, float *loss_accum,
+                                  gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream);
+
 const char *gsb_last_error(void);
 int32_t gsb_abi_version(void);
 /* number of kernels this library has launched in this process since the last reset */

@@ -62,6 +62,18 @@ center = wvt.inverse()[3, :3]
 out.update(cam_R=Rc, cam_T=T, fovx=np.float64(fovx), fovy=np.float64(fovy), world_view=wvt.numpy(),
            full_proj=full.numpy(), cam_center=center.numpy())
 
+# photometric loss (utils/loss_utils.py:40-86): L1 and SSIM values + autograd gradients of the reference's own functions
+from utils import loss_utils as LU  # noqa: E402
+gl = torch.Generator().manual_seed(99)
+img = torch.rand(3, 37, 53, generator=gl, dtype=torch.float32).requires_grad_(True)
+gt_img = (img.detach() + 0.15 * torch.randn(3, 37, 53, generator=gl)).clamp(0, 1)
+ssim_v = LU.ssim(img, gt_img)
+l1_v = LU.l1_loss(img, gt_img)
+loss_v = 0.8 * l1_v + 0.2 * (1.0 - ssim_v)
+(g_loss,) = torch.autograd.grad(loss_v, img)
+out.update(loss_img=img.detach().numpy(), loss_gt=gt_img.numpy(), loss_ssim=np.float32(ssim_v.item()), loss_l1=np.float32(l1_v.item()),
+           loss_total=np.float32(loss_v.item()), loss_grad=g_loss.numpy())
+
 dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_python.npz")
 np.savez_compressed(dst, **out)
 print("wrote", dst, {k: getattr(v, "shape", None) for k, v in out.items()})

@@ -119,3 +119,14 @@ def test_package_synthetic_generators_match_oracle_and_reference(golden):
     R0, T0 = SY.look_at((0.3, -0.2, -3.0))
     R1, T1 = TO.look_at_camera((0.3, -0.2, -3.0))
     assert np.allclose(R0, R1) and np.allclose(T0, T1)
+
+
+def test_photometric_loss_matches_reference_python(golden):
+    """SSIM / L1 / combined loss and its gradient against the reference's own utils/loss_utils.py (golden vectors)."""
+    img = torch.tensor(golden["loss_img"]).requires_grad_(True)
+    gt = torch.tensor(golden["loss_gt"])
+    assert abs(float(TO.ssim(img, gt)) - float(golden["loss_ssim"])) < 1e-6
+    loss = TO.photometric_loss(img, gt, 0.2)
+    assert abs(float(loss) - float(golden["loss_total"])) < 1e-6
+    (g,) = torch.autograd.grad(loss, img)
+    assert np.abs(g.numpy() - golden["loss_grad"]).max() < 1e-7

@@ -404,3 +404,37 @@ def test_debug_flag_float64_noncontiguous_and_side_stream():
     side.synchronize()
     assert np.array_equal(color.cpu().numpy(), base["color"])
     assert np.array_equal(radii.cpu().numpy(), base["radii"])
+
+
+@pytest.mark.parametrize("shape", [(3, 37, 53), (3, 128, 200), (1, 16, 16)])
+def test_fused_photometric_loss_and_fused_ssim(shape, golden):
+    """csrc/loss.cu against the reference-pinned restatement (oracle photometric_loss; golden vectors from the reference's own
+    utils/loss_utils.py): loss value within 1e-6, gradient within 1e-4 rel, including clamp's gradient mask."""
+    import diff_gaussian_rasterization as dgr
+    import fused_ssim
+    dev = torch.device("cuda", 0)
+    if shape == (3, 37, 53):
+        img, gt = torch.tensor(golden["loss_img"]), torch.tensor(golden["loss_gt"])
+    else:
+        g = torch.Generator().manual_seed(shape[1])
+        img = torch.rand(*shape, generator=g) * 1.3 - 0.15          # some values outside [0,1]: clamp mask exercised
+        gt = torch.rand(*shape, generator=g)
+    ref_in = img.clone().requires_grad_(True)
+    ref = TO.photometric_loss(ref_in, gt, 0.2)
+    (ref_g,) = torch.autograd.grad(ref, ref_in)
+    loss, grad, parts = dgr.photometric_loss_and_grad(img.to(dev), gt.to(dev), 0.2)
+    assert abs(float(loss.item()) - float(ref)) < 2e-6
+    err = (grad.cpu() - ref_g).abs().max().item() / (ref_g.abs().max().item() + 1e-20)
+    assert err < 1e-4, err
+    if shape == (3, 37, 53):
+        assert abs(float(loss.item()) - float(golden["loss_total"])) < 2e-6
+        assert np.abs(grad.cpu().numpy() - golden["loss_grad"]).max() < 1e-4 * np.abs(golden["loss_grad"]).max()
+    # drop-in fused_ssim: mean SSIM with autograd, images already in [0,1]
+    a = img.clamp(0, 1).to(dev).requires_grad_(True)
+    v = fused_ssim.fused_ssim(a.unsqueeze(0), gt.to(dev).unsqueeze(0))
+    a_ref = img.clamp(0, 1).requires_grad_(True)
+    v_ref = TO.ssim(a_ref, gt)
+    assert abs(float(v.item()) - float(v_ref)) < 2e-6
+    (ga,) = torch.autograd.grad(v, a)
+    (ga_ref,) = torch.autograd.grad(v_ref, a_ref)
+    assert (ga.cpu() - ga_ref).abs().max().item() <= 1e-4 * ga_ref.abs().max().item()
