@@ -57,20 +57,22 @@ l1_loss_grad_kernel(const float4 *__restrict__ img, const float4 *__restrict__ g
 __device__ constexpr float SSIM_W[11] = {1.0283801239e-03f, 7.5987582095e-03f, 3.6000773311e-02f, 1.0936068743e-01f,
                                          2.1300552785e-01f, 2.6601171494e-01f, 2.1300552785e-01f, 1.0936068743e-01f,
                                          3.6000773311e-02f, 7.5987582095e-03f, 1.0283801239e-03f};
-constexpr int SSIM_T = 16, SSIM_R = 5, SSIM_S = SSIM_T + 2 * SSIM_R;   // tile, radius, tile + halo = 26
+// 32x32-pixel tile per 256-thread block, halo 5: 42x42 inputs.  Both separable passes use register sliding windows: a
+// thread produces FOUR adjacent outputs from 14 loaded taps, so shared-memory loads per output drop from 11 to 3.5
+// (the first version -- one output per thread per pass -- ran at 40 % of its instruction-count floor, LSU bound).
+constexpr int SSIM_TX = 32, SSIM_TY = 32, SSIM_R = 5, SSIM_SX = SSIM_TX + 2 * SSIM_R, SSIM_SY = SSIM_TY + 2 * SSIM_R, SSIM_NT = 256;
 constexpr float SSIM_C1 = 0.01f * 0.01f, SSIM_C2 = 0.03f * 0.03f;
 
-__global__ void __launch_bounds__(SSIM_T * SSIM_T)
+__global__ void __launch_bounds__(SSIM_NT)
 ssim_maps_kernel(const float *__restrict__ img, const float *__restrict__ gt, const int H, const int W, float *__restrict__ M1,
                  float *__restrict__ M2, float *__restrict__ M3, float *loss_accum, const float w_l1, const float w_ssim) {
-    __shared__ float sx[SSIM_S][SSIM_S + 1], sy[SSIM_S][SSIM_S + 1];
-    __shared__ float h[5][SSIM_S][SSIM_T + 1];
+    __shared__ float sx[SSIM_SY][SSIM_SX + 1], sy[SSIM_SY][SSIM_SX + 1];
+    __shared__ float h[5][SSIM_SY][SSIM_TX + 1];
     __shared__ float red[2][8];
-    const int tx = threadIdx.x % SSIM_T, ty = threadIdx.x / SSIM_T;
-    const int x0 = blockIdx.x * SSIM_T, y0 = blockIdx.y * SSIM_T, c = blockIdx.z;
+    const int x0 = blockIdx.x * SSIM_TX, y0 = blockIdx.y * SSIM_TY, c = blockIdx.z;
     const size_t plane = (size_t)c * H * W;
-    for (int i = threadIdx.x; i < SSIM_S * SSIM_S; i += SSIM_T * SSIM_T) {
-        const int ly = i / SSIM_S, lx = i % SSIM_S;
+    for (int i = threadIdx.x; i < SSIM_SY * SSIM_SX; i += SSIM_NT) {
+        const int ly = i / SSIM_SX, lx = i % SSIM_SX;
         const int gx = x0 + lx - SSIM_R, gy = y0 + ly - SSIM_R;
         float a = 0.f, b = 0.f;
         if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
@@ -80,65 +82,86 @@ ssim_maps_kernel(const float *__restrict__ img, const float *__restrict__ gt, co
         sx[ly][lx] = a; sy[ly][lx] = b;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < SSIM_S * SSIM_T; i += SSIM_T * SSIM_T) {   // horizontal pass
-        const int ly = i / SSIM_T, lx = i % SSIM_T;
-        float m1 = 0.f, m2 = 0.f, xx = 0.f, yy = 0.f, xy = 0.f;
+    // horizontal pass: task = (row, 4-column segment)
+    for (int task = threadIdx.x; task < SSIM_SY * (SSIM_TX / 4); task += SSIM_NT) {
+        const int ly = task / (SSIM_TX / 4), lx0 = (task % (SSIM_TX / 4)) * 4;
+        float a[14], b[14];
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {
-            const float a = sx[ly][lx + k], b = sy[ly][lx + k], w = SSIM_W[k];
-            m1 += w * a; m2 += w * b; xx += w * a * a; yy += w * b * b; xy += w * a * b;
+        for (int j = 0; j < 14; ++j) { a[j] = sx[ly][lx0 + j]; b[j] = sy[ly][lx0 + j]; }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float m1 = 0.f, m2 = 0.f, xx = 0.f, yy = 0.f, xy = 0.f;
+#pragma unroll
+            for (int k = 0; k < 11; ++k) {
+                const float w = SSIM_W[k], wa = w * a[o + k], wb = w * b[o + k];
+                m1 += wa; m2 += wb; xx += wa * a[o + k]; yy += wb * b[o + k]; xy += wa * b[o + k];
+            }
+            h[0][ly][lx0 + o] = m1; h[1][ly][lx0 + o] = m2; h[2][ly][lx0 + o] = xx; h[3][ly][lx0 + o] = yy; h[4][ly][lx0 + o] = xy;
         }
-        h[0][ly][lx] = m1; h[1][ly][lx] = m2; h[2][ly][lx] = xx; h[3][ly][lx] = yy; h[4][ly][lx] = xy;
     }
     __syncthreads();
-    float mu1 = 0.f, mu2 = 0.f, ex2 = 0.f, ey2 = 0.f, exy = 0.f;
+    // vertical pass: thread = (column, 4-row segment)
+    const int tx = threadIdx.x % SSIM_TX, ty0 = (threadIdx.x / SSIM_TX) * 4;
+    float q[5][4];
 #pragma unroll
-    for (int k = 0; k < 11; ++k) {   // vertical pass
-        const float w = SSIM_W[k];
-        mu1 += w * h[0][ty + k][tx]; mu2 += w * h[1][ty + k][tx]; ex2 += w * h[2][ty + k][tx];
-        ey2 += w * h[3][ty + k][tx]; exy += w * h[4][ty + k][tx];
+    for (int qq = 0; qq < 5; ++qq) {
+        float v[14];
+#pragma unroll
+        for (int j = 0; j < 14; ++j) v[j] = h[qq][ty0 + j][tx];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 11; ++k) acc += SSIM_W[k] * v[o + k];
+            q[qq][o] = acc;
+        }
     }
-    const int gx = x0 + tx, gy = y0 + ty;
-    float m = 0.f, l1 = 0.f;
-    if (gx < W && gy < H) {
-        const float s1 = ex2 - mu1 * mu1, s2 = ey2 - mu2 * mu2, s12 = exy - mu1 * mu2;
-        const float A = mu1 * mu1 + mu2 * mu2 + SSIM_C1, B = s1 + s2 + SSIM_C2;
-        const float Cc = 2.f * mu1 * mu2 + SSIM_C1, D = 2.f * s12 + SSIM_C2;
-        const float iAB = 1.0f / (A * B);
-        m = Cc * D * iAB;
-        const float dm_ds1 = -m / B;              // = -C D / (A B^2)
-        const float dm_ds12 = 2.f * Cc * iAB;
-        const float dm_dmu1 = 2.f * mu2 * D * iAB - 2.f * mu1 * m / A + dm_ds1 * (-2.f * mu1) + dm_ds12 * (-mu2);
-        const size_t pid = plane + (size_t)gy * W + gx;
-        M1[pid] = dm_dmu1; M2[pid] = dm_ds1; M3[pid] = dm_ds12;
-        l1 = fabsf(sx[ty + SSIM_R][tx + SSIM_R] - sy[ty + SSIM_R][tx + SSIM_R]);
+    float msum = 0.f, l1sum = 0.f;
+    const int gx = x0 + tx;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        const int gy = y0 + ty0 + o;
+        if (gx < W && gy < H) {
+            const float mu1 = q[0][o], mu2 = q[1][o];
+            const float s1 = q[2][o] - mu1 * mu1, s2 = q[3][o] - mu2 * mu2, s12 = q[4][o] - mu1 * mu2;
+            const float A = mu1 * mu1 + mu2 * mu2 + SSIM_C1, B = s1 + s2 + SSIM_C2;
+            const float Cc = 2.f * mu1 * mu2 + SSIM_C1, D = 2.f * s12 + SSIM_C2;
+            const float iAB = 1.0f / (A * B);
+            const float m = Cc * D * iAB;
+            const float dm_ds1 = -m / B;              // = -C D / (A B^2)
+            const float dm_ds12 = 2.f * Cc * iAB;
+            const float dm_dmu1 = 2.f * mu2 * D * iAB - 2.f * mu1 * m / A + dm_ds1 * (-2.f * mu1) + dm_ds12 * (-mu2);
+            const size_t pid = plane + (size_t)gy * W + gx;
+            M1[pid] = dm_dmu1; M2[pid] = dm_ds1; M3[pid] = dm_ds12;
+            msum += m;
+            l1sum += fabsf(sx[ty0 + o + SSIM_R][tx + SSIM_R] - sy[ty0 + o + SSIM_R][tx + SSIM_R]);
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { m += __shfl_xor_sync(0xffffffffu, m, o); l1 += __shfl_xor_sync(0xffffffffu, l1, o); }
-    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = m; red[1][threadIdx.x >> 5] = l1; }
+    for (int o = 16; o > 0; o >>= 1) { msum += __shfl_xor_sync(0xffffffffu, msum, o); l1sum += __shfl_xor_sync(0xffffffffu, l1sum, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = msum; red[1][threadIdx.x >> 5] = l1sum; }
     __syncthreads();
     if (threadIdx.x == 0) {
         float sm = 0.f, sl = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) { sm += red[0][k]; sl += red[1][k]; }
-        // loss_accum[0] total, [1] mean |x - y|, [2] mean SSIM
+        // loss_accum[0] total, [1] sum |x - y|, [2] sum of the SSIM map
         atomicAdd(loss_accum + 0, w_l1 * sl - w_ssim * sm);
-        atomicAdd(loss_accum + 1, sl * (w_l1 > 0.f ? 1.0f : 0.0f));
+        atomicAdd(loss_accum + 1, sl);
         atomicAdd(loss_accum + 2, sm);
     }
 }
 
-__global__ void __launch_bounds__(SSIM_T * SSIM_T)
+__global__ void __launch_bounds__(SSIM_NT)
 ssim_grad_kernel(const float *__restrict__ img, const float *__restrict__ gt, const int H, const int W,
                  const float *__restrict__ M1, const float *__restrict__ M2, const float *__restrict__ M3,
                  float *__restrict__ grad, const float w_l1, const float w_ssim) {
-    __shared__ float s[3][SSIM_S][SSIM_S + 1];
-    __shared__ float h[3][SSIM_S][SSIM_T + 1];
-    const int tx = threadIdx.x % SSIM_T, ty = threadIdx.x / SSIM_T;
-    const int x0 = blockIdx.x * SSIM_T, y0 = blockIdx.y * SSIM_T, c = blockIdx.z;
+    __shared__ float s[3][SSIM_SY][SSIM_SX + 1];
+    __shared__ float h[3][SSIM_SY][SSIM_TX + 1];
+    const int x0 = blockIdx.x * SSIM_TX, y0 = blockIdx.y * SSIM_TY, c = blockIdx.z;
     const size_t plane = (size_t)c * H * W;
-    for (int i = threadIdx.x; i < SSIM_S * SSIM_S; i += SSIM_T * SSIM_T) {
-        const int ly = i / SSIM_S, lx = i % SSIM_S;
+    for (int i = threadIdx.x; i < SSIM_SY * SSIM_SX; i += SSIM_NT) {
+        const int ly = i / SSIM_SX, lx = i % SSIM_SX;
         const int gx = x0 + lx - SSIM_R, gy = y0 + ly - SSIM_R;
         float a = 0.f, b = 0.f, d = 0.f;
         if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
@@ -148,33 +171,52 @@ ssim_grad_kernel(const float *__restrict__ img, const float *__restrict__ gt, co
         s[0][ly][lx] = a; s[1][ly][lx] = b; s[2][ly][lx] = d;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < SSIM_S * SSIM_T; i += SSIM_T * SSIM_T) {
-        const int ly = i / SSIM_T, lx = i % SSIM_T;
-        float a = 0.f, b = 0.f, d = 0.f;
+    for (int task = threadIdx.x; task < SSIM_SY * (SSIM_TX / 4); task += SSIM_NT) {
+        const int ly = task / (SSIM_TX / 4), lx0 = (task % (SSIM_TX / 4)) * 4;
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {
-            const float w = SSIM_W[k];
-            a += w * s[0][ly][lx + k]; b += w * s[1][ly][lx + k]; d += w * s[2][ly][lx + k];
+        for (int qq = 0; qq < 3; ++qq) {
+            float v[14];
+#pragma unroll
+            for (int j = 0; j < 14; ++j) v[j] = s[qq][ly][lx0 + j];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < 11; ++k) acc += SSIM_W[k] * v[o + k];
+                h[qq][ly][lx0 + o] = acc;
+            }
         }
-        h[0][ly][lx] = a; h[1][ly][lx] = b; h[2][ly][lx] = d;
     }
     __syncthreads();
-    const int gx = x0 + tx, gy = y0 + ty;
-    if (gx >= W || gy >= H) return;
-    float g1 = 0.f, g2 = 0.f, g3 = 0.f;
+    const int tx = threadIdx.x % SSIM_TX, ty0 = (threadIdx.x / SSIM_TX) * 4;
+    float g[3][4];
 #pragma unroll
-    for (int k = 0; k < 11; ++k) {
-        const float w = SSIM_W[k];
-        g1 += w * h[0][ty + k][tx]; g2 += w * h[1][ty + k][tx]; g3 += w * h[2][ty + k][tx];
+    for (int qq = 0; qq < 3; ++qq) {
+        float v[14];
+#pragma unroll
+        for (int j = 0; j < 14; ++j) v[j] = h[qq][ty0 + j][tx];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < 11; ++k) acc += SSIM_W[k] * v[o + k];
+            g[qq][o] = acc;
+        }
     }
-    const size_t pid = plane + (size_t)gy * W + gx;
-    const float raw = img[pid], y = __ldg(gt + pid);
-    const float x = fminf(fmaxf(raw, 0.0f), 1.0f);
-    const float dssim = g1 + 2.f * x * g2 + y * g3;
-    const float d = x - y;
-    const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-    const float gx_ = w_l1 * sgn - w_ssim * dssim;
-    grad[pid] = (raw >= 0.0f && raw <= 1.0f) ? gx_ : 0.0f;
+    const int gx = x0 + tx;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        const int gy = y0 + ty0 + o;
+        if (gx >= W || gy >= H) continue;
+        const size_t pid = plane + (size_t)gy * W + gx;
+        const float raw = img[pid], y = __ldg(gt + pid);
+        const float x = fminf(fmaxf(raw, 0.0f), 1.0f);
+        const float dssim = g[0][o] + 2.f * x * g[1][o] + y * g[2][o];
+        const float d = x - y;
+        const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+        const float gv = w_l1 * sgn - w_ssim * dssim;
+        grad[pid] = (raw >= 0.0f && raw <= 1.0f) ? gv : 0.0f;
+    }
 }
 
 int launch_photometric_loss_grad(const float *img, const float *gt, int C, int H, int W, float lambda_dssim, float *grad,
@@ -183,10 +225,9 @@ int launch_photometric_loss_grad(const float *img, const float *gt, int C, int H
     const size_t n = (size_t)C * H * W;
     const float w_l1 = (1.0f - lambda_dssim) / (float)n, w_ssim = lambda_dssim / (float)n;
     float *M1 = maps, *M2 = maps + n, *M3 = maps + 2 * n;
-    const dim3 grid((W + SSIM_T - 1) / SSIM_T, (H + SSIM_T - 1) / SSIM_T, C);
-    GSB_LAUNCH("ssim_maps", false, stream, ssim_maps_kernel, grid, SSIM_T * SSIM_T, 0, img, gt, H, W, M1, M2, M3, loss_accum, w_l1,
-               w_ssim);
-    GSB_LAUNCH("ssim_grad", false, stream, ssim_grad_kernel, grid, SSIM_T * SSIM_T, 0, img, gt, H, W, M1, M2, M3, grad, w_l1, w_ssim);
+    const dim3 grid((W + SSIM_TX - 1) / SSIM_TX, (H + SSIM_TY - 1) / SSIM_TY, C);
+    GSB_LAUNCH("ssim_maps", false, stream, ssim_maps_kernel, grid, SSIM_NT, 0, img, gt, H, W, M1, M2, M3, loss_accum, w_l1, w_ssim);
+    GSB_LAUNCH("ssim_grad", false, stream, ssim_grad_kernel, grid, SSIM_NT, 0, img, gt, H, W, M1, M2, M3, grad, w_l1, w_ssim);
     return GSB_OK;
 }
 
