@@ -642,6 +642,72 @@ int32_t gsb_photometric_loss_grad(const float *image, const float *target, int32
                                         static_cast<cudaStream_t>(cuda_stream));
 }
 
+static bool store_fits_u32(int64_t P, int32_t sh_coeffs, int32_t n_children) {
+    const int64_t width = 11 + 3 * (int64_t)sh_coeffs;
+    return P >= 0 && P * width < ((int64_t)1 << 32) - 4096 && P * (2 + (int64_t)n_children) < ((int64_t)1 << 32) - 4096;
+}
+
+int32_t gsb_adam_step(const GsbAdamArgs *a, void *cuda_stream) {
+    if (!a || a->P < 0 || a->sh_coeffs < 1 || !store_fits_u32(a->P, a->sh_coeffs, 0) ||
+        (a->P > 0 && (!a->params || !a->grads || !a->exp_avg || !a->exp_avg_sq)) || !(a->bias2_sqrt > 0.0f)) {
+        set_error("gsb_adam_step: bad argument");
+        return GSB_ERR_ARGUMENT;
+    }
+    return launch_adam_step(a->P, a->sh_coeffs, a->params, a->grads, a->exp_avg, a->exp_avg_sq, a->act, a->visible, a->step_size,
+                            a->beta1, a->beta2, a->eps, a->bias2_sqrt, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int32_t gsb_activate(int64_t P, int32_t sh_coeffs, const float *params, float *act, void *cuda_stream) {
+    if (P < 0 || sh_coeffs < 1 || !store_fits_u32(P, sh_coeffs, 0) || (P > 0 && (!params || !act))) {
+        set_error("gsb_activate: bad argument");
+        return GSB_ERR_ARGUMENT;
+    }
+    return launch_activate(P, sh_coeffs, params, act, static_cast<cudaStream_t>(cuda_stream));
+}
+
+size_t gsb_densify_scratch_bytes(int64_t P, int32_t n_children) { return densify_scratch_bytes(P < 0 ? 0 : P, n_children < 1 ? 1 : n_children); }
+
+static bool densify_args_ok(const GsbDensifyArgs *a) {
+    return a && a->P >= 0 && a->sh_coeffs >= 1 && a->n_children >= 1 && a->n_children <= 8 &&
+           store_fits_u32(a->P, a->sh_coeffs, a->n_children) && (a->P == 0 || (a->params && a->scratch));
+}
+
+int32_t gsb_densify_plan(const GsbDensifyArgs *a, int64_t counts[4], void *cuda_stream) {
+    if (!densify_args_ok(a) || !counts || (a->P > 0 && (!a->grad_accum || !a->denom)) || !(a->grad_threshold > 0.0f)) {
+        set_error("gsb_densify_plan: bad argument (grad_threshold must be > 0)");
+        return GSB_ERR_ARGUMENT;
+    }
+    counts[0] = counts[1] = counts[2] = counts[3] = 0;
+    if (a->P == 0) return GSB_OK;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    uint32_t *dev = nullptr;
+    const int e = launch_densify_plan(a->P, a->sh_coeffs, a->n_children, a->params, a->grad_accum, a->denom, a->grad_threshold,
+                                      a->size_limit, a->min_opacity, a->world_limit, a->scratch, &dev, stream);
+    if (e) return e;
+    uint32_t host[8];
+    GSB_CUDA(cudaMemcpyAsync(host, dev, sizeof(host), cudaMemcpyDeviceToHost, stream));
+    GSB_CUDA(cudaStreamSynchronize(stream));
+    for (int k = 0; k < 4; ++k) counts[k] = host[k];
+    if (host[4] != host[1]) {
+        set_error("gsb_densify_plan: split count mismatch (%u vs %u)", host[4], host[1]);
+        return GSB_ERR_CUDA;
+    }
+    return GSB_OK;
+}
+
+int32_t gsb_densify_apply(const GsbDensifyArgs *a, const float *unit_samples, int64_t n_split, int64_t P_new, float *new_params,
+                          float *new_exp_avg, float *new_exp_avg_sq, void *cuda_stream) {
+    if (!densify_args_ok(a) || n_split < 0 || P_new < 0 || (n_split > 0 && !unit_samples) ||
+        !store_fits_u32(P_new, a->sh_coeffs, 0) ||
+        (P_new > 0 && (!new_params || !new_exp_avg || !new_exp_avg_sq || !a->exp_avg || !a->exp_avg_sq))) {
+        set_error("gsb_densify_apply: bad argument");
+        return GSB_ERR_ARGUMENT;
+    }
+    if (a->P == 0) return GSB_OK;
+    return launch_densify_apply(a->P, a->sh_coeffs, a->n_children, a->params, a->exp_avg, a->exp_avg_sq, a->scratch, unit_samples,
+                                n_split, P_new, new_params, new_exp_avg, new_exp_avg_sq, static_cast<cudaStream_t>(cuda_stream));
+}
+
 int32_t gsb_sort_pairs(uint32_t *keys, uint32_t *vals, int64_t n, int32_t begin_bit, int32_t end_bit,
                        gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream) {
     if (n < 0 || (n > 0 && (!keys || !vals)) || !alloc || begin_bit < 0 || end_bit > 32 || begin_bit > end_bit) {

@@ -104,4 +104,17 @@ int launch_photometric_loss_grad(const float *img, const float *gt, int C, int H
 int launch_render_fwd_ps(const RenderFwdArgs &a, bool debug, cudaStream_t stream);
 int launch_render_bwd_ps(const RenderBwdArgs &a, bool debug, cudaStream_t stream);
 
+// optimizer step and densification on the flat store (optim.cu, densify.cu)
+int launch_adam_step(int64_t P, int sh_coeffs, float *params, const float *grads, float *m, float *v, float *act,
+                     const uint8_t *visible, const float step_size[6], float beta1, float beta2, float eps, float bias2_sqrt,
+                     cudaStream_t stream);
+int launch_activate(int64_t P, int sh_coeffs, const float *params, float *act, cudaStream_t stream);
+size_t densify_scratch_bytes(int64_t P, int n_children);
+int launch_densify_plan(int64_t P, int sh_coeffs, int n_children, const float *params, const float *grad_accum, const float *denom,
+                        float grad_threshold, float size_limit, float min_opacity, float world_limit, void *scratch,
+                        uint32_t **counters_dev, cudaStream_t stream);
+int launch_densify_apply(int64_t P, int sh_coeffs, int n_children, const float *params, const float *m, const float *v, void *scratch,
+                         const float *unit_samples, int64_t n_split, int64_t P_new, float *new_params, float *new_m, float *new_v,
+                         cudaStream_t stream);
+
 }  // namespace gsb

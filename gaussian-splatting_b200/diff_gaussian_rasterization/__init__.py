@@ -57,6 +57,18 @@ _ALLOC_FN = CFUNCTYPE(c_void_p, c_void_p, c_int32, c_size_t)
 BUF_GEOM, BUF_BINNING, BUF_IMAGE = 0, 1, 2
 
 
+class _AdamArgs(Structure):          # GsbAdamArgs (include/gs_b200.h)
+    _fields_ = [("P", c_int64), ("sh_coeffs", c_int32), ("reserved", c_int32), ("params", c_void_p), ("grads", c_void_p),
+                ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("act", c_void_p), ("visible", c_void_p),
+                ("step_size", c_float * 6), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("bias2_sqrt", c_float)]
+
+
+class _DensifyArgs(Structure):       # GsbDensifyArgs
+    _fields_ = [("P", c_int64), ("sh_coeffs", c_int32), ("n_children", c_int32), ("params", c_void_p), ("exp_avg", c_void_p),
+                ("exp_avg_sq", c_void_p), ("grad_accum", c_void_p), ("denom", c_void_p), ("grad_threshold", c_float),
+                ("size_limit", c_float), ("min_opacity", c_float), ("world_limit", c_float), ("scratch", c_void_p)]
+
+
 def _load():
     if not os.path.exists(_LIB_PATH):
         raise ImportError(
@@ -92,8 +104,18 @@ def _load():
     lib.gsb_kernel_time.argtypes = [c_char_p, POINTER(ctypes.c_double), POINTER(c_int64), c_int32]
     lib.gsb_set_option.restype = c_int32
     lib.gsb_set_option.argtypes = [c_char_p, c_int32]
-    if lib.gsb_abi_version() != 4:
-        raise ImportError(f"{_LIB_PATH}: ABI version {lib.gsb_abi_version()} != 4")
+    lib.gsb_adam_step.restype = c_int32
+    lib.gsb_adam_step.argtypes = [POINTER(_AdamArgs), c_void_p]
+    lib.gsb_activate.restype = c_int32
+    lib.gsb_activate.argtypes = [c_int64, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.gsb_densify_scratch_bytes.restype = ctypes.c_size_t
+    lib.gsb_densify_scratch_bytes.argtypes = [c_int64, c_int32]
+    lib.gsb_densify_plan.restype = c_int32
+    lib.gsb_densify_plan.argtypes = [POINTER(_DensifyArgs), POINTER(c_int64 * 4), c_void_p]
+    lib.gsb_densify_apply.restype = c_int32
+    lib.gsb_densify_apply.argtypes = [POINTER(_DensifyArgs), c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+    if lib.gsb_abi_version() != 5:
+        raise ImportError(f"{_LIB_PATH}: ABI version {lib.gsb_abi_version()} != 5")
     return lib
 
 
@@ -169,6 +191,62 @@ def photometric_loss_and_grad(image: torch.Tensor, target: torch.Tensor, lambda_
     n = float(C * H * W)
     parts = acc / torch.tensor([1.0, n, n], dtype=torch.float32, device=img.device)
     return acc[:1], grad, parts
+
+
+def _stream_of(t: torch.Tensor):
+    if not t.is_cuda:
+        raise RuntimeError("libgs_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, act, P: int, sh_coeffs: int, step_size, beta1: float, beta2: float,
+              eps: float, bias2_sqrt: float, visible: Optional[torch.Tensor] = None) -> None:
+    """gsb_adam_step over the flat store (layout: include/gs_b200.h); every tensor float32, contiguous, same device."""
+    a = _AdamArgs()
+    a.P, a.sh_coeffs, a.reserved = int(P), int(sh_coeffs), 0
+    a.params, a.grads, a.exp_avg, a.exp_avg_sq = params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr()
+    a.act = act.data_ptr() if act is not None else None
+    if visible is not None:
+        visible = visible.to(torch.uint8).contiguous()
+    a.visible = visible.data_ptr() if visible is not None else None
+    a.step_size = (c_float * 6)(*[float(v) for v in step_size])
+    a.beta1, a.beta2, a.eps, a.bias2_sqrt = float(beta1), float(beta2), float(eps), float(bias2_sqrt)
+    stream = _stream_of(params)
+    with torch.cuda.device(params.device):
+        _check(_C.gsb_adam_step(byref(a), stream))
+
+
+def activate(params: torch.Tensor, act: torch.Tensor, P: int, sh_coeffs: int) -> None:
+    stream = _stream_of(params)
+    with torch.cuda.device(params.device):
+        _check(_C.gsb_activate(int(P), int(sh_coeffs), params.data_ptr(), act.data_ptr(), stream))
+
+
+def densify_plan(params, exp_avg, exp_avg_sq, grad_accum, denom, P: int, sh_coeffs: int, n_children: int, grad_threshold: float,
+                 size_limit: float, min_opacity: float, world_limit: float):
+    """gsb_densify_plan: returns (args, scratch, (n_clone, n_split, n_pruned, P_new)); one stream synchronisation."""
+    stream = _stream_of(params)
+    a = _DensifyArgs()
+    a.P, a.sh_coeffs, a.n_children = int(P), int(sh_coeffs), int(n_children)
+    a.params, a.exp_avg, a.exp_avg_sq = params.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr()
+    ga, dn = _f32c(grad_accum.reshape(-1)), _f32c(denom.reshape(-1))
+    a.grad_accum, a.denom = ga.data_ptr(), dn.data_ptr()
+    a.grad_threshold, a.size_limit = float(grad_threshold), float(size_limit)
+    a.min_opacity, a.world_limit = float(min_opacity), float(world_limit)
+    scratch = torch.empty(max(int(_C.gsb_densify_scratch_bytes(int(P), int(n_children))), 1), dtype=torch.uint8, device=params.device)
+    a.scratch = scratch.data_ptr()
+    counts = (c_int64 * 4)()
+    with torch.cuda.device(params.device):
+        _check(_C.gsb_densify_plan(byref(a), byref(counts), stream))
+    return a, (scratch, ga, dn), tuple(int(v) for v in counts)
+
+
+def densify_apply(args, unit_samples: Optional[torch.Tensor], n_split: int, P_new: int, new_params, new_exp_avg, new_exp_avg_sq) -> None:
+    us = _f32c(unit_samples) if unit_samples is not None and unit_samples.numel() else None
+    stream = _stream_of(new_params)
+    with torch.cuda.device(new_params.device):
+        _check(_C.gsb_densify_apply(byref(args), _ptr(us), int(n_split), int(P_new), new_params.data_ptr(), new_exp_avg.data_ptr(),
+                                    new_exp_avg_sq.data_ptr(), stream))
 
 
 class _Arena:

@@ -1,0 +1,286 @@
+"""Training state of the gaussians on ONE flat device buffer, mirroring the parts of the reference's
+``scene.GaussianModel`` that sit either side of the rasterizer (SURVEY.md section 8(f) rows 1 and 3;
+/root/reference/scene/gaussian_model.py):
+
+    training_setup :176-211 | update_learning_rate :213-223 | reset_opacity :258-261 | densify_and_prune :452-469
+    add_densification_stats :471-473 | oneupSHdegree :146-148 | activations :102-130 | optimizer.step() train.py:178-186
+
+What differs, and why.  The reference keeps six ``nn.Parameter`` tensors, lets autograd chain the rasterizer's gradients
+through exp / sigmoid / normalize / cat, runs ``torch.optim.Adam`` group by group, and rebuilds every tensor and both Adam
+moments with boolean-mask gathers and ``cat`` when it densifies.  Here the raw parameters, their gradients and both moments
+are four flat float32 buffers with the same group-after-group layout (include/gs_b200.h, "store"):
+
+  * the rasterizer's backward writes dLoss/d(activated value) straight into the gradient buffer (the activated tensors
+    returned by ``get_xyz`` ... ``get_rotation`` are leaves whose ``.grad`` aliases it),
+  * the data-parallel reduction is ONE ``all_reduce`` of ``self.grad``,
+  * ``optimizer_step`` is ONE kernel: activation backward + Adam for all six groups + re-activation (``gsb_adam_step``),
+  * ``densify_and_prune`` is a plan (one read-back) plus ONE gather into fresh buffers (``gsb_densify_plan/_apply``).
+
+Results are those of the reference (tests/test_store_gpu.py replays the fixture recorded from the reference class).
+The kernels are CUDA only: on a CPU tensor the calls raise -- there is no fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+import diff_gaussian_rasterization as _dgr
+
+__all__ = ["GaussianModel", "expon_lr", "store_offsets"]
+
+GROUPS = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")
+
+
+def expon_lr(step: int, lr_init: float, lr_final: float, lr_delay_steps: int = 0, lr_delay_mult: float = 1.0,
+             max_steps: int = 1000000) -> float:
+    """The position learning-rate schedule (utils/general_utils.py:29-62): log-linear from lr_init to lr_final."""
+    if step < 0 or (lr_init == 0.0 and lr_final == 0.0):
+        return 0.0
+    delay = 1.0
+    if lr_delay_steps > 0:
+        delay = lr_delay_mult + (1.0 - lr_delay_mult) * math.sin(0.5 * math.pi * min(max(step / lr_delay_steps, 0.0), 1.0))
+    t = min(max(step / max_steps, 0.0), 1.0)
+    return delay * math.exp(math.log(lr_init) * (1.0 - t) + math.log(lr_final) * t)
+
+
+def store_offsets(P: int, sh_coeffs: int) -> Dict[str, int]:
+    """First float of every group in the flat store (include/gs_b200.h)."""
+    feat = 3 * P
+    op = feat + 3 * sh_coeffs * P
+    return {"xyz": 0, "features": feat, "opacity": op, "scaling": op + P, "rotation": op + 4 * P, "total": op + 8 * P}
+
+
+class GaussianModel:
+    def __init__(self, sh_degree: int, optimizer_type: str = "default"):
+        self.active_sh_degree = 0
+        self.max_sh_degree = int(sh_degree)
+        self.sh_coeffs = (self.max_sh_degree + 1) ** 2
+        self.optimizer_type = optimizer_type
+        self.P = 0
+        self.store = self.grad = self.exp_avg = self.exp_avg_sq = self.act = None
+        self.max_radii2D = self.xyz_gradient_accum = self.denom = None
+        self.percent_dense = 0.0
+        self.spatial_lr_scale = 0.0
+        self.step_count = 0
+        self.lr: Dict[str, float] = {}
+        self.betas, self.eps = (0.9, 0.999), 1e-15
+        self._xyz_sched = None
+
+    # ---- construction ----------------------------------------------------------------------------------------------
+    def create_from_tensors(self, xyz, features_dc, features_rest, scaling, rotation, opacity, spatial_lr_scale: float = 1.0):
+        """Raw (pre-activation) parameters, shapes as in the reference: xyz [P,3], features_dc [P,1,3], features_rest
+        [P,M-1,3], scaling [P,3] (log), rotation [P,4], opacity [P,1] (logit).  (create_from_pcd :150-176 needs simple-knn;
+        out of scope -- initialise from tensors or from a checkpoint.)"""
+        P, M = int(xyz.shape[0]), self.sh_coeffs
+        if tuple(features_dc.shape) != (P, 1, 3) or tuple(features_rest.shape) != (P, M - 1, 3):
+            raise ValueError(f"features_dc / features_rest must be [P,1,3] / [P,{M - 1},3]")
+        self.spatial_lr_scale = float(spatial_lr_scale)
+        dev = xyz.device
+        self._allocate(P, dev)
+        with torch.no_grad():
+            self._xyz.copy_(xyz)
+            self._features[:, :1].copy_(features_dc)
+            self._features[:, 1:].copy_(features_rest)
+            self._scaling.copy_(scaling.reshape(P, 3))
+            self._rotation.copy_(rotation.reshape(P, 4))
+            self._opacity.copy_(opacity.reshape(P, 1))
+        self._reactivate()
+        self.max_radii2D = torch.zeros(P, device=dev)
+        return self
+
+    def _allocate(self, P: int, device):
+        total = store_offsets(P, self.sh_coeffs)["total"]
+        self.P = P
+        self.store = torch.zeros(total, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=device)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=device)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=device)
+        self.act = torch.zeros(8 * P, dtype=torch.float32, device=device)
+        self._bind()
+
+    def _bind(self):
+        """(Re)creates the typed views over the flat buffers.  The activated tensors are autograd leaves whose ``.grad`` is
+        the matching slice of ``self.grad``: gaussian_renderer.render_views_backward then accumulates in place."""
+        P, M, o = self.P, self.sh_coeffs, store_offsets(self.P, self.sh_coeffs)
+        cut = lambda buf, a, n, *shape: buf[a:a + n].view(*shape)
+        s = self.store
+        self._xyz = cut(s, o["xyz"], 3 * P, P, 3)
+        self._features = cut(s, o["features"], 3 * M * P, P, M, 3)
+        self._opacity = cut(s, o["opacity"], P, P, 1)
+        self._scaling = cut(s, o["scaling"], 3 * P, P, 3)
+        self._rotation = cut(s, o["rotation"], 4 * P, P, 4)
+        leaves = {"xyz": cut(s, o["xyz"], 3 * P, P, 3), "features": cut(s, o["features"], 3 * M * P, P, M, 3),
+                  "opacity": cut(self.act, 0, P, P, 1), "scaling": cut(self.act, P, 3 * P, P, 3),
+                  "rotation": cut(self.act, 4 * P, 4 * P, P, 4)}
+        gshape = {"xyz": (o["xyz"], 3 * P, (P, 3)), "features": (o["features"], 3 * M * P, (P, M, 3)),
+                  "opacity": (o["opacity"], P, (P, 1)), "scaling": (o["scaling"], 3 * P, (P, 3)),
+                  "rotation": (o["rotation"], 4 * P, (P, 4))}
+        for name, t in leaves.items():
+            t.requires_grad_(True)
+            a, n, shape = gshape[name]
+            t.grad = self.grad[a:a + n].view(*shape)
+        self._leaves = leaves
+
+    def _reactivate(self):
+        _dgr.activate(self.store, self.act, self.P, self.sh_coeffs)
+
+    # ---- what render() reads (gaussian_model.py:102-130) -----------------------------------------------------------
+    @property
+    def get_xyz(self):
+        return self._leaves["xyz"]
+
+    @property
+    def get_features(self):
+        return self._leaves["features"]
+
+    @property
+    def get_features_dc(self):
+        return self._features[:, :1]
+
+    @property
+    def get_features_rest(self):
+        return self._features[:, 1:]
+
+    @property
+    def _features_dc(self):
+        return self._features[:, :1]
+
+    @property
+    def _features_rest(self):
+        return self._features[:, 1:]
+
+    @property
+    def get_opacity(self):
+        return self._leaves["opacity"]
+
+    @property
+    def get_scaling(self):
+        return self._leaves["scaling"]
+
+    @property
+    def get_rotation(self):
+        return self._leaves["rotation"]
+
+    def get_covariance(self, scaling_modifier: float = 1.0):
+        raise NotImplementedError("compute_cov3D_python: the rasterizer builds the covariance from scales and rotations itself")
+
+    def oneupSHdegree(self):
+        if self.active_sh_degree < self.max_sh_degree:
+            self.active_sh_degree += 1
+
+    # ---- optimizer (training_setup :176-211, update_learning_rate :213-223, train.py:178-186) -------------------------
+    def training_setup(self, training_args):
+        g = lambda k: float(getattr(training_args, k))
+        self.percent_dense = g("percent_dense")
+        dev = self.store.device
+        self.xyz_gradient_accum = torch.zeros((self.P, 1), device=dev)
+        self.denom = torch.zeros((self.P, 1), device=dev)
+        self.lr = {"xyz": g("position_lr_init") * self.spatial_lr_scale, "f_dc": g("feature_lr"), "f_rest": g("feature_lr") / 20.0,
+                   "opacity": g("opacity_lr"), "scaling": g("scaling_lr"), "rotation": g("rotation_lr")}
+        self._xyz_sched = dict(lr_init=g("position_lr_init") * self.spatial_lr_scale,
+                               lr_final=g("position_lr_final") * self.spatial_lr_scale,
+                               lr_delay_mult=g("position_lr_delay_mult"), max_steps=int(g("position_lr_max_steps")))
+        self.step_count = 0
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+
+    def update_learning_rate(self, iteration: int) -> float:
+        self.lr["xyz"] = expon_lr(iteration, **self._xyz_sched)
+        return self.lr["xyz"]
+
+    def step_sizes(self):
+        """(step_size per group, sqrt(1 - beta2^t)) of the NEXT step, as torch.optim.Adam computes them in double."""
+        t = self.step_count + 1
+        if self.optimizer_type == "sparse_adam":
+            # [RECALL, UNVERIFIED_VS_REFERENCE] the accel branch's SparseGaussianAdam applies no bias correction
+            return [self.lr[n] for n in GROUPS], 1.0
+        bc1 = 1.0 - self.betas[0] ** t
+        return [self.lr[n] / bc1 for n in GROUPS], math.sqrt(1.0 - self.betas[1] ** t)
+
+    def optimizer_step(self, visible: Optional[torch.Tensor] = None):
+        """``optimizer.step()``: consumes ``self.grad`` (dLoss/d activated), updates the store and both moments in place and
+        rewrites the activated tensors.  ``visible`` ([P] bool): rows with False are left untouched (train.py:181-183)."""
+        ss, b2s = self.step_sizes()
+        _dgr.adam_step(self.store, self.grad, self.exp_avg, self.exp_avg_sq, self.act, self.P, self.sh_coeffs, ss, self.betas[0],
+                       self.betas[1], self.eps, b2s, visible)
+        self.step_count += 1
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    # ---- densification ---------------------------------------------------------------------------------------------
+    def add_densification_stats(self, viewspace_grad: torch.Tensor, update_filter: torch.Tensor):
+        """``viewspace_grad``: the [P,>=2] gradient of the screen-space means (``viewspace_point_tensor.grad``)."""
+        self.xyz_gradient_accum[update_filter] += torch.norm(viewspace_grad[update_filter, :2], dim=-1, keepdim=True)
+        self.denom[update_filter] += 1
+
+    def densify_and_prune(self, max_grad: float, min_opacity: float, extent: float, max_screen_size, radii=None,
+                          n_children: int = 2, unit_samples=None) -> Dict[str, int]:
+        """Clone small / split large gaussians whose mean view-space gradient is >= max_grad, then prune the transparent and
+        (when ``max_screen_size`` is set) the oversized ones -- row order, Adam-moment handling and random draw as in the
+        reference (one ``torch.randn`` of [n_children * n_split, 3] from the device generator, where the reference calls
+        ``torch.normal(mean=0, std=stds)`` with the same shape).  ``unit_samples``: the standard normals to use instead, a
+        tensor [n_children * n_split, 3] or a callable ``rows -> tensor`` (tests replaying a recorded draw)."""
+        dev = self.store.device
+        args, keep, (n_clone, n_split, n_pruned, P_new) = _dgr.densify_plan(
+            self.store, self.exp_avg, self.exp_avg_sq, self.xyz_gradient_accum, self.denom, self.P, self.sh_coeffs, n_children,
+            max_grad, self.percent_dense * extent, min_opacity, 0.1 * extent if max_screen_size else -1.0)
+        if not n_split:
+            unit = None
+        elif unit_samples is None:
+            unit = torch.randn((n_children * n_split, 3), device=dev)
+        else:
+            unit = unit_samples(n_children * n_split) if callable(unit_samples) else unit_samples
+            unit = unit.to(device=dev, dtype=torch.float32).reshape(n_children * n_split, 3).contiguous()
+        old = (self.store, self.exp_avg, self.exp_avg_sq)
+        total = store_offsets(P_new, self.sh_coeffs)["total"]
+        new = [torch.empty(total, dtype=torch.float32, device=dev) for _ in range(3)]
+        _dgr.densify_apply(args, unit, n_split, P_new, *new)
+        del keep, old
+        self.P = P_new
+        self.store, self.exp_avg, self.exp_avg_sq = new
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.act = torch.empty(8 * P_new, dtype=torch.float32, device=dev)
+        self._bind()
+        self._reactivate()
+        self.xyz_gradient_accum = torch.zeros((P_new, 1), device=dev)
+        self.denom = torch.zeros((P_new, 1), device=dev)
+        self.max_radii2D = torch.zeros(P_new, device=dev)
+        return {"n_clone": n_clone, "n_split": n_split, "n_pruned": n_pruned, "P": P_new}
+
+    def reset_opacity(self):
+        """raw opacity <- logit(min(sigmoid(raw), 0.01)); the group's Adam moments restart at zero (:258-261, :302-314)."""
+        o = store_offsets(self.P, self.sh_coeffs)
+        a, n = o["opacity"], self.P
+        with torch.no_grad():
+            y = torch.minimum(torch.sigmoid(self.store[a:a + n]), torch.full((), 0.01, device=self.store.device))
+            self.store[a:a + n] = torch.log(y / (1.0 - y))
+            self.exp_avg[a:a + n] = 0.0
+            self.exp_avg_sq[a:a + n] = 0.0
+        self._reactivate()
+
+    # ---- checkpoint (capture :63-76 / restore :78-99) -----------------------------------------------------------------
+    def capture(self):
+        return dict(active_sh_degree=self.active_sh_degree, max_sh_degree=self.max_sh_degree, P=self.P, store=self.store.clone(),
+                    exp_avg=self.exp_avg.clone(), exp_avg_sq=self.exp_avg_sq.clone(), max_radii2D=self.max_radii2D.clone(),
+                    xyz_gradient_accum=None if self.xyz_gradient_accum is None else self.xyz_gradient_accum.clone(),
+                    denom=None if self.denom is None else self.denom.clone(), step_count=self.step_count, lr=dict(self.lr),
+                    xyz_sched=self._xyz_sched, percent_dense=self.percent_dense, spatial_lr_scale=self.spatial_lr_scale)
+
+    def restore(self, state: dict):
+        if int(state["max_sh_degree"]) != self.max_sh_degree:
+            raise ValueError("checkpoint was written with another SH degree")
+        self.active_sh_degree = int(state["active_sh_degree"])
+        self._allocate(int(state["P"]), state["store"].device)
+        self.store.copy_(state["store"])
+        self.exp_avg.copy_(state["exp_avg"])
+        self.exp_avg_sq.copy_(state["exp_avg_sq"])
+        self.max_radii2D = state["max_radii2D"].clone()
+        self.xyz_gradient_accum = None if state["xyz_gradient_accum"] is None else state["xyz_gradient_accum"].clone()
+        self.denom = None if state["denom"] is None else state["denom"].clone()
+        self.step_count, self.lr, self._xyz_sched = int(state["step_count"]), dict(state["lr"]), state["xyz_sched"]
+        self.percent_dense, self.spatial_lr_scale = float(state["percent_dense"]), float(state["spatial_lr_scale"])
+        self._reactivate()
+        return self

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define GSB_ABI_VERSION 4
+#define GSB_ABI_VERSION 5
 
 /* error codes (0 = ok); gsb_last_error() holds the message of the calling thread's last failure */
 #define GSB_OK 0
@@ -181,6 +181,68 @@ int32_t gsb_l1_loss_grad(const float *image, const float *target, int64_t n, flo
 int32_t gsb_photometric_loss_grad(const float *image, const float *target, int32_t channels, int32_t height,
                                   int32_t width, float lambda_dssim, float *grad_out, float *loss_accum,
                                   gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream);
+
+/* ---- Training state around the path -------------------------------------
+ * The gaussians' RAW parameters live in ONE flat float buffer ("store"), group after group, each group [P, width]
+ * row-major.  With M = sh_coeffs:
+ *     xyz [P,3] | features [P,M,3] (row 0 = f_dc, rows 1.. = f_rest) | opacity [P,1] | scaling [P,3] | rotation [P,4]
+ * = (11 + 3M) floats per gaussian (59 at SH degree 3).  Gradients, exp_avg and exp_avg_sq use the same layout, so the
+ * data-parallel reduction is one all-reduce of one buffer and the optimizer is one launch.  The gradient buffer holds
+ * dLoss/d(ACTIVATED value) -- exactly what gsb_backward writes -- for the activations of scene/gaussian_model.py:33-46:
+ * identity (xyz, features), sigmoid (opacity), exp (scaling), normalize (rotation).
+ * `act` (8 floats per gaussian: sigmoid(opacity)[P] | exp(scaling)[P,3] | normalize(rotation)[P,4]) are the activated
+ * tensors the rasterizer reads; the optimizer rewrites them, so no separate activation pass runs between steps. */
+typedef struct GsbAdamArgs {
+    int64_t P;
+    int32_t sh_coeffs;
+    int32_t reserved;
+    float *params;            /* store, updated in place */
+    const float *grads;       /* dLoss/d activated, same layout */
+    float *exp_avg;
+    float *exp_avg_sq;
+    float *act;               /* rewritten from the updated parameters; may be NULL */
+    const uint8_t *visible;   /* NULL = every gaussian; else rows with visible[i] == 0 are left untouched */
+    float step_size[6];       /* lr_g / (1 - beta1^t) for xyz, f_dc, f_rest, opacity, scaling, rotation */
+    float beta1, beta2, eps;
+    float bias2_sqrt;         /* sqrt(1 - beta2^t) */
+} GsbAdamArgs;
+
+/* torch.optim.Adam (no weight decay, no amsgrad; scene/gaussian_model.py:176-199, train.py:178-186) over the six parameter
+ * groups in one launch, with the activation backward (autograd's part in the reference) and the re-activation fused in:
+ *   g_raw = J_act^T g;  m += (1-b1)(g_raw - m);  v = b2 v + (1-b2) g_raw^2;  p -= step_size * m / (sqrt(v)/bias2_sqrt + eps) */
+int32_t gsb_adam_step(const GsbAdamArgs *args, void *cuda_stream);
+
+/* act <- activations of the store (after initialisation, densification or an opacity reset) */
+int32_t gsb_activate(int64_t P, int32_t sh_coeffs, const float *params, float *act, void *cuda_stream);
+
+/* densify_and_prune (scene/gaussian_model.py:399-469) as a plan (classification + two scans; one host read-back) and one
+ * gather that writes the new store and its Adam moments.  Row order of the result is the reference's:
+ *   surviving originals | surviving clones | surviving children, copy-major (child k of the j-th split gaussian at k*n_split + j)
+ * Survivors keep their moments, new rows start at zero (:359-397).  Every threshold is passed in already multiplied out:
+ *   clone  if mean grad >= grad_threshold and max(exp(scaling)) <= size_limit   (size_limit = percent_dense * extent)
+ *   split  if mean grad >= grad_threshold and max(exp(scaling)) >  size_limit   (children: scaling / (0.8 * n_children))
+ *   prune  if sigmoid(opacity) < min_opacity, or (world_limit >= 0 and max(exp(scaling)) > world_limit = 0.1 * extent)
+ * The screen-size test of :462 never fires in the reference (max_radii2D is zeroed by densification_postfix first) and
+ * is therefore absent.  grad_threshold must be > 0 (a clone is never split). */
+typedef struct GsbDensifyArgs {
+    int64_t P;
+    int32_t sh_coeffs;
+    int32_t n_children;       /* 2 in the reference */
+    const float *params;      /* old store and moments */
+    const float *exp_avg;
+    const float *exp_avg_sq;
+    const float *grad_accum;  /* [P] accumulated view-space gradient norm */
+    const float *denom;       /* [P] how many views accumulated */
+    float grad_threshold, size_limit, min_opacity, world_limit;
+    void *scratch;            /* gsb_densify_scratch_bytes(P, n_children) bytes; written by plan, read by apply */
+} GsbDensifyArgs;
+size_t gsb_densify_scratch_bytes(int64_t P, int32_t n_children);
+/* counts = { n_clone, n_split, n_pruned, P_new }.  Synchronises the stream once (the caller needs n_split to draw the
+ * samples and P_new to size the new store -- the reference synchronises a dozen times here). */
+int32_t gsb_densify_plan(const GsbDensifyArgs *args, int64_t counts[4], void *cuda_stream);
+/* unit_samples: [n_children * n_split, 3] standard normals (the draw of torch.normal at :409). */
+int32_t gsb_densify_apply(const GsbDensifyArgs *args, const float *unit_samples, int64_t n_split, int64_t P_new,
+                          float *new_params, float *new_exp_avg, float *new_exp_avg_sq, void *cuda_stream);
 
 const char *gsb_last_error(void);
 int32_t gsb_abi_version(void);

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in decl:
         assert hasattr(lib, name), f"{name} declared in include/ but not exported"
     lib.gsb_abi_version.restype = ctypes.c_int32
-    assert lib.gsb_abi_version() == 4
+    assert lib.gsb_abi_version() == 5
 
 
 def test_struct_sizes_match_header():
@@ -38,6 +38,39 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(dgr._Inputs) == 64
     assert ctypes.sizeof(dgr._State) == 120
     assert ctypes.sizeof(dgr._Grads) == 64
+    assert ctypes.sizeof(dgr._AdamArgs) == 104
+    assert ctypes.sizeof(dgr._DensifyArgs) == 80
+
+
+def test_ctypes_mirrors_agree_with_the_c_compiler(tmp_path):
+    """sizeof / offsetof of the argument structs as gcc sees include/gs_b200.h vs the ctypes mirrors."""
+    import shutil
+    import subprocess
+    import sys
+    import pytest
+    gcc = shutil.which("gcc", path="/usr/bin") or shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    sys.path.insert(0, os.path.join(ROOT, "gaussian-splatting_b200"))
+    import diff_gaussian_rasterization as dgr
+    probes = {"GsbAdamArgs": (dgr._AdamArgs, ["P", "params", "visible", "step_size", "beta1", "bias2_sqrt"]),
+              "GsbDensifyArgs": (dgr._DensifyArgs, ["P", "n_children", "params", "denom", "grad_threshold", "world_limit", "scratch"]),
+              "GsbSettings": (dgr._Settings, []), "GsbInputs": (dgr._Inputs, []), "GsbState": (dgr._State, []), "GsbGrads": (dgr._Grads, [])}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gs_b200.h"', 'int main(void) {']
+    for cname, (_, fields) in probes.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines.append("return 0; }")
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, (ct, fields) in probes.items():
+        assert int(got[cname]) == ctypes.sizeof(ct), cname
+        for f in fields:
+            assert int(got[f"{cname}.{f}"]) == getattr(ct, f).offset, (cname, f)
 
 
 def test_argument_errors_are_reported_not_crashed():

@@ -1,0 +1,182 @@
+"""Runs the SOURCE of csrc/optim.cu and csrc/densify.cu on the CPU through tests/host_emul/cuda_shim.h (blocks sequential,
+threads of a block = host threads) and drives gaussian_store.GaussianModel with it: the kernels' index arithmetic, scans,
+row order and the host class's buffer surgery are checked against the reference fixture where no GPU exists.  The GPU parity
+tests proper are tests/test_store_gpu.py; nothing here is a product path (the library raises on CPU tensors)."""
+import ctypes
+import os
+import shutil
+import subprocess
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+import diff_gaussian_rasterization as dgr
+from gaussian_store import GaussianModel
+from oracle.model_oracle import GROUPS
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "reference_model.npz")
+RAW_KEY = {"xyz": "_xyz", "f_dc": "_features_dc", "f_rest": "_features_rest", "opacity": "_opacity", "scaling": "_scaling",
+           "rotation": "_rotation"}
+ACT = ("xyz", "features", "opacity", "scaling", "rotation")
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    gxx = shutil.which("g++", path="/usr/bin") or shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no host C++ compiler")
+    d = tmp_path_factory.mktemp("emul")
+    for f in ("cuda_shim.h", "emul_main.cpp"):
+        shutil.copy(os.path.join(ROOT, "tests", "host_emul", f), d / f)
+    for name in ("optim", "densify"):
+        src = open(os.path.join(ROOT, "gaussian-splatting_b200", "csrc", name + ".cu")).read().splitlines()
+        body = [l for l in src if l.strip() not in ('#include "common.cuh"', '#include "kernels.cuh"')]
+        assert len(body) == len(src) - 2
+        (d / f"{name}_body.inc").write_text("\n".join(body) + "\n")
+    subprocess.run([gxx, "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", str(d / "emul_main.cpp"), "-o", str(d / "libemul.so")],
+                   check=True)
+    lib = ctypes.CDLL(str(d / "libemul.so"))
+    vp, i64, i32, f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float
+    lib.emul_adam_step.argtypes = [i64, i32, vp, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32]
+    lib.emul_activate.argtypes = [i64, i32, vp, vp]
+    lib.emul_densify_scratch_bytes.restype = ctypes.c_size_t
+    lib.emul_densify_scratch_bytes.argtypes = [i64, i32]
+    lib.emul_densify_plan.argtypes = [i64, i32, i32, vp, vp, vp, f32, f32, f32, f32, vp, vp]
+    lib.emul_densify_apply.argtypes = [i64, i32, i32, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]
+    lib.emul_exclusive_scan.argtypes = [vp, vp, ctypes.c_size_t, vp, vp]
+    lib.emul_scan_partials.restype = ctypes.c_size_t
+    lib.emul_scan_partials.argtypes = [ctypes.c_size_t]
+    return lib
+
+
+@pytest.fixture()
+def on_host(emul, monkeypatch):
+    """Routes the four kernel entry points gaussian_store uses to the host build of the same kernel sources."""
+    def adam_step(params, grads, m, v, act, P, M, step_size, b1, b2, eps, bc2s, visible=None):
+        ss = np.asarray(step_size, dtype=np.float32)
+        vis = visible.to(torch.uint8).contiguous() if visible is not None else None
+        assert emul.emul_adam_step(P, M, params.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr(), act.data_ptr(),
+                                   vis.data_ptr() if vis is not None else None, ss.ctypes.data, b1, b2, eps, bc2s) == 0
+
+    def activate(params, act, P, M):
+        assert emul.emul_activate(P, M, params.data_ptr(), act.data_ptr()) == 0
+
+    def densify_plan(params, m, v, accum, denom, P, M, N, thr, size_limit, min_opacity, world_limit):
+        scratch = torch.zeros(max(emul.emul_densify_scratch_bytes(P, N), 1), dtype=torch.uint8)
+        ga, dn = accum.reshape(-1).float().contiguous(), denom.reshape(-1).float().contiguous()
+        counts = np.zeros(4, dtype=np.int64)
+        assert emul.emul_densify_plan(P, M, N, params.data_ptr(), ga.data_ptr(), dn.data_ptr(), thr, size_limit, min_opacity,
+                                      world_limit, scratch.data_ptr(), counts.ctypes.data) == 0
+        return dict(P=P, M=M, N=N, params=params, m=m, v=v, scratch=scratch), (scratch, ga, dn), tuple(int(c) for c in counts)
+
+    def densify_apply(args, unit, n_split, P_new, new_p, new_m, new_v):
+        u = unit.float().contiguous() if unit is not None else None
+        assert emul.emul_densify_apply(args["P"], args["M"], args["N"], args["params"].data_ptr(), args["m"].data_ptr(),
+                                       args["v"].data_ptr(), args["scratch"].data_ptr(), u.data_ptr() if u is not None else None,
+                                       n_split, P_new, new_p.data_ptr(), new_m.data_ptr(), new_v.data_ptr()) == 0
+
+    for name, fn in (("adam_step", adam_step), ("activate", activate), ("densify_plan", densify_plan), ("densify_apply", densify_apply)):
+        monkeypatch.setattr(dgr, name, fn)
+
+
+def test_scan_source_multi_tile(emul):
+    """> 256 chunks of 2048: the partials kernel loops over more than one tile of 256."""
+    n = 2048 * 300 + 77
+    rng = np.random.default_rng(0)
+    x = rng.integers(0, 3, n, dtype=np.uint32)
+    out = np.zeros(n, dtype=np.uint32)
+    partials = np.zeros(emul.emul_scan_partials(n), dtype=np.uint32)
+    total = np.zeros(1, dtype=np.uint32)
+    assert emul.emul_exclusive_scan(x.ctypes.data, out.ctypes.data, n, partials.ctypes.data, total.ctypes.data) == 0
+    ref = np.concatenate(([0], np.cumsum(x, dtype=np.uint64)[:-1])).astype(np.uint32)
+    assert np.array_equal(out, ref) and int(total[0]) == int(x.sum())
+    # in place
+    assert emul.emul_exclusive_scan(x.ctypes.data, x.ctypes.data, n, partials.ctypes.data, total.ctypes.data) == 0
+    assert np.array_equal(x, ref)
+
+
+def test_kernel_sources_replay_reference_fixture(on_host):
+    gold = {k: v for k, v in np.load(GOLD).items()}
+    opt = {k[4:]: float(v) for k, v in gold.items() if k.startswith("opt_")}
+    extent = float(gold["dens_extent"])
+    t = lambda k: torch.from_numpy(gold["init" + RAW_KEY[k]])
+    m = GaussianModel(3).create_from_tensors(t("xyz"), t("f_dc"), t("f_rest"), t("scaling"), t("rotation"), t("opacity"), extent)
+    m.training_setup(SimpleNamespace(**opt))
+
+    def step(it):
+        m.update_learning_rate(it)
+        act = {"xyz": m.get_xyz, "features": m.get_features, "opacity": m.get_opacity, "scaling": m.get_scaling,
+               "rotation": m.get_rotation}
+        for n in ACT:
+            g = torch.from_numpy(gold["w_" + n][:m.P]) + torch.from_numpy(gold["u_" + n][:m.P]) * act[n].detach()
+            act[n].grad.copy_(g.view_as(act[n]))
+        m.optimizer_step()
+
+    def check(tag):
+        raw = {"xyz": m._xyz, "f_dc": m._features_dc, "f_rest": m._features_rest, "opacity": m._opacity, "scaling": m._scaling,
+               "rotation": m._rotation}
+        for n in GROUPS:
+            ref = torch.from_numpy(gold[tag + RAW_KEY[n]])
+            assert tuple(raw[n].shape) == tuple(ref.shape), (tag, n, raw[n].shape, ref.shape)
+            torch.testing.assert_close(raw[n], ref, rtol=2e-6, atol=2e-6, msg=lambda s: f"{tag} {n}: {s}")
+        from gaussian_store import store_offsets
+        P, M, o = m.P, m.sh_coeffs, store_offsets(m.P, m.sh_coeffs)
+        for kind, buf in (("m", m.exp_avg), ("v", m.exp_avg_sq)):
+            feat = buf[o["features"]:o["opacity"]].view(P, M, 3)
+            got = {"xyz": buf[:3 * P].view(P, 3), "f_dc": feat[:, :1], "f_rest": feat[:, 1:], "opacity": buf[o["opacity"]:o["scaling"]].view(P, 1),
+                   "scaling": buf[o["scaling"]:o["rotation"]].view(P, 3), "rotation": buf[o["rotation"]:].view(P, 4)}
+            for n in GROUPS:
+                torch.testing.assert_close(got[n], torch.from_numpy(gold[f"{tag}_{kind}_{n}"]), rtol=1e-4,
+                                           atol=1e-9 if kind == "m" else 1e-13, msg=lambda s: f"{tag} {kind} {n}: {s}")
+
+    def densify(key, seed, max_screen):
+        m.xyz_gradient_accum = torch.from_numpy(gold[key + "_accum"]).clone()
+        m.denom = torch.from_numpy(gold[key + "_denom"]).clone()
+
+        def draw(rows):
+            torch.manual_seed(seed)
+            return torch.randn(rows, 3)
+
+        info = m.densify_and_prune(opt["densify_grad_threshold"], 0.005, extent, max_screen, unit_samples=draw)
+        assert info["P"] == int(gold["d_P" if key == "dens" else "d2_P"]), info
+        assert info["n_clone"] > 0 and info["n_split"] > 0
+
+    it = 0
+    for _ in range(3):
+        it += 1
+        step(it)
+    check("s3")
+    densify("dens", 77, 20)
+    check("d")
+    for _ in range(2):
+        it += 1
+        step(it)
+    check("s5")
+    m.reset_opacity()
+    it += 1
+    step(it)
+    check("s6")
+    densify("dens2", 78, None)
+    check("d2")
+
+
+def test_kernel_source_visible_mask(on_host):
+    g = torch.Generator().manual_seed(3)
+    P = 70
+    m = GaussianModel(1).create_from_tensors(torch.randn(P, 3, generator=g), torch.randn(P, 1, 3, generator=g),
+                                             torch.randn(P, 3, 3, generator=g), torch.randn(P, 3, generator=g) - 3,
+                                             torch.randn(P, 4, generator=g), torch.randn(P, 1, generator=g))
+    m.training_setup(SimpleNamespace(position_lr_init=1e-3, position_lr_final=1e-5, position_lr_delay_mult=0.01, position_lr_max_steps=100,
+                                     feature_lr=0.0025, opacity_lr=0.025, scaling_lr=0.005, rotation_lr=0.001, percent_dense=0.01))
+    m.grad.copy_(torch.randn(m.grad.shape, generator=g) * 1e-3)
+    before = (m.store.clone(), m.exp_avg.clone(), m.act.clone())
+    vis = torch.rand(P, generator=g) < 0.5
+    m.optimizer_step(visible=vis)
+    assert torch.equal(m._xyz[~vis], before[0][:3 * P].view(P, 3)[~vis]) and not torch.equal(m._xyz[vis], before[0][:3 * P].view(P, 3)[vis])
+    assert torch.equal(m._features[~vis], before[0][3 * P:3 * P + 12 * P].view(P, 4, 3)[~vis])
+    assert torch.equal(m._rotation[~vis], before[0][-4 * P:].view(P, 4)[~vis]) and not torch.equal(m._rotation[vis], before[0][-4 * P:].view(P, 4)[vis])
+    assert torch.equal(m.act[:P][~vis], before[2][:P][~vis])
+    assert float(m.exp_avg[:3 * P].view(P, 3)[~vis].abs().max()) == 0.0
