@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--loss", default="l1", choices=["l1", "l1_ssim"],
                     help="l1: mean |clamp(image) - target| (default, comparable across rounds); l1_ssim: the reference step's "
                          "0.8 L1 + 0.2 (1 - SSIM) (train.py:120-126), fused kernel")
+    ap.add_argument("--optimizer", action="store_true",
+                    help="whole training iteration: the gaussians live in gaussian_store.GaussianModel (raw parameters) and "
+                         "every step ends with its fused activation-backward + Adam step (outside the BASELINE metric)")
     ap.add_argument("--no-batch", action="store_true", help="views API view by view instead of gsb_forward_batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
@@ -243,7 +246,7 @@ def workload_config(a, world):
             "gaussians": a.gaussians, "image": [a.width, a.height], "sh_degree": a.sh_degree,
             "views_per_rank": a.views_per_rank, "views_total": a.views_per_rank * world,
             "parallelism": f"view-parallel x{world}, gaussians replicated, one all-reduce of 59 floats/gaussian",
-            "api": a.api, "loss": a.loss,
+            "api": a.api, "loss": a.loss, "optimizer": "fused_adam_store" if a.optimizer else "none",
             "l2": "inputs_exceed_l2 (236 MB parameters + 8 distinct views per step; no explicit flush)",
             "scene": f"xyz~U([-1,1]^3), log-scale~N({LOG_SCALE_MEAN},0.5), opacity=sigmoid(U(-2,4)), cameras on sphere r=3, seed 0"}
 
@@ -304,8 +307,32 @@ def main():
 
     torch.manual_seed(0)
     scene = make_scene(a.gaussians, seed=0, log_scale_mean=LOG_SCALE_MEAN)
-    pc = BenchGaussians(scene, a.sh_degree, dev)
-    bucket = GradientBucket(pc.parameters())
+    if a.optimizer:
+        from types import SimpleNamespace
+        from gaussian_store import GaussianModel
+        sc = {k: v.to(dev) for k, v in scene.items()}
+        pc = GaussianModel(int(round(math.sqrt(sc["shs"].shape[1]))) - 1)
+        pc.active_sh_degree = a.sh_degree
+        op = sc["opacities"].clamp(1e-6, 1 - 1e-6).reshape(-1, 1)
+        pc.create_from_tensors(sc["means3D"], sc["shs"][:, :1].contiguous(), sc["shs"][:, 1:].contiguous(), torch.log(sc["scales"]),
+                               sc["rotations"], torch.log(op / (1 - op)), 1.0)
+        pc.training_setup(SimpleNamespace(position_lr_init=0.00016, position_lr_final=0.0000016, position_lr_delay_mult=0.01,
+                                          position_lr_max_steps=30000, feature_lr=0.0025, opacity_lr=0.025, scaling_lr=0.005,
+                                          rotation_lr=0.001, percent_dense=0.01))      # arguments/__init__.py:77-89
+        del sc
+
+        class StoreBucket:           # the store's gradient buffer IS the all-reduce bucket
+            def zero_(self):
+                pc.grad.zero_()
+
+            def all_reduce(self):
+                if world > 1:
+                    dist.all_reduce(pc.grad, op=dist.ReduceOp.SUM)
+
+        bucket = StoreBucket()
+    else:
+        pc = BenchGaussians(scene, a.sh_degree, dev)
+        bucket = GradientBucket(pc.parameters())
     pipe = Pipe()
     bg = torch.zeros(3, device=dev)
     V, H, W = a.views_per_rank, a.height, a.width
@@ -367,6 +394,9 @@ def main():
                 loss.backward()
                 total += loss.detach()
         bucket.all_reduce()
+        if a.optimizer:
+            pc.update_learning_rate(pc.step_count + 1)
+            pc.optimizer_step()
         if host_inputs:
             # device -> host read of the step's result: an asynchronous copy into pinned memory every step (the host does
             # not stall on it; all of them have landed when the timed region's final synchronize returns)

@@ -132,6 +132,7 @@ def test_adam_step_matches_torch_adam_with_autograd_chain(P):
     raw, opt, oracle, m, g = _random_state(P, 5 + P, dev)
     shapes = {"xyz": (P, 3), "features": (P, 16, 3), "opacity": (P, 1), "scaling": (P, 3), "rotation": (P, 4)}
     for it in range(1, 5):
+        scale = 1e-3 if it < 3 else 1.0          # the moments keep the large step's rounding error afterwards
         grads = {n: torch.randn(*shapes[n], generator=g) * (1e-3 if it != 3 else 1.0) for n in ACT}
         oracle.step(it, grads)
         m.update_learning_rate(it)
@@ -143,8 +144,9 @@ def test_adam_step_matches_torch_adam_with_autograd_chain(P):
         for n in GROUPS:
             # a raw gradient that cancels to ~0 may flip the sign of m/sqrt(v): allow a 1e-4 fraction of outliers
             assert _frac_bad(rawm[n], oracle.p[n].detach(), 5e-6, 5e-6) <= 1e-4, (it, n)
-            assert _frac_bad(mom["m"][n], omom[n]["m"], 1e-4, 1e-9) <= 1e-4, (it, n)
-            assert _frac_bad(mom["v"][n], omom[n]["v"], 1e-4, 1e-14) <= 1e-4, (it, n)
+            # normalize's backward (g - y (y.g)) / |q| cancels: its absolute error scales with |g|, not with the result
+            assert _frac_bad(mom["m"][n], omom[n]["m"], 1e-4, 1e-9 + 2e-7 * scale) <= 1e-4, (it, n)
+            assert _frac_bad(mom["v"][n], omom[n]["v"], 1e-4, 1e-14 + 2e-9 * scale * scale) <= 1e-4, (it, n)
         act = oracle.activated()
         for n, leaf in (("opacity", m.get_opacity), ("scaling", m.get_scaling), ("rotation", m.get_rotation)):
             assert _frac_bad(leaf.detach(), act[n].detach(), 1e-5, 1e-6) <= 1e-4, (it, n, "activated")
