@@ -474,8 +474,8 @@ def main():
         rs = dgr.GaussianRasterizationSettings(H, W, math.tan(cams[0].FoVx * 0.5), math.tan(cams[0].FoVy * 0.5), bg, 1.0,
                                                cams[0].world_view_transform, cams[0].full_proj_transform, a.sh_degree,
                                                cams[0].camera_center, False, False, False)
-        _, radii, _, pack = dgr._forward_impl(pc._xyz.detach(), pc._shs.detach(), None, pc._opacity.detach().reshape(-1),
-                                              pc._scaling.detach(), pc._rotation.detach(), None, rs)
+        _, radii, _, pack = dgr._forward_impl(pc.get_xyz.detach(), pc.get_features.detach(), None, pc.get_opacity.detach().reshape(-1),
+                                              pc.get_scaling.detach(), pc.get_rotation.detach(), None, rs)
         sv = dgr.state_views(pack, H, W)
         D = int(pack["num_rendered"])
         lens = (sv["ranges"][:, 1] - sv["ranges"][:, 0]).float()
