@@ -261,6 +261,21 @@ class GaussianModel:
             self.exp_avg_sq[a:a + n] = 0.0
         self._reactivate()
 
+    # ---- point_cloud.ply (save_ply :239-256, load_ply :263-314) --------------------------------------------------------
+    def save_ply(self, path: str):
+        from .ply import write_gaussian_ply
+        c = lambda t: t.detach().cpu().numpy()
+        write_gaussian_ply(path, c(self._xyz), c(self._features_dc), c(self._features_rest), c(self._opacity), c(self._scaling),
+                           c(self._rotation))
+
+    def load_ply(self, path: str, device="cuda", spatial_lr_scale: Optional[float] = None):
+        from .ply import read_gaussian_ply
+        a = {k: torch.from_numpy(v).to(device) for k, v in read_gaussian_ply(path, self.max_sh_degree).items()}
+        self.create_from_tensors(a["xyz"], a["features_dc"], a["features_rest"], a["scaling"], a["rotation"], a["opacity"],
+                                 self.spatial_lr_scale if spatial_lr_scale is None else spatial_lr_scale)
+        self.active_sh_degree = self.max_sh_degree
+        return self
+
     # ---- checkpoint (capture :63-76 / restore :78-99) -----------------------------------------------------------------
     def capture(self):
         return dict(active_sh_degree=self.active_sh_degree, max_sh_degree=self.max_sh_degree, P=self.P, store=self.store.clone(),

@@ -253,3 +253,13 @@ def test_store_trains_through_the_rasterizer():
         m.optimizer_step()
         losses.append(float(out["losses"].sum()))
     assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0] * 0.98, losses
+
+
+def test_model_ply_round_trip(tmp_path):
+    dev = torch.device("cuda:0")
+    raw, opt, oracle, m, g = _random_state(257, 41, dev)
+    path = str(tmp_path / "point_cloud.ply")
+    m.save_ply(path)
+    m2 = _model_cls()(3).load_ply(path, device=dev, spatial_lr_scale=4.0)
+    assert m2.P == m.P and m2.active_sh_degree == 3 and torch.equal(m2.store, m.store)
+    torch.testing.assert_close(m2.act, m.act, rtol=0, atol=0)
