@@ -708,6 +708,17 @@ int32_t gsb_densify_apply(const GsbDensifyArgs *a, const float *unit_samples, in
                                 n_split, P_new, new_params, new_exp_avg, new_exp_avg_sq, static_cast<cudaStream_t>(cuda_stream));
 }
 
+int32_t gsb_knn_mean_dist2(const float *points, int64_t P, float *out, gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream) {
+    if (P < 0 || P >= ((int64_t)1 << 31) || !alloc || (P > 0 && (!points || !out))) {
+        set_error("gsb_knn_mean_dist2: bad argument");
+        return GSB_ERR_ARGUMENT;
+    }
+    if (P == 0) return GSB_OK;
+    void *scr = do_alloc(alloc, alloc_ctx, GSB_BUF_SCRATCH0, knn_scratch_bytes(P));
+    if (!scr) return GSB_ERR_ALLOC;
+    return launch_knn_mean_dist2(points, P, out, scr, static_cast<cudaStream_t>(cuda_stream));
+}
+
 int32_t gsb_sort_pairs(uint32_t *keys, uint32_t *vals, int64_t n, int32_t begin_bit, int32_t end_bit,
                        gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream) {
     if (n < 0 || (n > 0 && (!keys || !vals)) || !alloc || begin_bit < 0 || end_bit > 32 || begin_bit > end_bit) {

@@ -129,6 +129,12 @@ static int exclusive_scan_u32(const uint32_t *in, uint32_t *out, size_t n, uint3
     return GSB_OK;
 }
 
+// shared with knn.cu
+size_t scan_u32_partials(int64_t n) { return partial_count(n); }
+int scan_u32_exclusive(const uint32_t *in, uint32_t *out, size_t n, uint32_t *partials, uint32_t *total, cudaStream_t stream) {
+    return exclusive_scan_u32(in, out, n, partials, total, stream);
+}
+
 // ---- classification ------------------------------------------------------------------------------------------------------
 struct ClassifyArgs {
     uint32_t P;

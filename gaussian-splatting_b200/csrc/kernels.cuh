@@ -110,6 +110,12 @@ int launch_adam_step(int64_t P, int sh_coeffs, float *params, const float *grads
                      cudaStream_t stream);
 int launch_activate(int64_t P, int sh_coeffs, const float *params, float *act, cudaStream_t stream);
 size_t densify_scratch_bytes(int64_t P, int n_children);
+// exclusive scan of n uint32 (in == out allowed); partials: scan_u32_partials(n) words; *total receives the sum
+size_t scan_u32_partials(int64_t n);
+int scan_u32_exclusive(const uint32_t *in, uint32_t *out, size_t n, uint32_t *partials, uint32_t *total, cudaStream_t stream);
+// 3-nearest-neighbour mean squared distance (knn.cu)
+size_t knn_scratch_bytes(int64_t P);
+int launch_knn_mean_dist2(const float *points, int64_t P, float *out, void *scratch, cudaStream_t stream);
 int launch_densify_plan(int64_t P, int sh_coeffs, int n_children, const float *params, const float *grad_accum, const float *denom,
                         float grad_threshold, float size_limit, float min_opacity, float world_limit, void *scratch,
                         uint32_t **counters_dev, cudaStream_t stream);

@@ -114,6 +114,8 @@ def _load():
     lib.gsb_densify_plan.argtypes = [POINTER(_DensifyArgs), POINTER(c_int64 * 4), c_void_p]
     lib.gsb_densify_apply.restype = c_int32
     lib.gsb_densify_apply.argtypes = [POINTER(_DensifyArgs), c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.gsb_knn_mean_dist2.restype = c_int32
+    lib.gsb_knn_mean_dist2.argtypes = [c_void_p, c_int64, c_void_p, _ALLOC_FN, c_void_p, c_void_p]
     if lib.gsb_abi_version() != 5:
         raise ImportError(f"{_LIB_PATH}: ABI version {lib.gsb_abi_version()} != 5")
     return lib
@@ -247,6 +249,19 @@ def densify_apply(args, unit_samples: Optional[torch.Tensor], n_split: int, P_ne
     with torch.cuda.device(new_params.device):
         _check(_C.gsb_densify_apply(byref(args), _ptr(us), int(n_split), int(P_new), new_params.data_ptr(), new_exp_avg.data_ptr(),
                                     new_exp_avg_sq.data_ptr(), stream))
+
+
+def knn_mean_dist2(points: torch.Tensor) -> torch.Tensor:
+    """Mean squared distance of every point [P,3] to its three nearest other points (gsb_knn_mean_dist2; the replacement of
+    simple_knn._C.distCUDA2, scene/gaussian_model.py:159)."""
+    pts = _f32c(points.reshape(-1, 3))
+    stream = _stream_of(pts)
+    out = torch.empty(pts.shape[0], dtype=torch.float32, device=pts.device)
+    with torch.cuda.device(pts.device):
+        arena = _Arena(pts.device, stream)
+        rc = _C.gsb_knn_mean_dist2(pts.data_ptr(), int(pts.shape[0]), out.data_ptr(), arena.cb, None, stream)
+    _check(rc, arena)
+    return out
 
 
 class _Arena:

@@ -244,6 +244,12 @@ int32_t gsb_densify_plan(const GsbDensifyArgs *args, int64_t counts[4], void *cu
 int32_t gsb_densify_apply(const GsbDensifyArgs *args, const float *unit_samples, int64_t n_split, int64_t P_new,
                           float *new_params, float *new_exp_avg, float *new_exp_avg_sq, void *cuda_stream);
 
+/* Mean squared distance from every point to its three nearest other points: the replacement of
+ * simple_knn._C.distCUDA2 (scene/gaussian_model.py:21,159 -- initial scales).  points [P,3], out [P]; exact (uniform grid
+ * sized on the device, no host synchronisation); scratch through alloc. */
+int32_t gsb_knn_mean_dist2(const float *points, int64_t P, float *out, gsb_alloc_fn alloc, void *alloc_ctx,
+                           void *cuda_stream);
+
 const char *gsb_last_error(void);
 int32_t gsb_abi_version(void);
 /* number of kernels this library has launched in this process since the last reset */

@@ -26,6 +26,7 @@
 
 struct Idx3 { unsigned x = 0, y = 0, z = 0; };
 static thread_local Idx3 threadIdx, blockIdx;
+static Idx3 gridDim;
 
 struct BlockCtx {
     std::unique_ptr<std::barrier<>> block_bar;
@@ -49,7 +50,23 @@ inline uint32_t warp_exchange(uint32_t v, F pick) {
 inline uint32_t __shfl_up_sync(unsigned, uint32_t v, int d) { return warp_exchange(v, [d](int l) { return l - d >= 0 ? l - d : l; }); }
 inline uint32_t __shfl_xor_sync(unsigned, uint32_t v, int m) { return warp_exchange(v, [m](int l) { return l ^ m; }); }
 inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline uint32_t atomicMin(uint32_t *p, uint32_t v) {
+    uint32_t old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+inline uint32_t atomicMax(uint32_t *p, uint32_t v) {
+    uint32_t old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
+inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+struct float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 using std::isnan;
+using std::max;
+using std::min;
 
 // ---- what the sources expect from common.cuh (copied definitions: plain C++) ------------------------------------------------
 typedef void *cudaStream_t;
@@ -85,6 +102,7 @@ inline void emul_launch(unsigned grid, unsigned block, F body) {
     for (unsigned w = 0; w < warps; ++w) ctx.warp_bar.emplace_back(std::make_unique<std::barrier<>>(std::min(32u, block - 32 * w)));
     ctx.xchg.assign(warps * 32, 0u);
     g_ctx = &ctx;
+    gridDim.x = grid;
     for (unsigned b = 0; b < grid; ++b) {
         std::vector<std::thread> th;
         th.reserve(block);

@@ -8,8 +8,13 @@ int launch_adam_step(int64_t P, int sh_coeffs, float *params, const float *grads
                      const uint8_t *visible, const float step_size[6], float beta1, float beta2, float eps, float bias2_sqrt,
                      cudaStream_t stream);
 }
+namespace gsb {
+size_t scan_u32_partials(int64_t n);
+int scan_u32_exclusive(const uint32_t *in, uint32_t *out, size_t n, uint32_t *partials, uint32_t *total, cudaStream_t stream);
+}
 #include "optim_body.inc"
 #include "densify_body.inc"
+#include "knn_body.inc"
 
 extern "C" {
 int emul_adam_step(int64_t P, int M, float *params, const float *grads, float *m, float *v, float *act, const uint8_t *visible,
@@ -25,6 +30,10 @@ int emul_densify_plan(int64_t P, int M, int N, const float *params, const float 
     if (e) return e;
     for (int k = 0; k < 4; ++k) counts[k] = dev[k];
     return dev[4] == dev[1] ? 0 : 2;
+}
+size_t emul_knn_scratch_bytes(int64_t P) { return gsb::knn_scratch_bytes(P); }
+int emul_knn_mean_dist2(const float *points, int64_t P, float *out, void *scratch) {
+    return gsb::launch_knn_mean_dist2(points, P, out, scratch, nullptr);
 }
 int emul_exclusive_scan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *partials, uint32_t *total) {
     return gsb::exclusive_scan_u32(in, out, n, partials, total, nullptr);

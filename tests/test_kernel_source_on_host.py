@@ -31,7 +31,7 @@ def emul(tmp_path_factory):
     d = tmp_path_factory.mktemp("emul")
     for f in ("cuda_shim.h", "emul_main.cpp"):
         shutil.copy(os.path.join(ROOT, "tests", "host_emul", f), d / f)
-    for name in ("optim", "densify"):
+    for name in ("optim", "densify", "knn"):
         src = open(os.path.join(ROOT, "gaussian-splatting_b200", "csrc", name + ".cu")).read().splitlines()
         body = [l for l in src if l.strip() not in ('#include "common.cuh"', '#include "kernels.cuh"')]
         assert len(body) == len(src) - 2
@@ -180,3 +180,33 @@ def test_kernel_source_visible_mask(on_host):
     assert torch.equal(m._rotation[~vis], before[0][-4 * P:].view(P, 4)[~vis]) and not torch.equal(m._rotation[vis], before[0][-4 * P:].view(P, 4)[vis])
     assert torch.equal(m.act[:P][~vis], before[2][:P][~vis])
     assert float(m.exp_avg[:3 * P].view(P, 3)[~vis].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("kind", ["uniform", "clustered", "planar", "duplicates", "tiny"])
+def test_knn_source_matches_bruteforce(emul, kind):
+    from oracle.knn_oracle import mean_dist2_bruteforce
+    emul.emul_knn_scratch_bytes.restype = ctypes.c_size_t
+    emul.emul_knn_scratch_bytes.argtypes = [ctypes.c_int64]
+    emul.emul_knn_mean_dist2.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    r = np.random.default_rng(11)
+    if kind == "uniform":
+        pts = r.uniform(-3, 5, (1500, 3))
+    elif kind == "clustered":           # SfM-like: dense blobs and far outliers
+        pts = np.concatenate([r.normal(c, s, (400, 3)) for c, s in ((0, 0.01), (10, 1.0), (-50, 0.2))] + [r.uniform(-500, 500, (30, 3))])
+    elif kind == "planar":              # zero extent along z: the grid must not degenerate
+        pts = np.concatenate([r.uniform(0, 1, (900, 2)), np.full((900, 1), 0.25)], axis=1)
+    elif kind == "duplicates":
+        base = r.uniform(0, 1, (300, 3))
+        pts = np.concatenate([base, base[:120], base[:40], np.zeros((5, 3))])
+    else:
+        pts = r.uniform(0, 1, (3, 3))
+    pts = np.ascontiguousarray(pts, dtype=np.float32)
+    out = np.full(len(pts), -1.0, dtype=np.float32)
+    scratch = np.zeros(emul.emul_knn_scratch_bytes(len(pts)), dtype=np.uint8)
+    assert emul.emul_knn_mean_dist2(pts.ctypes.data, len(pts), out.ctypes.data, scratch.ctypes.data) == 0
+    ref = mean_dist2_bruteforce(pts)
+    np.testing.assert_allclose(out, ref, rtol=2e-5, atol=1e-12)
+    if kind == "tiny":                  # 3 points: two neighbours each; one point: zero
+        one = np.zeros(1, dtype=np.float32)
+        scratch = np.zeros(emul.emul_knn_scratch_bytes(1), dtype=np.uint8)
+        assert emul.emul_knn_mean_dist2(pts.ctypes.data, 1, one.ctypes.data, scratch.ctypes.data) == 0 and one[0] == 0.0

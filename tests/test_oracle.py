@@ -130,3 +130,16 @@ def test_photometric_loss_matches_reference_python(golden):
     assert abs(float(loss) - float(golden["loss_total"])) < 1e-6
     (g,) = torch.autograd.grad(loss, img)
     assert np.abs(g.numpy() - golden["loss_grad"]).max() < 1e-7
+
+
+def test_knn_oracles_agree():
+    """The two statements of the 3-nearest-neighbour statistic (brute force and k-d tree) agree, including coincident points."""
+    import numpy as np
+    from oracle.knn_oracle import mean_dist2_bruteforce, mean_dist2_kdtree
+    r = np.random.default_rng(2)
+    base = r.uniform(-1, 1, (400, 3))
+    pts = np.concatenate([base, base[:60], base[:10], r.normal(0, 0.001, (50, 3))]).astype(np.float32)
+    np.testing.assert_allclose(mean_dist2_kdtree(pts), mean_dist2_bruteforce(pts), rtol=1e-9, atol=1e-15)
+    assert mean_dist2_bruteforce(pts[:1])[0] == 0.0 and mean_dist2_bruteforce(pts[:0]).shape == (0,)
+    two = mean_dist2_bruteforce(np.array([[0, 0, 0], [3, 4, 0]], dtype=np.float32))
+    assert two.tolist() == [25.0, 25.0]
