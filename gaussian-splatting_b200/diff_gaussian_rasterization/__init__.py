@@ -254,8 +254,10 @@ def densify_apply(args, unit_samples: Optional[torch.Tensor], n_split: int, P_ne
 def knn_mean_dist2(points: torch.Tensor) -> torch.Tensor:
     """Mean squared distance of every point [P,3] to its three nearest other points (gsb_knn_mean_dist2; the replacement of
     simple_knn._C.distCUDA2, scene/gaussian_model.py:159)."""
+    stream = _stream_of(points)
+    if points.numel() == 0:
+        return torch.empty(0, dtype=torch.float32, device=points.device)
     pts = _f32c(points.reshape(-1, 3))
-    stream = _stream_of(pts)
     out = torch.empty(pts.shape[0], dtype=torch.float32, device=pts.device)
     with torch.cuda.device(pts.device):
         arena = _Arena(pts.device, stream)
