@@ -197,8 +197,34 @@ onesweep_hist_kernel(const uint32_t *__restrict__ keys, uint32_t *__restrict__ g
     }
 }
 
+// compile-time knobs of the ranking loop (A/B builds through GSB_LIBRARY; defaults are the measured best)
+#ifndef GSB_OS_GROUP
+#define GSB_OS_GROUP 8      // MATCH.ANY instructions issued back to back before their counter chains
+#endif
+#ifndef GSB_OS_MINB
+#define GSB_OS_MINB 3       // resident CTAs per SM the register allocation must allow
+#endif
+#ifndef GSB_OS_BALLOT
+#define GSB_OS_BALLOT 1     // 1: peers from nine ballots instead of MATCH.ANY (measured 2-12 % faster per pass)
+#endif
+
+__device__ __forceinline__ uint32_t digit_peers(const uint32_t d) {
+#if GSB_OS_BALLOT
+    uint32_t peers = 0xffffffffu;
+#pragma unroll
+    for (int bit = 0; bit <= RADIX_BITS; ++bit) {          // bit RADIX_BITS separates the out-of-range lanes (d == RADIX)
+        const bool one = (d >> bit) & 1u;
+        const uint32_t b = __ballot_sync(0xffffffffu, one);
+        peers &= one ? b : ~b;
+    }
+    return peers;
+#else
+    return __match_any_sync(0xffffffffu, d);
+#endif
+}
+
 template <int SORT_IPT>
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, GSB_OS_MINB)
 onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                      const uint32_t *__restrict__ ghist, volatile uint32_t *status, uint32_t *ticket, int64_t n,
@@ -241,22 +267,37 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
     const int64_t seg = (int64_t)b * SORT_KPB + (int64_t)w * (32 * SORT_IPT);
     uint32_t key[SORT_IPT], rank[SORT_IPT];
     const uint32_t lt_mask = (1u << lane) - 1u;
+    // The rounds are chained through the warp's digit counters, but the MATCH.ANY that finds a round's peers is not: issue
+    // a group of them back to back (ncu: 31 % of this kernel's stall samples sat on the first consumer of MATCH.ANY when
+    // every round waited for its own match) and only then walk the counter chain.
+    constexpr int GROUP = SORT_IPT < GSB_OS_GROUP ? SORT_IPT : GSB_OS_GROUP;
 #pragma unroll
-    for (int r = 0; r < SORT_IPT; ++r) {
-        const int64_t idx = seg + r * 32 + lane;
-        const bool valid = idx < n;
-        key[r] = valid ? keys_in[idx] : 0xffffffffu;
-        const uint32_t d = valid ? ((key[r] >> shift) & mask) : (uint32_t)RADIX;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (lane == leader && valid) {
-            base = warp_cnt[w][d];
-            warp_cnt[w][d] = base + __popc(peers);
+    for (int g0 = 0; g0 < SORT_IPT; g0 += GROUP) {
+        uint32_t peers[GROUP];
+#pragma unroll
+        for (int j = 0; j < GROUP; ++j) {
+            const int r = g0 + j;
+            const int64_t idx = seg + r * 32 + lane;
+            const bool valid = idx < n;
+            key[r] = valid ? keys_in[idx] : 0xffffffffu;
+            const uint32_t d = valid ? ((key[r] >> shift) & mask) : (uint32_t)RADIX;
+            peers[j] = digit_peers(d);
         }
-        base = __shfl_sync(0xffffffffu, base, leader);
-        rank[r] = base + __popc(peers & lt_mask);
-        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < GROUP; ++j) {
+            const int r = g0 + j;
+            const bool valid = seg + r * 32 + lane < n;
+            const uint32_t d = (key[r] >> shift) & mask;
+            const int leader = __ffs(peers[j]) - 1;
+            uint32_t base = 0;
+            if (lane == leader && valid) {
+                base = warp_cnt[w][d];
+                warp_cnt[w][d] = base + __popc(peers[j]);
+            }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            rank[r] = base + __popc(peers[j] & lt_mask);
+            __syncwarp();
+        }
     }
     __syncthreads();
 
