@@ -12,6 +12,12 @@ namespace gsb {
 size_t scan_u32_partials(int64_t n);
 int scan_u32_exclusive(const uint32_t *in, uint32_t *out, size_t n, uint32_t *partials, uint32_t *total, cudaStream_t stream);
 }
+namespace gsb {
+size_t sort_scratch_bytes(int64_t n, int V = 1);
+int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n, const unsigned long long *n_dev,
+               int begin_bit, int end_bit, void *scratch, bool debug, cudaStream_t stream, int V = 1, size_t sv = 0);
+}
+#include "radix_sort_body.inc"
 #include "optim_body.inc"
 #include "densify_body.inc"
 #include "knn_body.inc"
@@ -34,6 +40,14 @@ int emul_densify_plan(int64_t P, int M, int N, const float *params, const float 
 size_t emul_knn_scratch_bytes(int64_t P) { return gsb::knn_scratch_bytes(P); }
 int emul_knn_mean_dist2(const float *points, int64_t P, float *out, void *scratch) {
     return gsb::launch_knn_mean_dist2(points, P, out, scratch, nullptr);
+}
+size_t emul_sort_scratch_bytes(int64_t n, int V) { return gsb::sort_scratch_bytes(n, V); }
+// V independent sorts (view batch) of n pairs each, view v at element offset v * sv; n_dev (optional) = per-view counts
+int emul_sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n, const unsigned long long *n_dev,
+                    int begin_bit, int end_bit, void *scratch, int V, size_t sv, int variant, int force_small) {
+    gsb::g_sort_variant = variant;
+    gsb::g_sort_force_small = force_small;
+    return gsb::sort_pairs(keys, vals, keys_alt, vals_alt, n, n_dev, begin_bit, end_bit, scratch, false, nullptr, V, sv);
 }
 int emul_exclusive_scan(const uint32_t *in, uint32_t *out, size_t n, uint32_t *partials, uint32_t *total) {
     return gsb::exclusive_scan_u32(in, out, n, partials, total, nullptr);

@@ -31,10 +31,10 @@ def emul(tmp_path_factory):
     d = tmp_path_factory.mktemp("emul")
     for f in ("cuda_shim.h", "emul_main.cpp"):
         shutil.copy(os.path.join(ROOT, "tests", "host_emul", f), d / f)
-    for name in ("optim", "densify", "knn"):
+    for name in ("optim", "densify", "knn", "radix_sort"):
         src = open(os.path.join(ROOT, "gaussian-splatting_b200", "csrc", name + ".cu")).read().splitlines()
         body = [l for l in src if l.strip() not in ('#include "common.cuh"', '#include "kernels.cuh"')]
-        assert len(body) == len(src) - 2
+        assert len(src) - 2 <= len(body) < len(src)
         (d / f"{name}_body.inc").write_text("\n".join(body) + "\n")
     subprocess.run([gxx, "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", str(d / "emul_main.cpp"), "-o", str(d / "libemul.so")],
                    check=True)
@@ -210,3 +210,39 @@ def test_knn_source_matches_bruteforce(emul, kind):
         one = np.zeros(1, dtype=np.float32)
         scratch = np.zeros(emul.emul_knn_scratch_bytes(1), dtype=np.uint8)
         assert emul.emul_knn_mean_dist2(pts.ctypes.data, 1, one.ctypes.data, scratch.ctypes.data) == 0 and one[0] == 0.0
+
+
+@pytest.mark.parametrize("n,bits,V,variant,force_small", [
+    (1, 32, 1, 1, 0), (1000, 32, 1, 1, 0), (5000, 13, 1, 1, 0),       # onesweep, 1024-key blocks, multi-block look-back
+    (5000, 13, 3, 1, 0),                                              # view batch: three independent sorts, ragged counts
+    (70000, 13, 1, 1, 0),                                             # 69 blocks: the eight-deep look-back window wraps
+    (5000, 20, 1, 0, 0),                                              # classic histogram / row-scan / scatter path
+    (620000, 13, 1, 1, 0),                                            # 16 keys per thread (large-input instantiation)
+])
+def test_radix_sort_source_is_stable(emul, n, bits, V, variant, force_small):
+    """The hot path's sort (csrc/radix_sort.cu, both variants and both block sizes) on the host: stable order on the sorted
+    bits, values carried, untouched tails when the per-view count is below the launch size."""
+    u64, vp, i64, i32 = ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    emul.emul_sort_scratch_bytes.restype = ctypes.c_size_t
+    emul.emul_sort_scratch_bytes.argtypes = [i64, i32]
+    emul.emul_sort_pairs.argtypes = [vp, vp, vp, vp, i64, vp, i32, i32, vp, i32, ctypes.c_size_t, i32, i32]
+    r = np.random.default_rng(n + bits)
+    sv = n + 37                                                       # stride between the views' arrays
+    keys = r.integers(0, 2 ** 32, V * sv, dtype=np.uint64).astype(np.uint32)
+    if bits < 32:
+        keys &= np.uint32((1 << bits) - 1) | np.uint32(0xF0000000)    # high garbage bits must be ignored
+    vals = np.arange(V * sv, dtype=np.uint32)
+    counts = np.array([n if v == 0 else max(1, n - 11 * v) for v in range(V)], dtype=np.uint64)
+    k, v_ = keys.copy(), vals.copy()
+    ka, va = np.zeros_like(k), np.zeros_like(v_)
+    scratch = np.zeros(emul.emul_sort_scratch_bytes(n, V), dtype=np.uint8)
+    rc = emul.emul_sort_pairs(k.ctypes.data, v_.ctypes.data, ka.ctypes.data, va.ctypes.data, n, counts.ctypes.data if V > 1 else None,
+                              0, bits, scratch.ctypes.data, V, sv, variant, force_small)
+    assert rc == 0
+    mask = np.uint32((1 << bits) - 1) if bits < 32 else np.uint32(0xFFFFFFFF)
+    for view in range(V):
+        cnt = int(counts[view]) if V > 1 else n
+        seg = slice(view * sv, view * sv + cnt)
+        order = np.argsort(keys[seg] & mask, kind="stable")
+        assert np.array_equal(k[seg], keys[seg][order]), view
+        assert np.array_equal(v_[seg], vals[seg][order]), view
