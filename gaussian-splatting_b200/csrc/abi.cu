@@ -169,6 +169,7 @@ int32_t gsb_set_option(const char *name, int32_t value) {
     if (!strcmp(name, "time_kernels")) { g_time_kernels = value; return 0; }
     if (!strcmp(name, "sort_variant")) { g_sort_variant = value; return 0; }
     if (!strcmp(name, "sort_small")) { g_sort_force_small = value; return 0; }
+    if (!strcmp(name, "sort_big_ipt")) { if (value != 8 && value != 16) return 1; g_sort_big_ipt = value; return 0; }
     if (!strcmp(name, "render_fwd_variant")) { opt_fwd_variant = value; return 0; }
     if (!strcmp(name, "render_bwd_variant")) { opt_bwd_variant = value; return 0; }
     return 1;

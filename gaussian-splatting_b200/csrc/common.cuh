@@ -103,5 +103,6 @@ int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *val
                cudaStream_t stream, int V = 1, size_t sv = 0);
 extern int g_sort_variant;
 extern int g_sort_force_small;
+extern int g_sort_big_ipt;
 
 }  // namespace gsb

@@ -24,7 +24,16 @@ constexpr int SORT_IPT_BIG = 16;
 constexpr int SORT_IPT_SMALL = 4;
 constexpr int64_t SORT_SMALL_LIMIT = 148 * 4 * 1024;   // below ~0.6 M keys: 1024-key blocks to fill the SMs
 int g_sort_force_small = 0;   // option "sort_small": 1 = 4 keys per thread for every size (A/B)
-static inline int sort_ipt(int64_t n) { return (g_sort_force_small || n < SORT_SMALL_LIMIT) ? SORT_IPT_SMALL : SORT_IPT_BIG; }
+int g_sort_big_ipt = SORT_IPT_BIG;   // option "sort_big_ipt": 8 or 16 keys per thread for large inputs (A/B: 8 halves the block's
+                                     // shared memory and registers -> more resident CTAs to hide the ranking / look-back latency)
+static inline int sort_ipt(int64_t n) { return (g_sort_force_small || n < SORT_SMALL_LIMIT) ? SORT_IPT_SMALL : g_sort_big_ipt; }
+// runs CALL with the compile-time constant I = keys per thread
+#define SORT_WITH_IPT(ipt, CALL)                                       \
+    switch (ipt) {                                                     \
+        case SORT_IPT_SMALL: { constexpr int I = SORT_IPT_SMALL; CALL; } break; \
+        case 8: { constexpr int I = 8; CALL; } break;                  \
+        default: { constexpr int I = SORT_IPT_BIG; CALL; } break;      \
+    }
 
 template <int SORT_IPT>
 __global__ void __launch_bounds__(SORT_THREADS)
@@ -224,7 +233,7 @@ __device__ __forceinline__ uint32_t digit_peers(const uint32_t d) {
 }
 
 template <int SORT_IPT>
-__global__ void __launch_bounds__(SORT_THREADS, GSB_OS_MINB)
+__global__ void __launch_bounds__(SORT_THREADS, SORT_IPT >= 16 ? GSB_OS_MINB : 4)
 onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                      const uint32_t *__restrict__ ghist, volatile uint32_t *status, uint32_t *ticket, int64_t n,
@@ -404,8 +413,8 @@ static int onesweep_sort(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uin
         ps.mask[ps.npass] = (1u << bits) - 1u;
         ++ps.npass;
     }
-    const bool small = sort_ipt(n) == SORT_IPT_SMALL;
-    const int nblocks = (int)ceil_div(n, SORT_THREADS * sort_ipt(n));
+    const int ipt = sort_ipt(n);
+    const int nblocks = (int)ceil_div(n, SORT_THREADS * ipt);
     // layout: ghist[16 views][4][256] | ticket[16][4] (256 B) | status[V][npass][nblocks][256]
     uint32_t *ghist = static_cast<uint32_t *>(scratch);
     uint32_t *ticket = ghist + GSB_SORT_MAX_VIEWS * OS_MAX_PASSES * RADIX;
@@ -418,13 +427,8 @@ static int onesweep_sort(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uin
     uint32_t *kin = keys, *vin = vals, *kout = keys_alt, *vout = vals_alt;
     for (int p = 0; p < ps.npass; ++p) {
         uint32_t *st = status + (size_t)p * nblocks * RADIX;
-        if (small) {
-            GSB_LAUNCH("sort_scatter", debug, stream, onesweep_pass_kernel<SORT_IPT_SMALL>, dim3(nblocks, V), SORT_THREADS, 0, kin,
-                       vin, kout, vout, ghist + p * RADIX, st, ticket + p, n, n_dev, ps.shift[p], ps.mask[p], sv, sv_status);
-        } else {
-            GSB_LAUNCH("sort_scatter", debug, stream, onesweep_pass_kernel<SORT_IPT_BIG>, dim3(nblocks, V), SORT_THREADS, 0, kin,
-                       vin, kout, vout, ghist + p * RADIX, st, ticket + p, n, n_dev, ps.shift[p], ps.mask[p], sv, sv_status);
-        }
+        SORT_WITH_IPT(ipt, GSB_LAUNCH("sort_scatter", debug, stream, onesweep_pass_kernel<I>, dim3(nblocks, V), SORT_THREADS, 0, kin, vin,
+                                 kout, vout, ghist + p * RADIX, st, ticket + p, n, n_dev, ps.shift[p], ps.mask[p], sv, sv_status));
         uint32_t *t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
     }
@@ -455,8 +459,8 @@ int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *val
     if ((g_sort_variant == 1 || V > 1) && (end_bit - begin_bit) <= OS_MAX_PASSES * RADIX_BITS)
         return onesweep_sort(keys, vals, keys_alt, vals_alt, n, n_dev, begin_bit, end_bit, scratch, debug, stream, V, sv);
     if (V > 1) { set_error("sort_pairs: the view-batch sort needs the onesweep path"); return GSB_ERR_ARGUMENT; }
-    const bool small = sort_ipt(n) == SORT_IPT_SMALL;
-    const int nblocks = (int)ceil_div(n, SORT_THREADS * sort_ipt(n));
+    const int ipt = sort_ipt(n);
+    const int nblocks = (int)ceil_div(n, SORT_THREADS * ipt);
     uint32_t *table = static_cast<uint32_t *>(scratch);
     uint32_t *totals = reinterpret_cast<uint32_t *>(static_cast<char *>(scratch) +
                                                     align_up((size_t)RADIX * nblocks * sizeof(uint32_t), 256));
@@ -465,21 +469,11 @@ int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *val
     for (int bit = begin_bit; bit < end_bit; bit += RADIX_BITS) {
         const int bits = (end_bit - bit) < RADIX_BITS ? (end_bit - bit) : RADIX_BITS;
         const uint32_t mask = (1u << bits) - 1u;
-        if (small) {
-            GSB_LAUNCH("sort_hist", debug, stream, sort_hist_kernel<SORT_IPT_SMALL>, nblocks, SORT_THREADS, 0, kin, table, n,
-                       n_dev, nblocks, bit, mask);
-        } else {
-            GSB_LAUNCH("sort_hist", debug, stream, sort_hist_kernel<SORT_IPT_BIG>, nblocks, SORT_THREADS, 0, kin, table, n,
-                       n_dev, nblocks, bit, mask);
-        }
+        SORT_WITH_IPT(ipt, GSB_LAUNCH("sort_hist", debug, stream, sort_hist_kernel<I>, nblocks, SORT_THREADS, 0, kin, table, n, n_dev,
+                                 nblocks, bit, mask));
         GSB_LAUNCH("sort_rowscan", debug, stream, sort_rowscan_kernel, RADIX, 256, 0, table, totals, nblocks);
-        if (small) {
-            GSB_LAUNCH("sort_scatter", debug, stream, sort_scatter_kernel<SORT_IPT_SMALL>, nblocks, SORT_THREADS, 0, kin, vin,
-                       kout, vout, table, totals, n, n_dev, nblocks, bit, mask);
-        } else {
-            GSB_LAUNCH("sort_scatter", debug, stream, sort_scatter_kernel<SORT_IPT_BIG>, nblocks, SORT_THREADS, 0, kin, vin,
-                       kout, vout, table, totals, n, n_dev, nblocks, bit, mask);
-        }
+        SORT_WITH_IPT(ipt, GSB_LAUNCH("sort_scatter", debug, stream, sort_scatter_kernel<I>, nblocks, SORT_THREADS, 0, kin, vin, kout, vout,
+                                 table, totals, n, n_dev, nblocks, bit, mask));
         uint32_t *t = kin; kin = kout; kout = t;
         t = vin; vin = vout; vout = t;
         ++passes;

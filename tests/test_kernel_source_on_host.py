@@ -212,20 +212,21 @@ def test_knn_source_matches_bruteforce(emul, kind):
         assert emul.emul_knn_mean_dist2(pts.ctypes.data, 1, one.ctypes.data, scratch.ctypes.data) == 0 and one[0] == 0.0
 
 
-@pytest.mark.parametrize("n,bits,V,variant,force_small", [
-    (1, 32, 1, 1, 0), (1000, 32, 1, 1, 0), (5000, 13, 1, 1, 0),       # onesweep, 1024-key blocks, multi-block look-back
-    (5000, 13, 3, 1, 0),                                              # view batch: three independent sorts, ragged counts
-    (70000, 13, 1, 1, 0),                                             # 69 blocks: the eight-deep look-back window wraps
-    (5000, 20, 1, 0, 0),                                              # classic histogram / row-scan / scatter path
-    (620000, 13, 1, 1, 0),                                            # 16 keys per thread (large-input instantiation)
+@pytest.mark.parametrize("n,bits,V,variant,big_ipt", [
+    (1, 32, 1, 1, 16), (1000, 32, 1, 1, 16), (5000, 13, 1, 1, 16),    # onesweep, 1024-key blocks, multi-block look-back
+    (5000, 13, 3, 1, 16),                                             # view batch: three independent sorts, ragged counts
+    (70000, 13, 1, 1, 16),                                            # 69 blocks: the eight-deep look-back window wraps
+    (5000, 20, 1, 0, 16),                                             # classic histogram / row-scan / scatter path
+    (620000, 13, 1, 1, 16),                                           # 16 keys per thread (large-input instantiation)
+    (610000, 8, 1, 1, 8),                                             # option sort_big_ipt = 8
 ])
-def test_radix_sort_source_is_stable(emul, n, bits, V, variant, force_small):
+def test_radix_sort_source_is_stable(emul, n, bits, V, variant, big_ipt):
     """The hot path's sort (csrc/radix_sort.cu, both variants and both block sizes) on the host: stable order on the sorted
     bits, values carried, untouched tails when the per-view count is below the launch size."""
     u64, vp, i64, i32 = ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
     emul.emul_sort_scratch_bytes.restype = ctypes.c_size_t
     emul.emul_sort_scratch_bytes.argtypes = [i64, i32]
-    emul.emul_sort_pairs.argtypes = [vp, vp, vp, vp, i64, vp, i32, i32, vp, i32, ctypes.c_size_t, i32, i32]
+    emul.emul_sort_pairs.argtypes = [vp, vp, vp, vp, i64, vp, i32, i32, vp, i32, ctypes.c_size_t, i32, i32, i32]
     r = np.random.default_rng(n + bits)
     sv = n + 37                                                       # stride between the views' arrays
     keys = r.integers(0, 2 ** 32, V * sv, dtype=np.uint64).astype(np.uint32)
@@ -237,7 +238,7 @@ def test_radix_sort_source_is_stable(emul, n, bits, V, variant, force_small):
     ka, va = np.zeros_like(k), np.zeros_like(v_)
     scratch = np.zeros(emul.emul_sort_scratch_bytes(n, V), dtype=np.uint8)
     rc = emul.emul_sort_pairs(k.ctypes.data, v_.ctypes.data, ka.ctypes.data, va.ctypes.data, n, counts.ctypes.data if V > 1 else None,
-                              0, bits, scratch.ctypes.data, V, sv, variant, force_small)
+                              0, bits, scratch.ctypes.data, V, sv, variant, 0, big_ipt)
     assert rc == 0
     mask = np.uint32((1 << bits) - 1) if bits < 32 else np.uint32(0xFFFFFFFF)
     for view in range(V):
