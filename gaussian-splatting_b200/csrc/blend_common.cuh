@@ -8,6 +8,10 @@ namespace gsb {
 constexpr int MP_R = 128;           // gaussians staged per round (256 measured 2 % slower)
 constexpr float LOG2E = 1.4426950408889634f;
 
+#ifdef GSB_HOST_EMUL     // tests/host_emul: the approximate instructions become their libm counterparts
+inline float ex2_approx(const float x) { return exp2f(x); }
+inline float rcp_approx(const float x) { return 1.0f / x; }
+#else
 __device__ __forceinline__ float ex2_approx(const float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -20,6 +24,7 @@ __device__ __forceinline__ float rcp_approx(const float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+#endif
 
 // staged record: q0 = {x, y, A', B'}, q1 = {C', opacity, r, g} with A' = -0.5 log2e A, B' = -log2e B, C' = -0.5 log2e C
 __device__ __forceinline__ void stage_scale(float4 &q0, float4 &q1) {
@@ -65,15 +70,26 @@ __device__ __forceinline__ float reduce2_transposed(const float v0, const float 
 // tools/micro/ffma2_bench.cu: FFMA2 runs at half the FFMA issue rate (same FLOP/s), so it frees issue slots for
 // the ALU / MUFU / shuffle work around it -- what the issue-bound blend kernels need.
 typedef unsigned long long f32x2;
+#ifdef GSB_HOST_EMUL
+inline f32x2 pk(const float lo, const float hi) { f32x2 r; float t[2] = {lo, hi}; memcpy(&r, t, 8); return r; }
+inline void unpk(const f32x2 v, float &lo, float &hi) { float t[2]; memcpy(t, &v, 8); lo = t[0]; hi = t[1]; }
+#define GSB_F32X2_OP(name, expr_lo, expr_hi) \
+    { float al, ah, bl, bh, cl = 0.f, ch = 0.f; unpk(a, al, ah); unpk(b, bl, bh); (void)cl; (void)ch; return pk(expr_lo, expr_hi); }
+inline f32x2 fma2(const f32x2 a, const f32x2 b, const f32x2 c) { float al, ah, bl, bh, cl, ch; unpk(a, al, ah); unpk(b, bl, bh); unpk(c, cl, ch); return pk(fmaf(al, bl, cl), fmaf(ah, bh, ch)); }
+inline f32x2 mul2(const f32x2 a, const f32x2 b) GSB_F32X2_OP(mul2, al * bl, ah * bh)
+inline f32x2 add2(const f32x2 a, const f32x2 b) GSB_F32X2_OP(add2, al + bl, ah + bh)
+inline f32x2 sub2(const f32x2 a, const f32x2 b) GSB_F32X2_OP(sub2, al - bl, ah - bh)
+#else
 __device__ __forceinline__ f32x2 pk(const float lo, const float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ f32x2 pk1(const float v) { return pk(v, v); }
 __device__ __forceinline__ void unpk(const f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ float lo_of(const f32x2 v) { float a, b; unpk(v, a, b); return a; }
-__device__ __forceinline__ float hi_of(const f32x2 v) { float a, b; unpk(v, a, b); return b; }
 __device__ __forceinline__ f32x2 fma2(const f32x2 a, const f32x2 b, const f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ f32x2 mul2(const f32x2 a, const f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 add2(const f32x2 a, const f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 sub2(const f32x2 a, const f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+#endif
+__device__ __forceinline__ f32x2 pk1(const float v) { return pk(v, v); }
+__device__ __forceinline__ float lo_of(const f32x2 v) { float a, b; unpk(v, a, b); return a; }
+__device__ __forceinline__ float hi_of(const f32x2 v) { float a, b; unpk(v, a, b); return b; }
 __device__ __forceinline__ float hsum(const f32x2 v) { float a, b; unpk(v, a, b); return a + b; }
 
 }  // namespace gsb

@@ -1,6 +1,10 @@
 // common.cuh -- shared definitions for the sm_100a rasterizer kernels.
 #pragma once
+#ifdef GSB_HOST_EMUL        // tests/host_emul: these sources compiled for the CPU by the test-suite (never a product build)
+#include "cuda_shim.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 
@@ -39,9 +43,15 @@ constexpr int SPLAT_F4 = 3;
 // The culling tests are conservative by construction (padded limits and spans), so <= 2 ulp approximations are
 // fine there, and as inline PTX they are evaluated identically wherever they appear (the counting and the emitting
 // pass must agree bit for bit).  Projection / covariance / blending arithmetic never uses these.
+#ifdef GSB_HOST_EMUL
+inline float sqrt_apx(const float x) { return sqrtf(x); }
+inline float div_apx(const float a, const float b) { return a / b; }
+inline float rcp_apx(const float x) { return 1.0f / x; }
+#else
 __device__ __forceinline__ float sqrt_apx(const float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float div_apx(const float a, const float b) { float y; asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(y) : "f"(a), "f"(b)); return y; }
 __device__ __forceinline__ float rcp_apx(const float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
 
 // ---- host-side plumbing -------------------------------------------------------------------
 void set_error(const char *fmt, ...);
@@ -54,10 +64,20 @@ extern int g_time_kernels;
 void *timer_begin(const char *name, cudaStream_t stream);
 void timer_end(void *token, cudaStream_t stream);
 
+// the launch itself; dynamic shared memory is declared through GSB_DYNAMIC_SMEM so that both spellings stay in one place
+#ifdef GSB_HOST_EMUL
+#define GSB_KERNEL_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    gsb_emul_launch(dim3(grid), dim3(block), (size_t)(smem), [&] { kernel(__VA_ARGS__); })
+#define GSB_DYNAMIC_SMEM(type, name) type *name = reinterpret_cast<type *>(gsb_emul_dynamic_smem())
+#else
+#define GSB_KERNEL_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define GSB_DYNAMIC_SMEM(type, name) extern __shared__ type name[]
+#endif
+
 #define GSB_LAUNCH(name, debug, stream, kernel, grid, block, smem, ...)                         \
     do {                                                                                        \
         void *_tok = gsb::g_time_kernels ? gsb::timer_begin(name, (stream)) : nullptr;          \
-        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                             \
+        GSB_KERNEL_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__);                      \
         if (_tok) gsb::timer_end(_tok, (stream));                                               \
         ++gsb::g_launch_count;                                                                  \
         int _e = gsb::check_launch(name, (debug), (stream));                                    \

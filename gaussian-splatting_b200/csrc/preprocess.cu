@@ -176,7 +176,7 @@ __device__ __forceinline__ void preprocess_fwd_body(const CamParams &cam, const 
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_fwd_kernel(const CamArgs ca, const PreFwdArgs a) {
     __shared__ CamParams cam;
-    extern __shared__ float sh_rows[];
+    GSB_DYNAMIC_SMEM(float, sh_rows);
     load_cam(ca, cam);
     const int row0 = blockIdx.x * PRE_THREADS;
     const int nrows = min(PRE_THREADS, a.P - row0);
@@ -193,7 +193,7 @@ preprocess_fwd_kernel(const CamArgs ca, const PreFwdArgs a) {
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_fwd_batch_kernel(const CamArgsBatch cb, const PreFwdArgs a, const PreFwdBatchStrides st) {
     __shared__ CamParams cams[GSB_MAX_VIEWS];
-    extern __shared__ float sh_rows[];
+    GSB_DYNAMIC_SMEM(float, sh_rows);
     for (int v = 0; v < cb.V; ++v) load_cam(cb.cam[v], cams[v]);
     const int row0 = blockIdx.x * PRE_THREADS;
     const int nrows = min(PRE_THREADS, a.P - row0);
@@ -460,7 +460,7 @@ template <bool ACC>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_bwd_kernel(const CamArgs ca, const PreBwdArgs a) {
     __shared__ CamParams cam;
-    extern __shared__ float sh_rows[];
+    GSB_DYNAMIC_SMEM(float, sh_rows);
     load_cam(ca, cam);
     const int row0 = blockIdx.x * PRE_THREADS;
     const int nrows = min(PRE_THREADS, a.P - row0);
@@ -505,7 +505,7 @@ template <bool ACC>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_bwd_batch_kernel(const CamArgsBatch cb, const PreBwdArgs a, const PreBwdBatchStrides st) {
     __shared__ CamParams cams[GSB_MAX_VIEWS];
-    extern __shared__ float sh_rows[];
+    GSB_DYNAMIC_SMEM(float, sh_rows);
     for (int v = 0; v < cb.V; ++v) load_cam(cb.cam[v], cams[v]);
     const int row0 = blockIdx.x * PRE_THREADS;
     const int nrows = min(PRE_THREADS, a.P - row0);

@@ -23,10 +23,13 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_IPT_BIG = 16;
 constexpr int SORT_IPT_SMALL = 4;
 constexpr int64_t SORT_SMALL_LIMIT = 148 * 4 * 1024;   // below ~0.6 M keys: 1024-key blocks to fill the SMs
-int g_sort_force_small = 0;   // option "sort_small": 1 = 4 keys per thread for every size (A/B)
+int g_sort_force_small = 0;   // option "sort_small": 1 = 4 keys per thread for every size, -1 = never (A/B, tests)
 int g_sort_big_ipt = SORT_IPT_BIG;   // option "sort_big_ipt": 8 or 16 keys per thread for large inputs (A/B: 8 halves the block's
                                      // shared memory and registers -> more resident CTAs to hide the ranking / look-back latency)
-static inline int sort_ipt(int64_t n) { return (g_sort_force_small || n < SORT_SMALL_LIMIT) ? SORT_IPT_SMALL : g_sort_big_ipt; }
+static inline int sort_ipt(int64_t n) {
+    if (g_sort_force_small < 0) return g_sort_big_ipt;
+    return (g_sort_force_small || n < SORT_SMALL_LIMIT) ? SORT_IPT_SMALL : g_sort_big_ipt;
+}
 // runs CALL with the compile-time constant I = keys per thread
 #define SORT_WITH_IPT(ipt, CALL)                                       \
     switch (ipt) {                                                     \

@@ -69,7 +69,9 @@ class _DensifyArgs(Structure):       # GsbDensifyArgs
                 ("size_limit", c_float), ("min_opacity", c_float), ("world_limit", c_float), ("scratch", c_void_p)]
 
 
-def _load():
+def _load(path: Optional[str] = None):
+    """Loads libgs_b200.so (or another build of the same C ABI at ``path``) and declares the prototypes."""
+    _LIB_PATH = path or globals()["_LIB_PATH"]
     if not os.path.exists(_LIB_PATH):
         raise ImportError(
             f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -164,14 +166,15 @@ def state_views(pack: dict, height: int, width: int):
 def l1_loss_and_grad(image: torch.Tensor, target: torch.Tensor, loss_accum: Optional[torch.Tensor] = None):
     """mean |clamp(image,0,1) - target| and its gradient w.r.t. `image`, in one kernel.  Returns (loss, grad);
     `loss` is `loss_accum` (a 1-element float32 tensor that is ADDED to) or a fresh scalar tensor."""
+    _require_cuda(image)
     img, gt = _f32c(image), _f32c(target)
     n = img.numel()
     grad = torch.empty_like(img)
     if loss_accum is None:
         loss_accum = torch.zeros(1, dtype=torch.float32, device=img.device)
-    with torch.cuda.device(img.device):
+    with _device_ctx(img.device):
         rc = _C.gsb_l1_loss_grad(img.data_ptr(), gt.data_ptr(), n, 1.0 / n, grad.data_ptr(), loss_accum.data_ptr(),
-                                 torch.cuda.current_stream(img.device).cuda_stream)
+                                 _current_stream(img.device))
     _check(rc)
     return loss_accum, grad
 
@@ -180,12 +183,13 @@ def photometric_loss_and_grad(image: torch.Tensor, target: torch.Tensor, lambda_
     """The reference training step's loss (train.py:120-126) fused with its gradient:
     ``(1 - lambda) * mean|x - y| + lambda * (1 - SSIM(x, y))`` with ``x = clamp(image, 0, 1)``; image / target [C,H,W].
     Returns (loss[1], dloss/dimage, parts) with parts = tensor [loss, mean L1, mean SSIM] (device, no sync)."""
+    _require_cuda(image)
     img, gt = _f32c(image), _f32c(target)
     C, H, W = (int(v) for v in img.shape[-3:])
     grad = torch.empty_like(img)
     acc = torch.tensor([float(lambda_dssim), 0.0, 0.0], dtype=torch.float32).to(img.device, non_blocking=True)
-    with torch.cuda.device(img.device):
-        stream = torch.cuda.current_stream(img.device).cuda_stream
+    with _device_ctx(img.device):
+        stream = _current_stream(img.device)
         arena = _Arena(img.device, stream)
         rc = _C.gsb_photometric_loss_grad(img.data_ptr(), gt.data_ptr(), C, H, W, float(lambda_dssim), grad.data_ptr(),
                                           acc.data_ptr(), arena.cb, None, stream)
@@ -195,10 +199,25 @@ def photometric_loss_and_grad(image: torch.Tensor, target: torch.Tensor, lambda_
     return acc[:1], grad, parts
 
 
-def _stream_of(t: torch.Tensor):
+# The three places where this layer touches the CUDA runtime.  The library has no CPU path: CPU tensors are refused here.
+# (tests/host_emul swaps these three together with _C to drive a host build of the kernel SOURCES in the CPU test-suite.)
+def _require_cuda(t: torch.Tensor) -> None:
     if not t.is_cuda:
-        raise RuntimeError("libgs_b200 kernels need CUDA tensors (there is no CPU fallback)")
-    return torch.cuda.current_stream(t.device).cuda_stream
+        raise RuntimeError("diff_gaussian_rasterization (B200): tensors must live on a CUDA device; there is no CPU path "
+                           "(no CPU fallback)")
+
+
+def _current_stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _device_ctx(device):
+    return torch.cuda.device(device)
+
+
+def _stream_of(t: torch.Tensor):
+    _require_cuda(t)
+    return _current_stream(t.device)
 
 
 def adam_step(params, grads, exp_avg, exp_avg_sq, act, P: int, sh_coeffs: int, step_size, beta1: float, beta2: float,
@@ -214,13 +233,13 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, act, P: int, sh_coeffs: int, s
     a.step_size = (c_float * 6)(*[float(v) for v in step_size])
     a.beta1, a.beta2, a.eps, a.bias2_sqrt = float(beta1), float(beta2), float(eps), float(bias2_sqrt)
     stream = _stream_of(params)
-    with torch.cuda.device(params.device):
+    with _device_ctx(params.device):
         _check(_C.gsb_adam_step(byref(a), stream))
 
 
 def activate(params: torch.Tensor, act: torch.Tensor, P: int, sh_coeffs: int) -> None:
     stream = _stream_of(params)
-    with torch.cuda.device(params.device):
+    with _device_ctx(params.device):
         _check(_C.gsb_activate(int(P), int(sh_coeffs), params.data_ptr(), act.data_ptr(), stream))
 
 
@@ -238,7 +257,7 @@ def densify_plan(params, exp_avg, exp_avg_sq, grad_accum, denom, P: int, sh_coef
     scratch = torch.empty(max(int(_C.gsb_densify_scratch_bytes(int(P), int(n_children))), 1), dtype=torch.uint8, device=params.device)
     a.scratch = scratch.data_ptr()
     counts = (c_int64 * 4)()
-    with torch.cuda.device(params.device):
+    with _device_ctx(params.device):
         _check(_C.gsb_densify_plan(byref(a), byref(counts), stream))
     return a, (scratch, ga, dn), tuple(int(v) for v in counts)
 
@@ -246,7 +265,7 @@ def densify_plan(params, exp_avg, exp_avg_sq, grad_accum, denom, P: int, sh_coef
 def densify_apply(args, unit_samples: Optional[torch.Tensor], n_split: int, P_new: int, new_params, new_exp_avg, new_exp_avg_sq) -> None:
     us = _f32c(unit_samples) if unit_samples is not None and unit_samples.numel() else None
     stream = _stream_of(new_params)
-    with torch.cuda.device(new_params.device):
+    with _device_ctx(new_params.device):
         _check(_C.gsb_densify_apply(byref(args), _ptr(us), int(n_split), int(P_new), new_params.data_ptr(), new_exp_avg.data_ptr(),
                                     new_exp_avg_sq.data_ptr(), stream))
 
@@ -259,7 +278,7 @@ def knn_mean_dist2(points: torch.Tensor) -> torch.Tensor:
         return torch.empty(0, dtype=torch.float32, device=points.device)
     pts = _f32c(points.reshape(-1, 3))
     out = torch.empty(pts.shape[0], dtype=torch.float32, device=pts.device)
-    with torch.cuda.device(pts.device):
+    with _device_ctx(pts.device):
         arena = _Arena(pts.device, stream)
         rc = _C.gsb_knn_mean_dist2(pts.data_ptr(), int(pts.shape[0]), out.data_ptr(), arena.cb, None, stream)
     _check(rc, arena)
@@ -377,20 +396,19 @@ speculative_binning = True
 
 def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs):
     """Returns (color, radii, invdepth, ctx_pack).  All tensor arguments already float32-contiguous or None."""
-    if not means3D.is_cuda:
-        raise RuntimeError("diff_gaussian_rasterization (B200): tensors must live on a CUDA device; there is no CPU path")
+    _require_cuda(means3D)
     dev = means3D.device
     P = int(means3D.shape[0])
     H, W = int(rs.image_height), int(rs.image_width)
     M = int(sh.shape[1]) if sh is not None else 0
-    with torch.cuda.device(dev):
+    with _device_ctx(dev):
         keep = []
         cs = _c_settings(rs, M, keep)
         ci = _c_inputs(P, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         invdepth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _current_stream(dev)
         arena = _Arena(dev, stream)
         st = _State()
         hkey = (P, H, W, dev.index)
@@ -416,7 +434,7 @@ def _backward_impl(pack, rs, means3D, sh, colors_precomp, opacities, scales, rot
         grads["means2D"].zero_()
     dev = means3D.device
     P = int(means3D.shape[0])
-    with torch.cuda.device(dev):
+    with _device_ctx(dev):
         keep = []
         cs = _c_settings(rs, pack["sh_coeffs"], keep)
         ci = _c_inputs(P, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
@@ -426,7 +444,7 @@ def _backward_impl(pack, rs, means3D, sh, colors_precomp, opacities, scales, rot
         g.dL_dopacities = _ptr(grads.get("opacities"))
         g.dL_dscales, g.dL_drotations = _ptr(grads.get("scales")), _ptr(grads.get("rotations"))
         g.dL_dcov3D = _ptr(grads.get("cov3D_precomp"))
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _current_stream(dev)
         arena = _Arena(dev, stream)
         rc = _C.gsb_backward(byref(cs), byref(ci), byref(pack["state"]), out_color.data_ptr(), out_invdepth.data_ptr(),
                              grad_color.data_ptr(), _ptr(grad_invdepth), byref(g), int(bool(accumulate)), arena.cb,
@@ -439,20 +457,19 @@ MAX_BATCH_VIEWS = 16
 
 def _forward_batch_impl(means3D, sh, opacities, scales, rotations, settings_list):
     """View-batch forward (gsb_forward_batch): returns (color[V,3,H,W], radii[V,P], invdepth[V,1,H,W], pack)."""
-    if not means3D.is_cuda:
-        raise RuntimeError("diff_gaussian_rasterization (B200): tensors must live on a CUDA device; there is no CPU path")
+    _require_cuda(means3D)
     dev = means3D.device
     V, P = len(settings_list), int(means3D.shape[0])
     H, W = int(settings_list[0].image_height), int(settings_list[0].image_width)
     M = int(sh.shape[1])
-    with torch.cuda.device(dev):
+    with _device_ctx(dev):
         keep = []
         cs = (_Settings * V)(*[_c_settings(rs, M, keep) for rs in settings_list])
         ci = _c_inputs(P, means3D, sh, None, opacities, scales, rotations, None)
         color = torch.empty((V, 3, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((V, P), dtype=torch.int32, device=dev)
         invdepth = torch.empty((V, 1, H, W), dtype=torch.float32, device=dev)
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _current_stream(dev)
         arena = _Arena(dev, stream)
         states = (_State * V)()
         hkey = (P, H, W, dev.index, "batch")
@@ -475,7 +492,7 @@ def _backward_batch_impl(pack, settings_list, means3D, sh, opacities, scales, ro
     (means2D, if present, is [V,P,3] and per view)."""
     dev = means3D.device
     V, P = pack["V"], int(means3D.shape[0])
-    with torch.cuda.device(dev):
+    with _device_ctx(dev):
         keep = []
         cs = (_Settings * V)(*[_c_settings(rs, pack["sh_coeffs"], keep) for rs in settings_list])
         ci = _c_inputs(P, means3D, sh, None, opacities, scales, rotations, None)
@@ -483,7 +500,7 @@ def _backward_batch_impl(pack, settings_list, means3D, sh, opacities, scales, ro
         g.dL_dmeans3D, g.dL_dmeans2D = _ptr(grads.get("means3D")), _ptr(grads.get("means2D"))
         g.dL_dshs, g.dL_dopacities = _ptr(grads.get("shs")), _ptr(grads.get("opacities"))
         g.dL_dscales, g.dL_drotations = _ptr(grads.get("scales")), _ptr(grads.get("rotations"))
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _current_stream(dev)
         arena = _Arena(dev, stream)
         rc = _C.gsb_backward_batch(V, cs, byref(ci), pack["states"], out_color.data_ptr(), out_invdepth.data_ptr(),
                                    grad_color.data_ptr(), _ptr(grad_invdepth), byref(g), int(bool(accumulate)), arena.cb, None,
@@ -576,9 +593,9 @@ class GaussianRasterizer(nn.Module):
             present = torch.zeros((P,), dtype=torch.uint8, device=positions.device)
             if P > 0:
                 view, proj = _f32c(rs.viewmatrix), _f32c(rs.projmatrix)
-                with torch.cuda.device(positions.device):
+                with _device_ctx(positions.device):
                     rc = _C.gsb_mark_visible(P, pos.data_ptr(), view.data_ptr(), proj.data_ptr(), present.data_ptr(),
-                                             torch.cuda.current_stream(positions.device).cuda_stream)
+                                             _current_stream(positions.device))
                 _check(rc)
             return present.bool()
 

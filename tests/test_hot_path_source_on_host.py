@@ -1,0 +1,133 @@
+"""The hot path's kernel SOURCE (preprocess, depth sort, scan, emit, tile sort, tile ranges, forward blend, backward blend,
+chain rule -- the same .cu files that are compiled for sm_100a) executed on the CPU through tests/host_emul and compared
+with the oracle exactly like the -m gpu parity tests, at sizes the emulation finishes in seconds.  Same tolerances:
+forward 1e-5 abs, gradients 1e-4 rel.  Differences to a GPU run: ex2.approx / rcp.approx / sqrt.approx are their libm
+counterparts here, and float atomics arrive in another order.  Not a product path (see tests/host_emul/cuda_shim.h)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import gs_test_util as U
+from oracle import torch_oracle as TO
+
+
+def _weights(cam, seed=5):
+    gen = torch.Generator().manual_seed(seed)
+    H, W = cam.image_height, cam.image_width
+    return torch.randn(3, H, W, generator=gen).numpy(), torch.randn(1, H, W, generator=gen).numpy()
+
+
+def _check(scene, cam, mode, with_depth_grad=True):
+    args = U.make_args(scene, mode)
+    wc, wd = _weights(cam)
+    if not with_depth_grad:
+        wd = None
+    got = U.run_cuda(args, cam, wc, wd, device="cpu")
+    ref = U.run_oracle(args, cam, wc, wd)
+    assert (got["radii"] == ref["radii"]).all(), "radii differ"
+    mx, frac = U.assert_image_close(got["color"], ref["color"], "color")
+    U.assert_image_close(got["invdepth"], ref["invdepth"], "invdepth")
+    U.assert_grads_close(got["grads"], ref["grads"], flips=5e-3 if frac > 0 else 0.0)
+    return got, ref
+
+
+@pytest.mark.parametrize("deg", [0, 3])
+def test_sh_degrees(on_host, deg):
+    scene = TO.make_scene(250, seed=10 + deg, log_scale_mean=-2.4)
+    _check(scene, TO.make_camera(64, 48, sh_degree=deg, bg=(0.1, 0.3, 0.6)), "sh")
+
+
+@pytest.mark.parametrize("mode", ["sh", "precomp"])
+def test_antialiasing_and_precomputed_inputs(on_host, mode):
+    scene = TO.make_scene(250, seed=21, log_scale_mean=-2.6)
+    _check(scene, TO.make_camera(80, 48, sh_degree=3, antialiasing=True, bg=(1.0, 1.0, 1.0)), mode)
+
+
+def test_ragged_image_scale_modifier_no_depth_gradient(on_host):
+    scene = TO.make_scene(200, seed=33, log_scale_mean=-2.4)
+    _check(scene, TO.make_camera(70, 41, sh_degree=2, scale_modifier=0.7), "sh", with_depth_grad=False)
+
+
+def test_large_and_anisotropic_gaussians(on_host):
+    """Gaussians spanning many tiles: the exact tile culling, the patch masks and several staging rounds per tile."""
+    scene = TO.make_scene(90, seed=35, log_scale_mean=-1.2, log_scale_std=1.2)
+    _check(scene, TO.make_camera(80, 48, sh_degree=3, bg=(0.5, 0.5, 0.5)), "sh")
+
+
+def test_many_gaussians_per_tile(on_host):
+    """More than one 128-record staging round in most tiles."""
+    scene = TO.make_scene(700, seed=36, log_scale_mean=-2.0)
+    scene["opacities"] = scene["opacities"] * 0.15                      # keep transmittance alive deep into the lists
+    _check(scene, TO.make_camera(48, 32, sh_degree=1), "sh")
+
+
+def test_empty_and_all_culled(on_host):
+    dgr = on_host
+    cam = TO.make_camera(48, 32, sh_degree=0, bg=(0.2, 0.4, 0.6))
+    rast = dgr.GaussianRasterizer(U.settings_to(cam, "cpu"))
+    z = lambda *s: torch.zeros(*s)
+    color, radii, invd = rast(means3D=z(0, 3), means2D=z(0, 3), opacities=z(0, 1), shs=z(0, 1, 3), scales=z(0, 3), rotations=z(0, 4))
+    assert radii.numel() == 0 and torch.allclose(color, cam.bg[:, None, None].expand(3, 32, 48))
+    scene = TO.make_scene(60, seed=1, sh_coeffs=1)
+    scene["means3D"][:, 2] -= 100.0
+    got = U.run_cuda(U.make_args(scene, "sh"), cam, *_weights(cam), device="cpu")
+    assert (got["radii"] == 0).all() and all(np.all(v == 0) for v in got["grads"].values() if v is not None)
+
+
+def test_view_batch_path_matches_per_view_autograd(on_host):
+    """gsb_forward_batch / gsb_backward_batch (parameters read once for all views, batched sorts and scans, gradients summed in
+    place) against per-view render() + autograd, both on the host build."""
+    import bench
+    from gaussian_renderer import GradientBucket, render, render_views_backward
+    dev = "cpu"
+    scene = TO.make_scene(300, seed=51, log_scale_mean=-2.6)
+    W, H = 64, 48
+    cams = [bench.BenchCamera(W, H, math.radians(60.0), *bench.view_pose(i, 3.0), dev) for i in range(2)]
+    gts = [torch.rand(3, H, W, generator=torch.Generator().manual_seed(i)) for i in range(2)]
+    bg = torch.tensor([0.1, 0.2, 0.3])
+
+    def run(fused):
+        pc = bench.BenchGaussians(scene, 3, dev)
+        bucket = GradientBucket(pc.parameters())
+        if fused:
+            losses = render_views_backward(cams, pc, bench.Pipe(), bg, lambda img, d, i: (img - gts[i]).abs().mean() + 0.1 * d.mean())["losses"]
+        else:
+            ls = []
+            for i, cam in enumerate(cams):
+                pkg = render(cam, pc, bench.Pipe(), bg)
+                loss = (pkg["render"] - gts[i]).abs().mean() + 0.1 * pkg["depth"].mean()
+                loss.backward()
+                ls.append(loss.detach())
+            losses = torch.stack(ls)
+        return losses.numpy(), bucket.flat.numpy().copy()
+
+    l0, g0 = run(False)
+    l1, g1 = run(True)
+    assert np.allclose(l0, l1, rtol=1e-6, atol=1e-7)
+    assert np.abs(g0 - g1).max() <= 1e-4 * np.abs(g0).max()
+
+
+@pytest.mark.parametrize("shape", [(3, 37, 53), (1, 16, 16)])
+def test_fused_losses_source(on_host, shape, golden):
+    dgr = on_host
+    g = torch.Generator().manual_seed(7)
+    img = (torch.rand(*shape, generator=g) * 1.4 - 0.2).requires_grad_(True)      # some values outside [0,1]: clamp mask
+    gt = torch.rand(*shape, generator=g)
+    ref = TO.photometric_loss(img.clamp(0, 1), gt, 0.2)
+    (g_ref,) = torch.autograd.grad(ref, img)
+    loss, grad, parts = dgr.photometric_loss_and_grad(img.detach(), gt, 0.2)
+    assert abs(float(loss) - float(ref)) < 2e-6
+    assert float((grad - g_ref).abs().max()) <= 1e-4 * float(g_ref.abs().max())
+    if shape == (3, 37, 53):                                                       # the reference's own numbers
+        x, y = torch.from_numpy(golden["loss_img"]), torch.from_numpy(golden["loss_gt"])
+        l2, g2, p2 = dgr.photometric_loss_and_grad(x, y, 0.2)
+        assert abs(float(l2) - float(golden["loss_total"])) < 2e-6 and abs(float(p2[2]) - float(golden["loss_ssim"])) < 2e-6
+        assert np.abs(g2.numpy() - golden["loss_grad"]).max() <= 1e-4 * np.abs(golden["loss_grad"]).max()
+    n = img.numel() // 4 * 4
+    l1, g1 = dgr.l1_loss_and_grad(img.detach().reshape(-1)[:n].contiguous(), gt.reshape(-1)[:n].contiguous())
+    x = img.detach().reshape(-1)[:n].clone().requires_grad_(True)
+    r1 = (x.clamp(0, 1) - gt.reshape(-1)[:n]).abs().mean()
+    (gr1,) = torch.autograd.grad(r1, x)
+    assert abs(float(l1) - float(r1)) < 1e-6 and float((g1 - gr1).abs().max()) <= 1e-6

@@ -1,19 +1,18 @@
-"""Runs the SOURCE of csrc/optim.cu and csrc/densify.cu on the CPU through tests/host_emul/cuda_shim.h (blocks sequential,
-threads of a block = host threads) and drives gaussian_store.GaussianModel with it: the kernels' index arithmetic, scans,
-row order and the host class's buffer surgery are checked against the reference fixture where no GPU exists.  The GPU parity
-tests proper are tests/test_store_gpu.py; nothing here is a product path (the library raises on CPU tensors)."""
+"""Runs the SOURCE of the CUDA kernels on the CPU (tests/host_emul: the unmodified .cu files compiled with g++ against a shim
+of the CUDA language -- blocks sequential, threads of a block = host threads, so barriers, shuffles, votes and shared
+memory keep their meaning) and drives the real Python layer with it.  Index arithmetic, scans, sort orders, row orders
+and the host classes' buffer surgery are checked against the reference fixtures and the oracles where no GPU exists; the
+hot path itself is covered by tests/test_hot_path_source_on_host.py.  The GPU parity tests proper are the -m gpu files;
+nothing here is a product path (the library raises on CPU tensors)."""
 import ctypes
 import os
-import shutil
-import subprocess
 from types import SimpleNamespace
 
 import numpy as np
 import pytest
 import torch
 
-import diff_gaussian_rasterization as dgr
-from gaussian_store import GaussianModel
+from gaussian_store import GaussianModel, store_offsets
 from oracle.model_oracle import GROUPS
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -24,67 +23,28 @@ ACT = ("xyz", "features", "opacity", "scaling", "rotation")
 
 
 @pytest.fixture(scope="module")
-def emul(tmp_path_factory):
-    gxx = shutil.which("g++", path="/usr/bin") or shutil.which("g++")
-    if gxx is None:
-        pytest.skip("no host C++ compiler")
-    d = tmp_path_factory.mktemp("emul")
-    for f in ("cuda_shim.h", "emul_main.cpp"):
-        shutil.copy(os.path.join(ROOT, "tests", "host_emul", f), d / f)
-    for name in ("optim", "densify", "knn", "radix_sort"):
-        src = open(os.path.join(ROOT, "gaussian-splatting_b200", "csrc", name + ".cu")).read().splitlines()
-        body = [l for l in src if l.strip() not in ('#include "common.cuh"', '#include "kernels.cuh"')]
-        assert len(src) - 2 <= len(body) < len(src)
-        (d / f"{name}_body.inc").write_text("\n".join(body) + "\n")
-    subprocess.run([gxx, "-std=c++20", "-O1", "-shared", "-fPIC", "-pthread", str(d / "emul_main.cpp"), "-o", str(d / "libemul.so")],
-                   check=True)
-    lib = ctypes.CDLL(str(d / "libemul.so"))
-    vp, i64, i32, f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float
-    lib.emul_adam_step.argtypes = [i64, i32, vp, vp, vp, vp, vp, vp, vp, f32, f32, f32, f32]
-    lib.emul_activate.argtypes = [i64, i32, vp, vp]
-    lib.emul_densify_scratch_bytes.restype = ctypes.c_size_t
-    lib.emul_densify_scratch_bytes.argtypes = [i64, i32]
-    lib.emul_densify_plan.argtypes = [i64, i32, i32, vp, vp, vp, f32, f32, f32, f32, vp, vp]
-    lib.emul_densify_apply.argtypes = [i64, i32, i32, vp, vp, vp, vp, vp, i64, i64, vp, vp, vp]
+def emul(host_lib):
+    lib = ctypes.CDLL(host_lib)
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
     lib.emul_exclusive_scan.argtypes = [vp, vp, ctypes.c_size_t, vp, vp]
     lib.emul_scan_partials.restype = ctypes.c_size_t
     lib.emul_scan_partials.argtypes = [ctypes.c_size_t]
+    lib.emul_sort_scratch_bytes.restype = ctypes.c_size_t
+    lib.emul_sort_scratch_bytes.argtypes = [i64, i32]
+    lib.emul_sort_pairs.argtypes = [vp, vp, vp, vp, i64, vp, i32, i32, vp, i32, ctypes.c_size_t, i32, i32, i32]
     return lib
 
 
-@pytest.fixture()
-def on_host(emul, monkeypatch):
-    """Routes the four kernel entry points gaussian_store uses to the host build of the same kernel sources."""
-    def adam_step(params, grads, m, v, act, P, M, step_size, b1, b2, eps, bc2s, visible=None):
-        ss = np.asarray(step_size, dtype=np.float32)
-        vis = visible.to(torch.uint8).contiguous() if visible is not None else None
-        assert emul.emul_adam_step(P, M, params.data_ptr(), grads.data_ptr(), m.data_ptr(), v.data_ptr(), act.data_ptr(),
-                                   vis.data_ptr() if vis is not None else None, ss.ctypes.data, b1, b2, eps, bc2s) == 0
-
-    def activate(params, act, P, M):
-        assert emul.emul_activate(P, M, params.data_ptr(), act.data_ptr()) == 0
-
-    def densify_plan(params, m, v, accum, denom, P, M, N, thr, size_limit, min_opacity, world_limit):
-        scratch = torch.zeros(max(emul.emul_densify_scratch_bytes(P, N), 1), dtype=torch.uint8)
-        ga, dn = accum.reshape(-1).float().contiguous(), denom.reshape(-1).float().contiguous()
-        counts = np.zeros(4, dtype=np.int64)
-        assert emul.emul_densify_plan(P, M, N, params.data_ptr(), ga.data_ptr(), dn.data_ptr(), thr, size_limit, min_opacity,
-                                      world_limit, scratch.data_ptr(), counts.ctypes.data) == 0
-        return dict(P=P, M=M, N=N, params=params, m=m, v=v, scratch=scratch), (scratch, ga, dn), tuple(int(c) for c in counts)
-
-    def densify_apply(args, unit, n_split, P_new, new_p, new_m, new_v):
-        u = unit.float().contiguous() if unit is not None else None
-        assert emul.emul_densify_apply(args["P"], args["M"], args["N"], args["params"].data_ptr(), args["m"].data_ptr(),
-                                       args["v"].data_ptr(), args["scratch"].data_ptr(), u.data_ptr() if u is not None else None,
-                                       n_split, P_new, new_p.data_ptr(), new_m.data_ptr(), new_v.data_ptr()) == 0
-
-    for name, fn in (("adam_step", adam_step), ("activate", activate), ("densify_plan", densify_plan), ("densify_apply", densify_apply)):
-        monkeypatch.setattr(dgr, name, fn)
+def test_product_layer_still_refuses_cpu_tensors(host_lib):
+    """Outside the on_host fixture nothing runs on the CPU."""
+    import diff_gaussian_rasterization as dgr
+    with pytest.raises(RuntimeError, match="no CPU"):
+        dgr.knn_mean_dist2(torch.zeros(4, 3))
 
 
 def test_scan_source_multi_tile(emul):
     """> 256 chunks of 2048: the partials kernel loops over more than one tile of 256."""
-    n = 2048 * 300 + 77
+    n = 2048 * 258 + 77
     rng = np.random.default_rng(0)
     x = rng.integers(0, 3, n, dtype=np.uint32)
     out = np.zeros(n, dtype=np.uint32)
@@ -93,8 +53,7 @@ def test_scan_source_multi_tile(emul):
     assert emul.emul_exclusive_scan(x.ctypes.data, out.ctypes.data, n, partials.ctypes.data, total.ctypes.data) == 0
     ref = np.concatenate(([0], np.cumsum(x, dtype=np.uint64)[:-1])).astype(np.uint32)
     assert np.array_equal(out, ref) and int(total[0]) == int(x.sum())
-    # in place
-    assert emul.emul_exclusive_scan(x.ctypes.data, x.ctypes.data, n, partials.ctypes.data, total.ctypes.data) == 0
+    assert emul.emul_exclusive_scan(x.ctypes.data, x.ctypes.data, n, partials.ctypes.data, total.ctypes.data) == 0     # in place
     assert np.array_equal(x, ref)
 
 
@@ -122,7 +81,6 @@ def test_kernel_sources_replay_reference_fixture(on_host):
             ref = torch.from_numpy(gold[tag + RAW_KEY[n]])
             assert tuple(raw[n].shape) == tuple(ref.shape), (tag, n, raw[n].shape, ref.shape)
             torch.testing.assert_close(raw[n], ref, rtol=2e-6, atol=2e-6, msg=lambda s: f"{tag} {n}: {s}")
-        from gaussian_store import store_offsets
         P, M, o = m.P, m.sh_coeffs, store_offsets(m.P, m.sh_coeffs)
         for kind, buf in (("m", m.exp_avg), ("v", m.exp_avg_sq)):
             feat = buf[o["features"]:o["opacity"]].view(P, M, 3)
@@ -183,11 +141,9 @@ def test_kernel_source_visible_mask(on_host):
 
 
 @pytest.mark.parametrize("kind", ["uniform", "clustered", "planar", "duplicates", "tiny"])
-def test_knn_source_matches_bruteforce(emul, kind):
+def test_knn_source_matches_bruteforce(on_host, kind):
     from oracle.knn_oracle import mean_dist2_bruteforce
-    emul.emul_knn_scratch_bytes.restype = ctypes.c_size_t
-    emul.emul_knn_scratch_bytes.argtypes = [ctypes.c_int64]
-    emul.emul_knn_mean_dist2.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    from simple_knn._C import distCUDA2
     r = np.random.default_rng(11)
     if kind == "uniform":
         pts = r.uniform(-3, 5, (1500, 3))
@@ -201,32 +157,24 @@ def test_knn_source_matches_bruteforce(emul, kind):
     else:
         pts = r.uniform(0, 1, (3, 3))
     pts = np.ascontiguousarray(pts, dtype=np.float32)
-    out = np.full(len(pts), -1.0, dtype=np.float32)
-    scratch = np.zeros(emul.emul_knn_scratch_bytes(len(pts)), dtype=np.uint8)
-    assert emul.emul_knn_mean_dist2(pts.ctypes.data, len(pts), out.ctypes.data, scratch.ctypes.data) == 0
-    ref = mean_dist2_bruteforce(pts)
-    np.testing.assert_allclose(out, ref, rtol=2e-5, atol=1e-12)
-    if kind == "tiny":                  # 3 points: two neighbours each; one point: zero
-        one = np.zeros(1, dtype=np.float32)
-        scratch = np.zeros(emul.emul_knn_scratch_bytes(1), dtype=np.uint8)
-        assert emul.emul_knn_mean_dist2(pts.ctypes.data, 1, one.ctypes.data, scratch.ctypes.data) == 0 and one[0] == 0.0
+    out = distCUDA2(torch.from_numpy(pts)).numpy()
+    np.testing.assert_allclose(out, mean_dist2_bruteforce(pts), rtol=2e-5, atol=1e-12)
+    if kind == "tiny":                  # one point: zero; no points: empty
+        assert distCUDA2(torch.from_numpy(pts[:1])).tolist() == [0.0] and distCUDA2(torch.zeros(0, 3)).numel() == 0
 
 
-@pytest.mark.parametrize("n,bits,V,variant,big_ipt", [
-    (1, 32, 1, 1, 16), (1000, 32, 1, 1, 16), (5000, 13, 1, 1, 16),    # onesweep, 1024-key blocks, multi-block look-back
-    (5000, 13, 3, 1, 16),                                             # view batch: three independent sorts, ragged counts
-    (70000, 13, 1, 1, 16),                                            # 69 blocks: the eight-deep look-back window wraps
-    (5000, 20, 1, 0, 16),                                             # classic histogram / row-scan / scatter path
-    (620000, 13, 1, 1, 16),                                           # 16 keys per thread (large-input instantiation)
-    (610000, 8, 1, 1, 8),                                             # option sort_big_ipt = 8
+@pytest.mark.parametrize("n,bits,V,variant,small,big_ipt", [
+    (1, 32, 1, 1, 0, 16), (1000, 32, 1, 1, 0, 16), (5000, 13, 1, 1, 0, 16),   # onesweep, 1024-key blocks, multi-block look-back
+    (5000, 13, 3, 1, 0, 16),                                                  # view batch: three independent sorts, ragged counts
+    (70000, 13, 1, 1, 0, 16),                                                 # 69 blocks: the eight-deep look-back window wraps
+    (5000, 10, 1, 0, 0, 16),                                                  # classic histogram / row-scan / scatter path
+    (90000, 13, 2, 1, -1, 16),                                                # 16 keys per thread (large-input instantiation)
+    (50000, 8, 1, 1, -1, 8),                                                  # option sort_big_ipt = 8
+    (50000, 8, 1, 0, -1, 16),                                                 # classic path, 16 keys per thread
 ])
-def test_radix_sort_source_is_stable(emul, n, bits, V, variant, big_ipt):
-    """The hot path's sort (csrc/radix_sort.cu, both variants and both block sizes) on the host: stable order on the sorted
+def test_radix_sort_source_is_stable(emul, n, bits, V, variant, small, big_ipt):
+    """The hot path's sort (csrc/radix_sort.cu, both variants and all block sizes) on the host: stable order on the sorted
     bits, values carried, untouched tails when the per-view count is below the launch size."""
-    u64, vp, i64, i32 = ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
-    emul.emul_sort_scratch_bytes.restype = ctypes.c_size_t
-    emul.emul_sort_scratch_bytes.argtypes = [i64, i32]
-    emul.emul_sort_pairs.argtypes = [vp, vp, vp, vp, i64, vp, i32, i32, vp, i32, ctypes.c_size_t, i32, i32, i32]
     r = np.random.default_rng(n + bits)
     sv = n + 37                                                       # stride between the views' arrays
     keys = r.integers(0, 2 ** 32, V * sv, dtype=np.uint64).astype(np.uint32)
@@ -238,7 +186,7 @@ def test_radix_sort_source_is_stable(emul, n, bits, V, variant, big_ipt):
     ka, va = np.zeros_like(k), np.zeros_like(v_)
     scratch = np.zeros(emul.emul_sort_scratch_bytes(n, V), dtype=np.uint8)
     rc = emul.emul_sort_pairs(k.ctypes.data, v_.ctypes.data, ka.ctypes.data, va.ctypes.data, n, counts.ctypes.data if V > 1 else None,
-                              0, bits, scratch.ctypes.data, V, sv, variant, 0, big_ipt)
+                              0, bits, scratch.ctypes.data, V, sv, variant, small, big_ipt)
     assert rc == 0
     mask = np.uint32((1 << bits) - 1) if bits < 32 else np.uint32(0xFFFFFFFF)
     for view in range(V):
