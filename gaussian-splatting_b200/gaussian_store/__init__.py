@@ -71,8 +71,7 @@ class GaussianModel:
     # ---- construction ----------------------------------------------------------------------------------------------
     def create_from_tensors(self, xyz, features_dc, features_rest, scaling, rotation, opacity, spatial_lr_scale: float = 1.0):
         """Raw (pre-activation) parameters, shapes as in the reference: xyz [P,3], features_dc [P,1,3], features_rest
-        [P,M-1,3], scaling [P,3] (log), rotation [P,4], opacity [P,1] (logit).  (create_from_pcd :150-176 needs simple-knn;
-        out of scope -- initialise from tensors or from a checkpoint.)"""
+        [P,M-1,3], scaling [P,3] (log), rotation [P,4], opacity [P,1] (logit)."""
         P, M = int(xyz.shape[0]), self.sh_coeffs
         if tuple(features_dc.shape) != (P, 1, 3) or tuple(features_rest.shape) != (P, M - 1, 3):
             raise ValueError(f"features_dc / features_rest must be [P,1,3] / [P,{M - 1},3]")
@@ -89,6 +88,20 @@ class GaussianModel:
         self._reactivate()
         self.max_radii2D = torch.zeros(P, device=dev)
         return self
+
+    def create_from_pcd(self, points: torch.Tensor, colors: torch.Tensor, spatial_lr_scale: float = 1.0):
+        """Initialisation from a point cloud (gaussian_model.py:150-172): colours -> SH DC band (RGB2SH, utils/sh_utils.py:114-115),
+        higher bands zero, isotropic log-scales from the mean squared distance to the three nearest neighbours (the
+        ``distCUDA2`` call, here gsb_knn_mean_dist2), identity rotations, opacity 0.1.  ``points`` [N,3], ``colors`` [N,3] in [0,1]."""
+        pts = points.detach().to(torch.float32).reshape(-1, 3).contiguous()
+        N, M = int(pts.shape[0]), self.sh_coeffs
+        dc = ((colors.detach().to(pts.device, torch.float32).reshape(N, 3) - 0.5) / 0.28209479177387814).reshape(N, 1, 3)
+        dist2 = torch.clamp_min(_dgr.knn_mean_dist2(pts), 0.0000001)
+        scales = torch.log(torch.sqrt(dist2))[:, None].repeat(1, 3)
+        rots = torch.zeros((N, 4), device=pts.device)
+        rots[:, 0] = 1
+        opac = torch.full((N, 1), math.log(0.1 / 0.9), device=pts.device)          # inverse_sigmoid(0.1)
+        return self.create_from_tensors(pts, dc, torch.zeros((N, M - 1, 3), device=pts.device), scales, rots, opac, spatial_lr_scale)
 
     def _allocate(self, P: int, device):
         total = store_offsets(P, self.sh_coeffs)["total"]

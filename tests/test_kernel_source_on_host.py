@@ -140,6 +140,22 @@ def test_kernel_source_visible_mask(on_host):
     assert float(m.exp_avg[:3 * P].view(P, 3)[~vis].abs().max()) == 0.0
 
 
+def test_create_from_pcd_on_host(on_host):
+    """gaussian_model.py:150-172 on the store: SH DC from colours, log-scales from the 3-nn distances, opacity 0.1."""
+    from oracle.knn_oracle import mean_dist2_bruteforce
+    g = torch.Generator().manual_seed(9)
+    pts, cols = torch.rand(400, 3, generator=g) * 4 - 2, torch.rand(400, 3, generator=g)
+    m = GaussianModel(3).create_from_pcd(pts, cols, spatial_lr_scale=2.5)
+    assert m.P == 400 and m.spatial_lr_scale == 2.5
+    torch.testing.assert_close(m._features_dc[:, 0], (cols - 0.5) / 0.28209479177387814)
+    assert float(m._features_rest.abs().max()) == 0.0
+    ref = torch.from_numpy(np.log(np.sqrt(np.maximum(mean_dist2_bruteforce(pts.numpy()), 1e-7)))).float()
+    torch.testing.assert_close(m._scaling, ref[:, None].repeat(1, 3), rtol=1e-5, atol=1e-5)
+    assert torch.equal(m._rotation, torch.tensor([1.0, 0, 0, 0]).repeat(400, 1))
+    torch.testing.assert_close(m.get_opacity.detach(), torch.full((400, 1), 0.1))
+    torch.testing.assert_close(m.get_scaling.detach(), torch.exp(m._scaling))
+
+
 @pytest.mark.parametrize("kind", ["uniform", "clustered", "planar", "duplicates", "tiny"])
 def test_knn_source_matches_bruteforce(on_host, kind):
     from oracle.knn_oracle import mean_dist2_bruteforce
