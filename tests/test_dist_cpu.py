@@ -109,3 +109,71 @@ def test_store_gradient_buffer_is_the_allreduce_bucket_gloo_world2():
         assert p.exitcode == 0
     res = dict(q.get(timeout=5) for _ in range(2))
     assert res == {0: True, 1: True}
+
+
+def _train_worker(rank, world, port, q, lib):
+    """One rank of a 2-process data-parallel training step with the REAL kernels' source (host build) and gloo."""
+    for p in (os.path.join(ROOT, "gaussian-splatting_b200"), os.path.join(ROOT, "tests", "host_emul"), ROOT, os.path.join(ROOT, "tests")):
+        sys.path.insert(0, p)
+    import math
+    from types import SimpleNamespace
+    import build as host_build
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        with host_build.python_layer_on_host(lib) as dgr:
+            import bench
+            from gaussian_renderer import render_views_backward, shard_views
+            from gaussian_renderer.synthetic import make_scene
+            from gaussian_store import GaussianModel
+            sc = make_scene(220, seed=4, log_scale_mean=-2.5)
+            op = sc["opacities"].clamp(1e-6, 1 - 1e-6).reshape(-1, 1)
+            m = GaussianModel(3)
+            m.active_sh_degree = 3
+            m.create_from_tensors(sc["means3D"], sc["shs"][:, :1].contiguous(), sc["shs"][:, 1:].contiguous(), torch.log(sc["scales"]),
+                                  sc["rotations"], torch.log(op / (1 - op)), 1.0)
+            m.training_setup(SimpleNamespace(position_lr_init=0.00016, position_lr_final=0.0000016, position_lr_delay_mult=0.01,
+                                             position_lr_max_steps=30000, feature_lr=0.0025, opacity_lr=0.025, scaling_lr=0.005,
+                                             rotation_lr=0.001, percent_dense=0.01))
+            W, H, NV = 48, 32, 4
+            cams = [bench.BenchCamera(W, H, math.radians(60.0), *bench.view_pose(i, 3.0), "cpu") for i in range(NV)]
+            gts = [torch.rand(3, H, W, generator=torch.Generator().manual_seed(100 + i)) for i in range(NV)]
+            mine = shard_views(list(range(NV)), rank, world)
+            m.update_learning_rate(1)
+            render_views_backward([cams[i] for i in mine], m, bench.Pipe(), torch.zeros(3),
+                                  lambda img, d, k: dgr.l1_loss_and_grad(img, gts[mine[k]]), loss_returns_grad=True, overwrite=True)
+            if world > 1:
+                dist.all_reduce(m.grad)                      # the one collective of the step
+            grad = m.grad.clone()
+            m.optimizer_step()
+            q.put((rank, world, grad.numpy(), m.store.numpy().copy()))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+def test_data_parallel_training_step_with_kernel_sources_gloo_world2(host_lib):
+    """View-parallel step end to end on the CPU: each rank renders its views with the kernels' source (tests/host_emul),
+    ONE gloo all-reduce of the store's gradient buffer, fused Adam on every rank.  The reduced gradient equals the
+    single-process gradient over all views, and both ranks end with bit-identical parameters."""
+    import numpy as np
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q, host_lib)) for r in range(2)]
+    procs.append(ctx.Process(target=_train_worker, args=(0, 1, port + 1, q, host_lib)))     # single-process reference
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=600) for _ in range(3)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    single = next(g for g in got if g[1] == 1)
+    ranks = sorted((g for g in got if g[1] == 2), key=lambda g: g[0])
+    assert np.array_equal(ranks[0][2], ranks[1][2]) and np.array_equal(ranks[0][3], ranks[1][3])
+    scale = np.abs(single[2]).max()
+    assert scale > 0 and np.abs(ranks[0][2] - single[2]).max() <= 1e-5 * scale
+    assert not np.array_equal(ranks[0][3], single[3] * 0)            # parameters were stepped
+    moved = np.abs(ranks[0][3] - single[3])
+    assert float((moved > 1e-3).mean()) < 1e-3                        # same step up to sign flips of ~zero gradients
