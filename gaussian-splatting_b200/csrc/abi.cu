@@ -36,8 +36,8 @@ void timer_end(void *token, cudaStream_t stream) {
 }
 
 static int opt_cull = 1;
-static int opt_fwd_variant = 6;  // one pixel per thread + sub-tile patch culling, 6 CTAs/SM (tools/sweep.py)
-static int opt_bwd_variant = 10;  // 2x2 px/thread, sub-tile culling, packed f32x2 (FFMA2), 16 CTAs/SM  // render_mp.cu, 2x2 pixels per thread (tools/sweep.py: 0.74 ms vs 1.41 / 1.03)
+static int opt_fwd_variant = 6;  // one pixel per thread + sub-tile patch culling, 6 CTAs/SM (tests/analysis/sweep.py)
+static int opt_bwd_variant = 10;  // 2x2 px/thread, sub-tile culling, packed f32x2 (FFMA2), 16 CTAs/SM  // render_mp.cu, 2x2 pixels per thread (tests/analysis/sweep.py: 0.74 ms vs 1.41 / 1.03)
 
 void set_error(const char *fmt, ...) {
     va_list ap;

@@ -1,5 +1,5 @@
 // render_ps.cu -- "patch-slot" blend kernels (EXPERIMENT, measured slower, NOT the default; fwd/bwd variant 5).
-// Kept selectable through gsb_set_option so the A/B in DESIGN.md section 4 can be reproduced (tools/sweep.py):
+// Kept selectable through gsb_set_option so the A/B in DESIGN.md section 4 can be reproduced (tests/analysis/sweep.py):
 // forward 0.49 ms vs 0.33, backward 0.77 ms vs 0.73 at the time -- the per-slot warp-uniform branches serialise the
 // four slots and remove the instruction-level parallelism the 2x2 kernels get from evaluating them together.
 //

@@ -3,7 +3,7 @@ pixel evaluations the blend kernels EXECUTE actually contribute?  Uses the oracl
 tool is an analysis aid, not a product or benchmark path) on a window of tiles in the image centre and replays, per tile,
 what the kernels do: depth-ordered list, per-pixel termination at T < 1e-4, per-entry 8x4 patch masks.
 
-    python tools/lane_efficiency.py [--tiles-x 8 --tiles-y 6]
+    python tests/analysis/lane_efficiency.py [--tiles-x 8 --tiles-y 6]
 """
 import argparse
 import math
@@ -13,7 +13,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "gaussian-splatting_b200"))
 import bench  # noqa: E402

@@ -1,7 +1,7 @@
 """A/B sweep of kernel variants on the bench workload: correctness vs the CPU oracle at a medium size, then
-per-kernel CUDA-event times at full size.  python tools/sweep.py "fwd,bwd;fwd,bwd;..." """
+per-kernel CUDA-event times at full size.  python tests/analysis/sweep.py "fwd,bwd;fwd,bwd;..." """
 import json, math, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "gaussian-splatting_b200"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import numpy as np, torch

@@ -4,12 +4,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "gaussian-splatting_b200"))
 import torch
 import bench
-from oracle import torch_oracle as TO
+from gaussian_renderer.synthetic import make_scene
 import diff_gaussian_rasterization as dgr
 
 dev = torch.device("cuda", 0)
 P, W, H = 1_000_000, 1920, 1080
-scene = TO.make_scene(P, seed=0, log_scale_mean=bench.LOG_SCALE_MEAN)
+scene = make_scene(P, seed=0, log_scale_mean=bench.LOG_SCALE_MEAN)
 pc = bench.BenchGaussians(scene, 3, dev)
 cam = bench.BenchCamera(W, H, math.radians(60.0), *bench.view_pose(0, 3.0), dev)
 bg = torch.zeros(3, device=dev)

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "gaussian-splatting_b200"))
 import torch
 import bench
-from oracle import torch_oracle as TO
+from gaussian_renderer.synthetic import make_scene
 import diff_gaussian_rasterization as dgr
 from gaussian_renderer import GradientBucket, render_views_backward
 
@@ -16,7 +16,7 @@ for kv in os.environ.get("GS_OPTS", "").split(","):
     if "=" in kv:
         k, v = kv.split("="); dgr.set_option(k, int(v))
 dev = torch.device("cuda", 0)
-scene = TO.make_scene(P, seed=0, log_scale_mean=bench.LOG_SCALE_MEAN)
+scene = make_scene(P, seed=0, log_scale_mean=bench.LOG_SCALE_MEAN)
 pc = bench.BenchGaussians(scene, 3, dev)
 bucket = GradientBucket(pc.parameters())
 bg = torch.zeros(3, device=dev)
