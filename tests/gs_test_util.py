@@ -39,21 +39,22 @@ def make_args(scene, mode, seed=3):
 def run_cuda(args, cam, wc=None, wd=None, device="cuda"):
     import diff_gaussian_rasterization as dgr
     rs = settings_to(cam, device)
-    t = {k: (v.to(device).requires_grad_(True) if v is not None else None) for k, v in args.items()}
+    # fresh leaves: on the CPU (host build of the kernel sources) .to() would alias the caller's tensors and their .grad
+    t = {k: (v.detach().clone().to(device).requires_grad_(True) if v is not None else None) for k, v in args.items()}
     P = args["means3D"].shape[0]
     m2d = torch.zeros(P, 3, device=device, requires_grad=True)
     rast = dgr.GaussianRasterizer(raster_settings=rs)
     color, radii, invd = rast(means3D=t["means3D"], means2D=m2d, shs=t["shs"], colors_precomp=t["colors_precomp"],
                               opacities=t["opacities"], scales=t["scales"], rotations=t["rotations"],
                               cov3D_precomp=t["cov3D_precomp"])
-    out = dict(color=color.detach().cpu().numpy(), radii=radii.cpu().numpy(), invdepth=invd.detach().cpu().numpy())
+    out = dict(color=color.detach().cpu().numpy().copy(), radii=radii.cpu().numpy().copy(), invdepth=invd.detach().cpu().numpy().copy())
     if wc is not None:
         loss = (color * torch.as_tensor(wc, dtype=torch.float32, device=device)).sum()
         if wd is not None:
             loss = loss + (invd * torch.as_tensor(wd, dtype=torch.float32, device=device)).sum()
         loss.backward()
-        g = {k: (v.grad.detach().cpu().numpy() if v is not None and v.grad is not None else None) for k, v in t.items()}
-        g["means2D"] = m2d.grad.detach().cpu().numpy()
+        g = {k: (v.grad.detach().cpu().numpy().copy() if v is not None and v.grad is not None else None) for k, v in t.items()}
+        g["means2D"] = m2d.grad.detach().cpu().numpy().copy()
         out["grads"] = g
     return out
 
