@@ -120,7 +120,11 @@ size_t sort_scratch_bytes(int64_t n, int V = 1);
 // n_dev is an array of V counts.
 int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n,
                const unsigned long long *n_dev, int begin_bit, int end_bit, void *scratch, bool debug,
-               cudaStream_t stream, int V = 1, size_t sv = 0);
+               cudaStream_t stream, int V = 1, size_t sv = 0, bool hist_ready = false);
+// The onesweep path keeps its digit histograms at the start of `scratch`: [GSB_SORT_MAX_VIEWS][GSB_SORT_MAX_PASSES][256] uint32,
+// pass p = bits [begin_bit + 8p, ...).  hist_ready = true: the caller has filled them (launch_ranges_from_counts) and the
+// sort's own histogram pass over the keys is skipped.
+constexpr int GSB_SORT_MAX_VIEWS = 16, GSB_SORT_MAX_PASSES = 4, GSB_SORT_RADIX = 256;
 extern int g_sort_variant;
 extern int g_sort_force_small;
 extern int g_sort_big_ipt;

@@ -180,8 +180,8 @@ sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__rest
 #define OS_FLAG_AGG (1u << 30)
 #define OS_FLAG_PREFIX (2u << 30)
 #define OS_VALUE_MASK ((1u << 30) - 1u)
-constexpr int OS_MAX_PASSES = 4;
-constexpr int GSB_SORT_MAX_VIEWS = 16;
+constexpr int OS_MAX_PASSES = GSB_SORT_MAX_PASSES;
+static_assert(RADIX == GSB_SORT_RADIX, "histogram layout shared with binning.cu");
 
 struct OnesweepPasses {
     int npass;
@@ -406,7 +406,7 @@ static size_t onesweep_scratch_bytes(int64_t n, int V) {
 
 static int onesweep_sort(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n,
                          const unsigned long long *n_dev, int begin_bit, int end_bit, void *scratch, bool debug,
-                         cudaStream_t stream, int V, size_t sv) {
+                         cudaStream_t stream, int V, size_t sv, bool hist_ready) {
     OnesweepPasses ps;
     ps.npass = 0;
     for (int bit = begin_bit; bit < end_bit; bit += RADIX_BITS) {
@@ -424,9 +424,14 @@ static int onesweep_sort(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uin
     uint32_t *status = ticket + 64;
     const size_t sv_status = (size_t)ps.npass * nblocks * RADIX;
     const size_t zero_bytes = (size_t)GSB_SORT_MAX_VIEWS * OS_MAX_PASSES * RADIX * 4 + 256 + (size_t)V * sv_status * 4;
-    GSB_CUDA(cudaMemsetAsync(scratch, 0, zero_bytes, stream));
-    const int hist_blocks = (int)(ceil_div(n, 256 * 16) < 148 * 8 ? ceil_div(n, 256 * 16) : 148 * 8);
-    GSB_LAUNCH("sort_hist", debug, stream, onesweep_hist_kernel, dim3(hist_blocks, V), 256, 0, keys, ghist, n, n_dev, ps, sv);
+    if (hist_ready) {      // the histograms are already there: clear only the tickets and the look-back status words
+        const size_t hist_bytes = (size_t)GSB_SORT_MAX_VIEWS * OS_MAX_PASSES * RADIX * 4;
+        GSB_CUDA(cudaMemsetAsync(static_cast<char *>(scratch) + hist_bytes, 0, zero_bytes - hist_bytes, stream));
+    } else {
+        GSB_CUDA(cudaMemsetAsync(scratch, 0, zero_bytes, stream));
+        const int hist_blocks = (int)(ceil_div(n, 256 * 16) < 148 * 8 ? ceil_div(n, 256 * 16) : 148 * 8);
+        GSB_LAUNCH("sort_hist", debug, stream, onesweep_hist_kernel, dim3(hist_blocks, V), 256, 0, keys, ghist, n, n_dev, ps, sv);
+    }
     uint32_t *kin = keys, *vin = vals, *kout = keys_alt, *vout = vals_alt;
     for (int p = 0; p < ps.npass; ++p) {
         uint32_t *st = status + (size_t)p * nblocks * RADIX;
@@ -452,7 +457,7 @@ size_t sort_scratch_bytes(int64_t n, int V) {
 
 int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n,
                const unsigned long long *n_dev, int begin_bit, int end_bit, void *scratch, bool debug,
-               cudaStream_t stream, int V, size_t sv) {
+               cudaStream_t stream, int V, size_t sv, bool hist_ready) {
     if (n <= 0 || end_bit <= begin_bit) return GSB_OK;
     if (n >= (int64_t)1 << 30) {
         set_error("sort_pairs: n=%lld does not fit 30-bit positions", (long long)n);
@@ -460,7 +465,8 @@ int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *val
     }
     if (V > GSB_SORT_MAX_VIEWS) { set_error("sort_pairs: more than %d views", GSB_SORT_MAX_VIEWS); return GSB_ERR_ARGUMENT; }
     if ((g_sort_variant == 1 || V > 1) && (end_bit - begin_bit) <= OS_MAX_PASSES * RADIX_BITS)
-        return onesweep_sort(keys, vals, keys_alt, vals_alt, n, n_dev, begin_bit, end_bit, scratch, debug, stream, V, sv);
+        return onesweep_sort(keys, vals, keys_alt, vals_alt, n, n_dev, begin_bit, end_bit, scratch, debug, stream, V, sv, hist_ready);
+    if (hist_ready) { set_error("sort_pairs: precomputed histograms need the onesweep path"); return GSB_ERR_ARGUMENT; }
     if (V > 1) { set_error("sort_pairs: the view-batch sort needs the onesweep path"); return GSB_ERR_ARGUMENT; }
     const int ipt = sort_ipt(n);
     const int nblocks = (int)ceil_div(n, SORT_THREADS * ipt);

@@ -19,7 +19,7 @@ def _weights(cam, seed=5):
     return torch.randn(3, H, W, generator=gen).numpy(), torch.randn(1, H, W, generator=gen).numpy()
 
 
-def _check(scene, cam, mode, with_depth_grad=True):
+def _check(scene, cam, mode, with_depth_grad=True, grad_tol=U.GRAD_REL_TOL):
     args = U.make_args(scene, mode)
     wc, wd = _weights(cam)
     if not with_depth_grad:
@@ -29,7 +29,7 @@ def _check(scene, cam, mode, with_depth_grad=True):
     assert (got["radii"] == ref["radii"]).all(), "radii differ"
     mx, frac = U.assert_image_close(got["color"], ref["color"], "color")
     U.assert_image_close(got["invdepth"], ref["invdepth"], "invdepth")
-    U.assert_grads_close(got["grads"], ref["grads"], flips=5e-3 if frac > 0 else 0.0)
+    U.assert_grads_close(got["grads"], ref["grads"], tol=grad_tol, flips=5e-3 if frac > 0 else 0.0)
     return got, ref
 
 
@@ -53,7 +53,9 @@ def test_ragged_image_scale_modifier_no_depth_gradient(on_host):
 def test_large_and_anisotropic_gaussians(on_host):
     """Gaussians spanning many tiles: the exact tile culling, the patch masks and several staging rounds per tile."""
     scene = TO.make_scene(90, seed=35, log_scale_mean=-1.2, log_scale_std=1.2)
-    _check(scene, TO.make_camera(80, 48, sh_degree=3, bg=(0.5, 0.5, 0.5)), "sh")
+    # strongly anisotropic footprints: the float32 oracle's own gradients are 1-2e-4 from float64 here, and the order in which
+    # the float atomics land (not reproducible) moves the kernels' result by as much -- hence 5e-4 instead of 1e-4
+    _check(scene, TO.make_camera(80, 48, sh_degree=3, bg=(0.5, 0.5, 0.5)), "sh", grad_tol=5e-4)
 
 
 def test_many_gaussians_per_tile(on_host):
@@ -179,3 +181,33 @@ def test_needle_gaussians_are_as_exact_as_float32_allows(on_host):
     assert np.abs(got["color"] - ref["color"]).max() <= 0.2 * oracle_err
     assert np.abs(got["color"] - c64).max() <= 1.2 * oracle_err
     U.assert_grads_close(got["grads"], ref["grads"], tol=1e-2)
+
+
+def test_fused_ranges_option(on_host):
+    """Option fused_ranges (default off; an A/B candidate): tile ranges and the tile sort's digit histograms come from per-tile
+    counters that emit fills, instead of a pass over the D sorted keys and a histogram pass over the D unsorted ones.  Same
+    images and gradients on the single-view and the view-batch path."""
+    import bench
+    from gaussian_renderer import GradientBucket, render_views_backward
+    dgr = on_host
+    scene = TO.make_scene(180, seed=62, log_scale_mean=-2.1, log_scale_std=0.6)
+    cam = TO.make_camera(80, 48, sh_degree=2, bg=(0.2, 0.1, 0.3))          # 5 x 3 tiles, some of them empty at the border
+    W, H = 64, 48
+    cams = [bench.BenchCamera(W, H, math.radians(60.0), *bench.view_pose(i, 3.0), "cpu") for i in range(1)]
+    gts = [torch.rand(3, H, W, generator=torch.Generator().manual_seed(i)) for i in range(1)]
+
+    def batch():
+        pc = bench.BenchGaussians(scene, 3, "cpu")
+        bucket = GradientBucket(pc.parameters())
+        out = render_views_backward(cams, pc, bench.Pipe(), torch.zeros(3), lambda img, d, i: (img - gts[i]).abs().mean() + 0.1 * d.mean())
+        return out["losses"].numpy().copy(), bucket.flat.numpy().copy()
+
+    base_l, base_g = batch()
+    dgr.set_option("fused_ranges", 1)
+    try:
+        _check(scene, cam, "sh")
+        l, g = batch()
+    finally:
+        dgr.set_option("fused_ranges", 0)
+    assert np.array_equal(base_l, l)
+    assert np.abs(base_g - g).max() <= 1e-5 * np.abs(base_g).max()           # float atomics arrive in another order
