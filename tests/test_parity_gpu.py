@@ -438,3 +438,44 @@ def test_fused_photometric_loss_and_fused_ssim(shape, golden):
     (ga,) = torch.autograd.grad(v, a)
     (ga_ref,) = torch.autograd.grad(v_ref, a_ref)
     assert (ga.cpu() - ga_ref).abs().max().item() <= 1e-4 * ga_ref.abs().max().item()
+
+
+@pytest.mark.parametrize("opts", [{"fused_ranges": 1}, {"sort_small": -1, "sort_big_ipt": 8}, {"sort_small": -1, "sort_big_ipt": 16, "fused_ranges": 1}],
+                         ids=["fused_ranges", "sort_ipt8", "sort_ipt16_fused"])
+def test_ab_options_keep_results(opts):
+    """The prepared A/B knobs (off by default) change neither the image nor, beyond the order of float atomics, the gradients;
+    single-view and view-batch path."""
+    import math
+    import bench
+    import diff_gaussian_rasterization as dgr
+    from gaussian_renderer import GradientBucket, render_views_backward
+    dev = torch.device("cuda", 0)
+    scene = TO.make_scene(20000, seed=71, log_scale_mean=-3.4)
+    cam = TO.make_camera(400, 240, sh_degree=3, bg=(0.2, 0.4, 0.1))
+    args = U.make_args(scene, "sh")
+    wc, wd = _weights(cam)
+    W, H = 320, 200
+    cams = [bench.BenchCamera(W, H, math.radians(60.0), *bench.view_pose(i, 3.0), dev) for i in range(3)]
+    gts = [torch.rand(3, H, W, generator=torch.Generator().manual_seed(i)).to(dev) for i in range(3)]
+
+    def batch():
+        pc = bench.BenchGaussians(scene, 3, dev)
+        bucket = GradientBucket(pc.parameters())
+        out = render_views_backward(cams, pc, bench.Pipe(), torch.zeros(3, device=dev), lambda img, d, i: (img - gts[i]).abs().mean() + 0.1 * d.mean())
+        return out["losses"].cpu().numpy(), bucket.flat.cpu().numpy()
+
+    base, (bl, bg_) = U.run_cuda(args, cam, wc, wd), batch()
+    defaults = {"fused_ranges": 0, "sort_small": 0, "sort_big_ipt": 16}
+    try:
+        for k, v in opts.items():
+            dgr.set_option(k, v)
+        got, (l, g) = U.run_cuda(args, cam, wc, wd), batch()
+    finally:
+        for k in opts:
+            dgr.set_option(k, defaults[k])
+    assert np.array_equal(base["color"], got["color"]) and np.array_equal(base["invdepth"], got["invdepth"])
+    assert np.array_equal(base["radii"], got["radii"]) and np.array_equal(bl, l)
+    for k, v in base["grads"].items():
+        if v is not None:
+            assert np.abs(v - got["grads"][k]).max() <= 1e-4 * (np.abs(v).max() + 1e-20), k
+    assert np.abs(bg_ - g).max() <= 1e-4 * np.abs(bg_).max()
