@@ -495,7 +495,7 @@ def main():
     torch.cuda.synchronize()
     breakdown = {}
     for name in ("preprocess_fwd", "sort_hist", "sort_rowscan", "sort_scatter", "scan_reduce", "scan_partials",
-                 "scan_apply", "emit", "tile_ranges", "render_fwd", "render_bwd", "preprocess_bwd"):
+                 "scan_apply", "emit", "tile_ranges", "ranges_from_counts", "render_fwd", "render_bwd", "preprocess_bwd", "adam_step"):
         t, n = dgr.kernel_time(name)
         breakdown[name] = round(t / (2 * V), 4)
     dgr.kernel_time("", reset=True)
