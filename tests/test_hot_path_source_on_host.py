@@ -185,29 +185,12 @@ def test_needle_gaussians_are_as_exact_as_float32_allows(on_host):
 
 def test_fused_ranges_option(on_host):
     """Option fused_ranges (default off; an A/B candidate): tile ranges and the tile sort's digit histograms come from per-tile
-    counters that emit fills, instead of a pass over the D sorted keys and a histogram pass over the D unsorted ones.  Same
-    images and gradients on the single-view and the view-batch path."""
-    import bench
-    from gaussian_renderer import GradientBucket, render_views_backward
+    counters that emit fills, instead of a pass over the D sorted keys and a histogram pass over the D unsorted ones.  Single
+    view against the oracle here (some tiles empty at the image border); the -m gpu suite repeats it on the view-batch path."""
     dgr = on_host
     scene = TO.make_scene(180, seed=62, log_scale_mean=-2.1, log_scale_std=0.6)
-    cam = TO.make_camera(80, 48, sh_degree=2, bg=(0.2, 0.1, 0.3))          # 5 x 3 tiles, some of them empty at the border
-    W, H = 64, 48
-    cams = [bench.BenchCamera(W, H, math.radians(60.0), *bench.view_pose(i, 3.0), "cpu") for i in range(1)]
-    gts = [torch.rand(3, H, W, generator=torch.Generator().manual_seed(i)) for i in range(1)]
-
-    def batch():
-        pc = bench.BenchGaussians(scene, 3, "cpu")
-        bucket = GradientBucket(pc.parameters())
-        out = render_views_backward(cams, pc, bench.Pipe(), torch.zeros(3), lambda img, d, i: (img - gts[i]).abs().mean() + 0.1 * d.mean())
-        return out["losses"].numpy().copy(), bucket.flat.numpy().copy()
-
-    base_l, base_g = batch()
     dgr.set_option("fused_ranges", 1)
     try:
-        _check(scene, cam, "sh")
-        l, g = batch()
+        _check(scene, TO.make_camera(80, 48, sh_degree=2, bg=(0.2, 0.1, 0.3)), "sh")
     finally:
         dgr.set_option("fused_ranges", 0)
-    assert np.array_equal(base_l, l)
-    assert np.abs(base_g - g).max() <= 1e-5 * np.abs(base_g).max()           # float atomics arrive in another order
