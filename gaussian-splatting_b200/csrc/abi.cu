@@ -18,6 +18,7 @@ int g_time_kernels = 0;
 // ---- kernel timing records ----
 struct TimerRec { char name[32]; cudaEvent_t e0, e1; };
 static std::vector<TimerRec *> g_timer_recs;
+static std::mutex g_timer_mutex;
 
 void *timer_begin(const char *name, cudaStream_t stream) {
     if (g_time_kernels == 1 && strncmp(name, "render_", 7) != 0) return nullptr;
@@ -32,13 +33,13 @@ void *timer_begin(const char *name, cudaStream_t stream) {
 void timer_end(void *token, cudaStream_t stream) {
     TimerRec *r = static_cast<TimerRec *>(token);
     cudaEventRecord(r->e1, stream);
+    std::lock_guard<std::mutex> lock(g_timer_mutex);
     g_timer_recs.push_back(r);
 }
 
 static int opt_cull = 1;
 static int opt_fused_ranges = 0;  // 1: tile ranges and the tile sort's histograms from counters filled by emit (A/B; binning.cu)
-static int opt_fwd_variant = 6;  // one pixel per thread + sub-tile patch culling, 6 CTAs/SM (tests/analysis/sweep.py)
-static int opt_bwd_variant = 10;  // 2x2 px/thread, sub-tile culling, packed f32x2 (FFMA2), 16 CTAs/SM  // render_mp.cu, 2x2 pixels per thread (tests/analysis/sweep.py: 0.74 ms vs 1.41 / 1.03)
+static int opt_tile_order = 0;    // 1: blend CTAs take the tiles by descending list length (render.cu tile_order_kernel; A/B)
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -57,12 +58,10 @@ int check_launch(const char *what, bool debug, cudaStream_t stream) {
     return GSB_OK;
 }
 
-// pinned read-back slot for the instance count, one per device, created on first use
-static std::mutex g_slot_mutex;   // the tiny per-device caches below are shared by all host threads
-
+// pinned read-back slot for the instance count: one per (host thread, device), created on first use, so that two host
+// threads driving the same device (a viewer next to the training thread) never share a slot or its event
 static unsigned long long *pinned_slot() {
-    static unsigned long long *slots[64] = {nullptr};
-    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    static thread_local unsigned long long *slots[64] = {nullptr};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     if (!slots[dev]) {
@@ -74,8 +73,7 @@ static unsigned long long *pinned_slot() {
 }
 
 static cudaEvent_t readback_event() {
-    static cudaEvent_t evs[64] = {nullptr};
-    std::lock_guard<std::mutex> lock(g_slot_mutex);
+    static thread_local cudaEvent_t evs[64] = {nullptr};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     if (!evs[dev] && cudaEventCreateWithFlags(&evs[dev], cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -145,11 +143,12 @@ static size_t carve_image(void *base, size_t npix, ImageView &v) {
     v.n_contrib = c.take<uint32_t>(npix);
     return c.bytes();
 }
-struct BinningView { uint32_t *point_list; uint2 *ranges; };
+struct BinningView { uint32_t *point_list; uint2 *ranges; uint32_t *tile_order; };
 static size_t carve_binning(void *base, int64_t D, int num_tiles, BinningView &v) {
     Carver c(base);
     v.point_list = c.take<uint32_t>((size_t)(D > 0 ? D : 1));
     v.ranges = c.take<uint2>((size_t)num_tiles);
+    v.tile_order = c.take<uint32_t>((size_t)num_tiles);
     return c.bytes();
 }
 
@@ -172,13 +171,13 @@ int32_t gsb_set_option(const char *name, int32_t value) {
     if (!strcmp(name, "sort_small")) { g_sort_force_small = value; return 0; }
     if (!strcmp(name, "fused_ranges")) { opt_fused_ranges = value; return 0; }
     if (!strcmp(name, "sort_big_ipt")) { if (value != 8 && value != 16) return 1; g_sort_big_ipt = value; return 0; }
-    if (!strcmp(name, "render_fwd_variant")) { opt_fwd_variant = value; return 0; }
-    if (!strcmp(name, "render_bwd_variant")) { opt_bwd_variant = value; return 0; }
+    if (!strcmp(name, "tile_order")) { opt_tile_order = value; return 0; }
     return 1;
 }
 
 int32_t gsb_kernel_time(const char *name, double *total_ms, int64_t *launches, int32_t reset) {
     // waits for the recorded events; name == NULL or "" sums every kernel
+    std::lock_guard<std::mutex> lock(g_timer_mutex);
     double ms = 0.0;
     int64_t n = 0;
     for (TimerRec *r : g_timer_recs) {
@@ -196,6 +195,12 @@ int32_t gsb_kernel_time(const char *name, double *total_ms, int64_t *launches, i
     if (total_ms) *total_ms = ms;
     if (launches) *launches = n;
     return GSB_OK;
+}
+
+// optional heavy-tiles-first permutation for the blend launches (option tile_order); lives behind the tile ranges in BINNING
+static int maybe_tile_order(const uint2 *ranges, int V, int num_tiles, uint32_t *order, bool debug, cudaStream_t stream) {
+    if (!opt_tile_order) return GSB_OK;
+    return launch_tile_order(ranges, V, num_tiles, order, debug, stream);
 }
 
 int32_t gsb_forward(const GsbSettings *s, const GsbInputs *in, float *out_color, int32_t *out_radii,
@@ -261,7 +266,7 @@ int32_t gsb_forward(const GsbSettings *s, const GsbInputs *in, float *out_color,
         st->binning = do_alloc(alloc, alloc_ctx, GSB_BUF_BINNING, st->binning_bytes);
         if (!st->binning) return GSB_ERR_ALLOC;
         carve_binning(st->binning, cap, num_tiles, bv);
-        st->point_list = bv.point_list; st->ranges = bv.ranges;
+        st->point_list = bv.point_list; st->ranges = bv.ranges; st->tile_order = opt_tile_order ? bv.tile_order : nullptr;
         int r;
         if (cap > 0 && P > 0) {
             const size_t Dn = (size_t)cap;
@@ -294,13 +299,15 @@ int32_t gsb_forward(const GsbSettings *s, const GsbInputs *in, float *out_color,
             r = launch_tile_ranges(nullptr, 0, nullptr, num_tiles, bv.ranges, 1, 0, debug, stream);
             if (r) return r;
         }
+        r = maybe_tile_order(bv.ranges, 1, num_tiles, bv.tile_order, debug, stream);
+        if (r) return r;
         RenderFwdArgs ra;
-        ra.W = cam.W; ra.H = cam.H; ra.gx = cam.gx; ra.gy = cam.gy; ra.ranges = bv.ranges; ra.point_list = bv.point_list;
-        ra.splat = splat; ra.bg = s->bg; ra.out_color = out_color; ra.out_invdepth = out_invdepth; ra.final_T = iv.final_T;
+        memset(&ra, 0, sizeof(ra));
+        ra.W = cam.W; ra.H = cam.H; ra.gx = cam.gx; ra.gy = cam.gy; ra.V = 1;
+        ra.ranges = bv.ranges; ra.point_list = bv.point_list; ra.tile_order = static_cast<const uint32_t *>(st->tile_order);
+        ra.splat = splat; ra.bg[0] = s->bg; ra.out_color = out_color; ra.out_invdepth = out_invdepth; ra.final_T = iv.final_T;
         ra.n_contrib = iv.n_contrib;
-        if (opt_fwd_variant == 5) return launch_render_fwd_ps(ra, debug, stream);
-        return (opt_fwd_variant == 2 || opt_fwd_variant == 3) ? launch_render_fwd_mp(ra, opt_fwd_variant == 3 ? 4 : 2, debug, stream)
-                                                              : launch_render_fwd(ra, opt_fwd_variant, debug, stream);
+        return launch_render_fwd(ra, debug, stream);
     };
 
     int64_t D = 0;
@@ -370,43 +377,28 @@ int32_t gsb_backward(const GsbSettings *s, const GsbInputs *in, const GsbState *
         return GSB_ERR_ARGUMENT;
     }
     if (P == 0) return GSB_OK;
-    const size_t npix = (size_t)cam.W * cam.H;
     const size_t dacc_bytes = align_up((size_t)P * DACC_STRIDE * sizeof(float), 256);
     float *dacc = static_cast<float *>(do_alloc(alloc, alloc_ctx, GSB_BUF_SCRATCH0, dacc_bytes));
     if (!dacc) return GSB_ERR_ALLOC;
     GSB_CUDA(cudaMemsetAsync(dacc, 0, dacc_bytes, stream));
-
-    (void)npix;
     const float4 *splat = static_cast<const float4 *>(st->splat);
 
-    if (st->num_rendered > 0) {
+    if (st->num_rendered != 0) {
         RenderBwdArgs ra;
-        ra.W = cam.W; ra.H = cam.H; ra.gx = cam.gx; ra.gy = cam.gy; ra.ranges = static_cast<const uint2 *>(st->ranges);
-        ra.point_list = st->point_list;
-        ra.splat = splat; ra.bg = s->bg; ra.final_T = st->final_T; ra.n_contrib = st->n_contrib; ra.dL_dcolor = dL_dcolor;
+        memset(&ra, 0, sizeof(ra));
+        ra.W = cam.W; ra.H = cam.H; ra.gx = cam.gx; ra.gy = cam.gy; ra.V = 1;
+        ra.ranges = static_cast<const uint2 *>(st->ranges); ra.point_list = st->point_list;
+        ra.tile_order = static_cast<const uint32_t *>(st->tile_order);
+        ra.splat = splat; ra.n_contrib = st->n_contrib; ra.dL_dcolor = dL_dcolor;
         ra.dL_dinvdepth = dL_dinvdepth; ra.dacc = dacc; ra.out_color = out_color; ra.out_invdepth = out_invdepth;
-        rc = opt_bwd_variant == 5 ? launch_render_bwd_ps(ra, debug, stream) : opt_bwd_variant >= 2 ? launch_render_bwd_mp(ra, opt_bwd_variant == 3 ? 4 : (opt_bwd_variant == 4 ? -2 : (opt_bwd_variant == 6 ? -12 : (opt_bwd_variant == 7 ? -16 : (opt_bwd_variant == 8 ? -20 : (opt_bwd_variant == 9 ? -21 : (opt_bwd_variant == 10 ? -22 : (opt_bwd_variant == 11 ? -23 : (opt_bwd_variant == 12 ? -24 : 2)))))))), debug, stream)
-                                  : launch_render_bwd(ra, opt_bwd_variant, debug, stream);
+        rc = launch_render_bwd(ra, debug, stream);
         if (rc) return rc;
     }
     PreBwdArgs pa;
     pa.P = P; pa.means = in->means3D; pa.shs = in->shs; pa.opac = in->opacities; pa.scales = in->scales; pa.rots = in->rotations;
     pa.cov_pre = in->cov3D_precomp; pa.splat = splat; pa.dacc = dacc; pa.g = *grads;
-    pa.moments = opt_bwd_variant >= 2 ? 1 : 0;
+    pa.p_begin = 0; pa.p_end = P;
     return launch_preprocess_bwd(cam, pa, accumulate != 0, debug, stream);
-}
-
-
-static int run_render_fwd(const RenderFwdArgs &ra, bool debug, cudaStream_t stream) {
-    if (opt_fwd_variant == 5) return launch_render_fwd_ps(ra, debug, stream);
-    return (opt_fwd_variant == 2 || opt_fwd_variant == 3) ? launch_render_fwd_mp(ra, opt_fwd_variant == 3 ? 4 : 2, debug, stream)
-                                                          : launch_render_fwd(ra, opt_fwd_variant, debug, stream);
-}
-
-static int run_render_bwd(const RenderBwdArgs &ra, bool debug, cudaStream_t stream) {
-    return opt_bwd_variant == 5 ? launch_render_bwd_ps(ra, debug, stream)
-           : opt_bwd_variant >= 2 ? launch_render_bwd_mp(ra, opt_bwd_variant == 3 ? 4 : (opt_bwd_variant == 4 ? -2 : (opt_bwd_variant == 6 ? -12 : (opt_bwd_variant == 7 ? -16 : (opt_bwd_variant == 8 ? -20 : (opt_bwd_variant == 9 ? -21 : (opt_bwd_variant == 10 ? -22 : (opt_bwd_variant == 11 ? -23 : (opt_bwd_variant == 12 ? -24 : 2)))))))), debug, stream)
-                                  : launch_render_bwd(ra, opt_bwd_variant, debug, stream);
 }
 
 static int check_batch(int32_t V, const GsbSettings *s, const GsbInputs *in, CamArgsBatch &cb) {
@@ -430,14 +422,12 @@ static int check_batch(int32_t V, const GsbSettings *s, const GsbInputs *in, Cam
     return GSB_OK;
 }
 
-int32_t gsb_forward_batch(int32_t V, const GsbSettings *s, const GsbInputs *in, float *out_color, int32_t *out_radii,
-                          float *out_invdepth, int64_t capacity_hint, gsb_alloc_fn alloc, void *alloc_ctx, GsbState *states,
-                          void *cuda_stream) {
-    if (!s || !in || !out_color || !out_radii || !out_invdepth || !alloc || !states || in->P <= 0) {
-        set_error("gsb_forward_batch: NULL argument or empty input");
-        return GSB_ERR_ARGUMENT;
-    }
-    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+// shared body of gsb_forward_batch (counts read back, capacity repaired) and gsb_forward_batch_async (no host
+// synchronisation at all: fixed capacity, counts and their running maximum stay on the device)
+static int forward_batch_impl(int32_t V, const GsbSettings *s, const GsbInputs *in, float *out_color, int32_t *out_radii,
+                              float *out_invdepth, int64_t capacity_hint, unsigned long long *counts_dev, gsb_alloc_fn alloc,
+                              void *alloc_ctx, GsbState *states, cudaStream_t stream) {
+    const bool async = counts_dev != nullptr;
     CamArgsBatch cb;
     int rc = check_batch(V, s, in, cb);
     if (rc) return rc;
@@ -484,6 +474,7 @@ int32_t gsb_forward_batch(int32_t V, const GsbSettings *s, const GsbInputs *in, 
     if (!scr0) return GSB_ERR_ALLOC;
     Carver c0r(scr0);
     carve0(c0r);
+    if (async) total = counts_dev;     // the caller's buffer: the counts outlive the call
 
     PreFwdArgs pa;
     pa.P = P; pa.means = in->means3D; pa.shs = in->shs; pa.colors = nullptr; pa.opac = in->opacities;
@@ -502,24 +493,34 @@ int32_t gsb_forward_batch(int32_t V, const GsbSettings *s, const GsbInputs *in, 
     ba.sv_gauss = Pn; ba.sv_splat = sv_splat; ba.sv_partials = np; ba.sv_inst = 0; ba.tile_count = nullptr;
     rc = launch_tile_scan(ba, V, debug, stream);
     if (rc) return rc;
-    unsigned long long *h = pinned_slot();
-    cudaEvent_t ev = readback_event();
-    if (!h || !ev) { set_error("pinned read-back slot unavailable"); return GSB_ERR_CUDA; }
-    GSB_CUDA(cudaMemcpyAsync(h, total, (size_t)V * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-    GSB_CUDA(cudaEventRecord(ev, stream));
+    unsigned long long *h = nullptr;
+    cudaEvent_t ev = nullptr;
+    if (async) {
+        rc = launch_count_max(total, V, debug, stream);     // counts_dev[GSB_MAX_VIEWS] = max(itself, the V counts)
+        if (rc) return rc;
+    } else {
+        h = pinned_slot();
+        ev = readback_event();
+        if (!h || !ev) { set_error("pinned read-back slot unavailable"); return GSB_ERR_CUDA; }
+        GSB_CUDA(cudaMemcpyAsync(h, total, (size_t)V * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        GSB_CUDA(cudaEventRecord(ev, stream));
+    }
 
     auto bin_and_blend = [&](int64_t cap) -> int {
-        // BINNING: [V][cap] point lists, then [V][num_tiles] ranges
+        // BINNING: [V][cap] point lists, then [V][num_tiles] ranges, then [V][num_tiles] tile order
         const size_t capn = (size_t)(cap > 0 ? cap : 1);
         const size_t pl_bytes = align_up((size_t)V * capn * 4, 256);
-        const size_t bin_bytes = pl_bytes + align_up((size_t)V * num_tiles * sizeof(uint2), 256);
+        const size_t rg_bytes = align_up((size_t)V * num_tiles * sizeof(uint2), 256);
+        const size_t bin_bytes = pl_bytes + rg_bytes + align_up((size_t)V * num_tiles * sizeof(uint32_t), 256);
         char *bin = static_cast<char *>(do_alloc(alloc, alloc_ctx, GSB_BUF_BINNING, bin_bytes));
         if (!bin) return GSB_ERR_ALLOC;
         uint32_t *point_list = reinterpret_cast<uint32_t *>(bin);
         uint2 *ranges = reinterpret_cast<uint2 *>(bin + pl_bytes);
+        uint32_t *tile_order = reinterpret_cast<uint32_t *>(bin + pl_bytes + rg_bytes);
         for (int v = 0; v < V; ++v) {
             states[v].binning = bin; states[v].binning_bytes = bin_bytes; states[v].binning_capacity = cap;
             states[v].point_list = point_list + (size_t)v * capn; states[v].ranges = ranges + (size_t)v * num_tiles;
+            states[v].tile_order = opt_tile_order ? tile_order + (size_t)v * num_tiles : nullptr;
         }
         int r;
         if (cap > 0) {
@@ -554,18 +555,25 @@ int32_t gsb_forward_batch(int32_t V, const GsbSettings *s, const GsbInputs *in, 
             r = launch_tile_ranges(nullptr, 0, nullptr, num_tiles, ranges, V, 0, debug, stream);
             if (r) return r;
         }
-        for (int v = 0; v < V; ++v) {
-            RenderFwdArgs ra;
-            ra.W = c0.W; ra.H = c0.H; ra.gx = c0.gx; ra.gy = c0.gy; ra.ranges = static_cast<const uint2 *>(states[v].ranges);
-            ra.point_list = states[v].point_list; ra.splat = static_cast<const float4 *>(states[v].splat); ra.bg = s[v].bg;
-            ra.out_color = out_color + (size_t)v * 3 * npix; ra.out_invdepth = out_invdepth + (size_t)v * npix;
-            ra.final_T = const_cast<float *>(states[v].final_T); ra.n_contrib = const_cast<uint32_t *>(states[v].n_contrib);
-            r = run_render_fwd(ra, debug, stream);
-            if (r) return r;
-        }
-        return GSB_OK;
+        r = maybe_tile_order(ranges, V, num_tiles, tile_order, debug, stream);
+        if (r) return r;
+        // ONE blend launch for the V views
+        RenderFwdArgs ra;
+        memset(&ra, 0, sizeof(ra));
+        ra.W = c0.W; ra.H = c0.H; ra.gx = c0.gx; ra.gy = c0.gy; ra.V = V;
+        ra.sv_ranges = (size_t)num_tiles; ra.sv_list = capn; ra.sv_splat = sv_splat; ra.sv_color = 3 * npix; ra.sv_depth = npix;
+        ra.sv_image = image_bytes / sizeof(float);
+        ra.ranges = ranges; ra.point_list = point_list; ra.tile_order = opt_tile_order ? tile_order : nullptr; ra.splat = splat;
+        for (int v = 0; v < V; ++v) ra.bg[v] = s[v].bg;
+        ra.out_color = out_color; ra.out_invdepth = out_invdepth;
+        ra.final_T = const_cast<float *>(states[0].final_T); ra.n_contrib = const_cast<uint32_t *>(states[0].n_contrib);
+        return launch_render_fwd(ra, debug, stream);
     };
 
+    if (async) {
+        for (int v = 0; v < V; ++v) states[v].num_rendered = -1;     // known to the device only
+        return bin_and_blend(capacity_hint);
+    }
     bool blended = false;
     if (capacity_hint > 0 && capacity_hint < (1ll << 30)) {
         rc = bin_and_blend(capacity_hint);
@@ -586,14 +594,38 @@ int32_t gsb_forward_batch(int32_t V, const GsbSettings *s, const GsbInputs *in, 
     return GSB_OK;
 }
 
-int32_t gsb_backward_batch(int32_t V, const GsbSettings *s, const GsbInputs *in, const GsbState *states, const float *out_color,
-                           const float *out_invdepth, const float *dL_dcolor, const float *dL_dinvdepth, const GsbGrads *grads,
-                           int32_t accumulate, gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream) {
-    if (!s || !in || !states || !out_color || !out_invdepth || !dL_dcolor || !grads || !alloc || in->P <= 0) {
-        set_error("gsb_backward_batch: NULL argument or empty input");
+int32_t gsb_forward_batch(int32_t V, const GsbSettings *s, const GsbInputs *in, float *out_color, int32_t *out_radii,
+                          float *out_invdepth, int64_t capacity_hint, gsb_alloc_fn alloc, void *alloc_ctx, GsbState *states,
+                          void *cuda_stream) {
+    if (!s || !in || !out_color || !out_radii || !out_invdepth || !alloc || !states || in->P <= 0) {
+        set_error("gsb_forward_batch: NULL argument or empty input");
         return GSB_ERR_ARGUMENT;
     }
-    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    return forward_batch_impl(V, s, in, out_color, out_radii, out_invdepth, capacity_hint, nullptr, alloc, alloc_ctx, states,
+                              static_cast<cudaStream_t>(cuda_stream));
+}
+
+int32_t gsb_forward_batch_async(int32_t V, const GsbSettings *s, const GsbInputs *in, float *out_color, int32_t *out_radii,
+                                float *out_invdepth, int64_t capacity, uint64_t *counts_dev, gsb_alloc_fn alloc, void *alloc_ctx,
+                                GsbState *states, void *cuda_stream) {
+    if (!s || !in || !out_color || !out_radii || !out_invdepth || !alloc || !states || in->P <= 0 || !counts_dev) {
+        set_error("gsb_forward_batch_async: NULL argument or empty input");
+        return GSB_ERR_ARGUMENT;
+    }
+    if (capacity <= 0 || capacity >= (1ll << 30)) {
+        set_error("gsb_forward_batch_async: capacity %lld outside 1..2^30-1", (long long)capacity);
+        return GSB_ERR_ARGUMENT;
+    }
+    static_assert(sizeof(uint64_t) == sizeof(unsigned long long), "count type");
+    return forward_batch_impl(V, s, in, out_color, out_radii, out_invdepth, capacity, reinterpret_cast<unsigned long long *>(counts_dev),
+                              alloc, alloc_ctx, states, static_cast<cudaStream_t>(cuda_stream));
+}
+
+// shared body of gsb_backward_batch / gsb_backward_batch_chunked
+static int backward_batch_impl(int32_t V, const GsbSettings *s, const GsbInputs *in, const GsbState *states, const float *out_color,
+                               const float *out_invdepth, const float *dL_dcolor, const float *dL_dinvdepth, const GsbGrads *grads,
+                               int32_t accumulate, int32_t n_chunks, gsb_chunk_fn on_chunk, void *chunk_ctx, gsb_alloc_fn alloc,
+                               void *alloc_ctx, cudaStream_t stream) {
     CamArgsBatch cb;
     int rc = check_batch(V, s, in, cb);
     if (rc) return rc;
@@ -601,36 +633,80 @@ int32_t gsb_backward_batch(int32_t V, const GsbSettings *s, const GsbInputs *in,
     const CamArgs &c0 = cb.cam[0];
     const int P = in->P;
     const size_t npix = (size_t)c0.W * c0.H;
+    bool any = false, uniform = true;
     for (int v = 0; v < V; ++v) {
         if (states[v].P != P || states[v].num_tiles != c0.gx * c0.gy || !states[v].splat || !states[v].ranges || !states[v].final_T) {
             set_error("gsb_backward_batch: state %d does not match the inputs", v);
             return GSB_ERR_ARGUMENT;
         }
+        any = any || states[v].num_rendered != 0;
+        // the batched blend launch addresses view v at base + v * stride: the states must come from ONE forward_batch call
+        if (v > 0 && (states[v].binning != states[0].binning || states[v].image != states[0].image || states[v].geom != states[0].geom))
+            uniform = false;
     }
+    if (!uniform) { set_error("gsb_backward_batch: states of different forward calls"); return GSB_ERR_ARGUMENT; }
     const size_t sv_dacc = (size_t)P * DACC_STRIDE;
     const size_t dacc_bytes = align_up((size_t)V * sv_dacc * sizeof(float), 256);
     float *dacc = static_cast<float *>(do_alloc(alloc, alloc_ctx, GSB_BUF_SCRATCH0, dacc_bytes));
     if (!dacc) return GSB_ERR_ALLOC;
     GSB_CUDA(cudaMemsetAsync(dacc, 0, dacc_bytes, stream));
-    for (int v = 0; v < V; ++v) {
-        if (states[v].num_rendered <= 0) continue;
+    const size_t sv_splat = V > 1 ? (size_t)((const float4 *)states[1].splat - (const float4 *)states[0].splat) : 0;
+    if (any) {
         RenderBwdArgs ra;
-        ra.W = c0.W; ra.H = c0.H; ra.gx = c0.gx; ra.gy = c0.gy; ra.ranges = static_cast<const uint2 *>(states[v].ranges);
-        ra.point_list = states[v].point_list; ra.splat = static_cast<const float4 *>(states[v].splat); ra.bg = s[v].bg;
-        ra.final_T = states[v].final_T; ra.n_contrib = states[v].n_contrib;
-        ra.dL_dcolor = dL_dcolor + (size_t)v * 3 * npix; ra.dL_dinvdepth = dL_dinvdepth ? dL_dinvdepth + (size_t)v * npix : nullptr;
-        ra.dacc = dacc + (size_t)v * sv_dacc; ra.out_color = out_color + (size_t)v * 3 * npix; ra.out_invdepth = out_invdepth + (size_t)v * npix;
-        rc = run_render_bwd(ra, debug, stream);
+        memset(&ra, 0, sizeof(ra));
+        ra.W = c0.W; ra.H = c0.H; ra.gx = c0.gx; ra.gy = c0.gy; ra.V = V;
+        if (V > 1) {
+            ra.sv_ranges = (size_t)((const uint2 *)states[1].ranges - (const uint2 *)states[0].ranges);
+            ra.sv_list = (size_t)(states[1].point_list - states[0].point_list);
+            ra.sv_image = (size_t)(states[1].n_contrib - states[0].n_contrib);
+        }
+        ra.sv_splat = sv_splat; ra.sv_color = 3 * npix; ra.sv_depth = npix; ra.sv_dacc = sv_dacc;
+        ra.ranges = static_cast<const uint2 *>(states[0].ranges); ra.point_list = states[0].point_list;
+        ra.tile_order = static_cast<const uint32_t *>(states[0].tile_order);
+        ra.splat = static_cast<const float4 *>(states[0].splat); ra.n_contrib = states[0].n_contrib;
+        ra.dL_dcolor = dL_dcolor; ra.dL_dinvdepth = dL_dinvdepth; ra.dacc = dacc; ra.out_color = out_color; ra.out_invdepth = out_invdepth;
+        rc = launch_render_bwd(ra, debug, stream);
         if (rc) return rc;
     }
     PreBwdArgs pa;
     pa.P = P; pa.means = in->means3D; pa.shs = in->shs; pa.opac = in->opacities; pa.scales = in->scales; pa.rots = in->rotations;
     pa.cov_pre = nullptr; pa.splat = static_cast<const float4 *>(states[0].splat); pa.dacc = dacc; pa.g = *grads;
-    pa.moments = opt_bwd_variant >= 2 ? 1 : 0;
     PreBwdBatchStrides ps;
-    ps.splat = (size_t)((const float4 *)states[V > 1 ? 1 : 0].splat - (const float4 *)states[0].splat);
-    ps.dacc = sv_dacc; ps.means2D = (size_t)P * 3;
-    return launch_preprocess_bwd_batch(cb, pa, ps, accumulate != 0, debug, stream);
+    ps.splat = sv_splat; ps.dacc = sv_dacc; ps.means2D = (size_t)P * 3;
+    // gaussian-range chunks: chunk c's gradients are final when its launch completes, so the caller can start reducing
+    // them (on_chunk: e.g. enqueue an all-reduce of the chunk's rows on another stream) while the next chunk computes
+    if (n_chunks < 1) n_chunks = 1;
+    const int step = (int)align_up((size_t)ceil_div(P, n_chunks), 256);
+    for (int c = 0, p0 = 0; p0 < P; ++c, p0 += step) {
+        pa.p_begin = p0; pa.p_end = p0 + step < P ? p0 + step : P;
+        rc = launch_preprocess_bwd_batch(cb, pa, ps, accumulate != 0, debug, stream);
+        if (rc) return rc;
+        if (on_chunk) on_chunk(chunk_ctx, c, pa.p_begin, pa.p_end);
+    }
+    return GSB_OK;
+}
+
+int32_t gsb_backward_batch(int32_t V, const GsbSettings *s, const GsbInputs *in, const GsbState *states, const float *out_color,
+                           const float *out_invdepth, const float *dL_dcolor, const float *dL_dinvdepth, const GsbGrads *grads,
+                           int32_t accumulate, gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream) {
+    if (!s || !in || !states || !out_color || !out_invdepth || !dL_dcolor || !grads || !alloc || in->P <= 0) {
+        set_error("gsb_backward_batch: NULL argument or empty input");
+        return GSB_ERR_ARGUMENT;
+    }
+    return backward_batch_impl(V, s, in, states, out_color, out_invdepth, dL_dcolor, dL_dinvdepth, grads, accumulate, 1, nullptr, nullptr,
+                               alloc, alloc_ctx, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int32_t gsb_backward_batch_chunked(int32_t V, const GsbSettings *s, const GsbInputs *in, const GsbState *states, const float *out_color,
+                                   const float *out_invdepth, const float *dL_dcolor, const float *dL_dinvdepth, const GsbGrads *grads,
+                                   int32_t accumulate, int32_t n_chunks, gsb_chunk_fn on_chunk, void *chunk_ctx, gsb_alloc_fn alloc,
+                                   void *alloc_ctx, void *cuda_stream) {
+    if (!s || !in || !states || !out_color || !out_invdepth || !dL_dcolor || !grads || !alloc || in->P <= 0 || n_chunks < 1 || n_chunks > 64) {
+        set_error("gsb_backward_batch_chunked: NULL argument, empty input or n_chunks outside 1..64");
+        return GSB_ERR_ARGUMENT;
+    }
+    return backward_batch_impl(V, s, in, states, out_color, out_invdepth, dL_dcolor, dL_dinvdepth, grads, accumulate, n_chunks, on_chunk,
+                               chunk_ctx, alloc, alloc_ctx, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int32_t gsb_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,

@@ -110,6 +110,17 @@ int launch_tile_scan(const BinArgs &a, int V, bool debug, cudaStream_t stream) {
     return GSB_OK;
 }
 
+__global__ void count_max_kernel(unsigned long long *counts, const int V) {
+    unsigned long long m = counts[GSB_MAX_VIEWS];
+    for (int v = 0; v < V; ++v) m = counts[v] > m ? counts[v] : m;
+    counts[GSB_MAX_VIEWS] = m;
+}
+
+int launch_count_max(unsigned long long *counts, int V, bool debug, cudaStream_t stream) {
+    GSB_LAUNCH("count_max", debug, stream, count_max_kernel, 1, 1, 0, counts, V);
+    return GSB_OK;
+}
+
 // K3: one thread per depth rank; writes (tile id, gaussian id) for every tile the gaussian's cull ellipse meets.
 __global__ void __launch_bounds__(256)
 emit_kernel(BinArgs a, uint32_t *__restrict__ inst_tile, uint32_t *__restrict__ inst_gauss, const uint32_t cap) {

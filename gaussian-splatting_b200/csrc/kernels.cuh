@@ -6,7 +6,7 @@
 namespace gsb {
 
 // per-gaussian gradient accumulator written by the backward blend kernel (float, 48 B stride):
-//   0,1 mean2D (NDC-scaled)  2,3,4 conic A,B,C  5 opacity  6,7,8 rgb  9 inverse depth  10,11 pad
+//   0..4 raw moments of t = dL/d(power): sum t dx, t dy, t dx^2, t dx dy, t dy^2   5 opacity  6,7,8 rgb  9 inverse depth  10,11 pad
 constexpr int DACC_STRIDE = 12;
 
 // ---- view-batch variants: per-view arrays are laid out [V][...] with uniform strides (in elements) ----
@@ -35,7 +35,7 @@ struct PreBwdArgs {
     const float *means, *shs, *opac, *scales, *rots, *cov_pre;
     const float4 *splat;
     const float *dacc;    // [P*DACC_STRIDE]
-    int moments;          // dacc[0..4] hold raw moments of d(power) (render_mp.cu) instead of mean/conic gradients
+    int p_begin, p_end;   // gaussian range of this launch (chunked backward: the caller reduces finished chunks meanwhile)
     GsbGrads g;
 };
 
@@ -57,23 +57,27 @@ struct BinArgs {
     uint32_t *tile_count;     // option fused_ranges: [V][num_tiles + 1] instance counters filled by emit (NULL = off)
 };
 
+// Blend launches cover V views (blockIdx.y): every per-view array is base + view * stride (strides in elements; 0 and V = 1
+// for the single-view call).  tile_order (optional, [V][tiles]): blockIdx.x -> tile id permutation (heavy tiles first).
 struct RenderFwdArgs {
-    int W, H, gx, gy;
+    int W, H, gx, gy, V;
+    size_t sv_ranges, sv_list, sv_splat /* float4 */, sv_color, sv_depth, sv_image;
     const uint2 *ranges;
     const uint32_t *point_list;
+    const uint32_t *tile_order;
     const float4 *splat;
-    const float *bg;
+    const float *bg[GSB_MAX_VIEWS];
     float *out_color, *out_invdepth, *final_T;
     uint32_t *n_contrib;
 };
 
 struct RenderBwdArgs {
-    int W, H, gx, gy;
+    int W, H, gx, gy, V;
+    size_t sv_ranges, sv_list, sv_splat /* float4 */, sv_color, sv_depth, sv_image, sv_dacc;
     const uint2 *ranges;
     const uint32_t *point_list;
+    const uint32_t *tile_order;
     const float4 *splat;
-    const float *bg;
-    const float *final_T;
     const uint32_t *n_contrib;
     const float *out_color, *out_invdepth;   // forward outputs
     const float *dL_dcolor, *dL_dinvdepth;
@@ -90,6 +94,8 @@ int launch_mark_visible(int P, const float *means, const float *view, uint8_t *p
 size_t scan_partials_count(int P);
 // V > 1: blockIdx.y = view, arrays offset by the BinArgs strides; totals / n_dev are arrays of V counts
 int launch_tile_scan(const BinArgs &a, int V, bool debug, cudaStream_t stream);
+// async forward: counts[GSB_MAX_VIEWS] = max(counts[GSB_MAX_VIEWS], counts[0..V))  (running maximum the host polls later)
+int launch_count_max(unsigned long long *counts, int V, bool debug, cudaStream_t stream);
 int launch_emit(const BinArgs &a, int V, uint32_t *inst_tile, uint32_t *inst_gauss, int64_t cap, bool debug, cudaStream_t stream);
 // option fused_ranges: tile ranges AND the tile sort's digit histograms from the per-tile counters emit filled
 // (replaces tile_ranges' pass over the D sorted keys and the sort's histogram pass over the D unsorted ones)
@@ -98,16 +104,13 @@ int launch_ranges_from_counts(const uint32_t *tile_count, int V, int num_tiles, 
 int launch_tile_ranges(const uint32_t *sorted_tiles, int64_t D, const unsigned long long *n_dev, int num_tiles,
                        uint2 *ranges, int V, size_t sv_inst, bool debug, cudaStream_t stream);
 
-int launch_render_fwd(const RenderFwdArgs &a, int variant, bool debug, cudaStream_t stream);
-int launch_render_bwd(const RenderBwdArgs &a, int variant, bool debug, cudaStream_t stream);
-int launch_render_fwd_mp(const RenderFwdArgs &a, int qh, bool debug, cudaStream_t stream);
-int launch_render_bwd_mp(const RenderBwdArgs &a, int qh, bool debug, cudaStream_t stream);
+int launch_render_fwd(const RenderFwdArgs &a, bool debug, cudaStream_t stream);
+int launch_render_bwd(const RenderBwdArgs &a, bool debug, cudaStream_t stream);
+int launch_tile_order(const uint2 *ranges, int V, int num_tiles, uint32_t *order, bool debug, cudaStream_t stream);
 int launch_l1_loss_grad(const float *img, const float *gt, int64_t n, float scale, float *grad, float *loss_accum,
                         cudaStream_t stream);
 int launch_photometric_loss_grad(const float *img, const float *gt, int C, int H, int W, float lambda_dssim, float *grad,
                                  float *loss_accum, float *maps, cudaStream_t stream);
-int launch_render_fwd_ps(const RenderFwdArgs &a, bool debug, cudaStream_t stream);
-int launch_render_bwd_ps(const RenderBwdArgs &a, bool debug, cudaStream_t stream);
 
 // optimizer step and densification on the flat store (optim.cu, densify.cu)
 int launch_adam_step(int64_t P, int sh_coeffs, float *params, const float *grads, float *m, float *v, float *act,

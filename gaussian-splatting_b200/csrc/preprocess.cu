@@ -273,17 +273,13 @@ __device__ __forceinline__ bool preprocess_bwd_view(const CamParams &cam, const 
         if (A0.x == 0.f && A0.y == 0.f && A0.z == 0.f && A0.w == 0.f && A1.x == 0.f && A1.y == 0.f && A1.z == 0.f && A1.w == 0.f &&
             A2.x == 0.f && A2.y == 0.f)
             return false;
-        float d_m2x = A0.x, d_m2y = A0.y;
-        float dA = A0.z, dB = A0.w, dC = A1.x;
-        if (a.moments) {
-            // raw moments of t = dL/d(power):  sum t dx, t dy, t dx^2, t dx dy, t dy^2   (render_mp.cu)
-            const float4 r0 = a.splat[(size_t)i * SPLAT_F4], r1 = a.splat[(size_t)i * SPLAT_F4 + 1];
-            const float cA = r0.z, cB = r0.w, cC = r1.x;
-            const float Mx = A0.x, My = A0.y, Mxx = A0.z, Mxy = A0.w, Myy = A1.x;
-            d_m2x = (-cA * Mx - cB * My) * (0.5f * cam.W);
-            d_m2y = (-cC * My - cB * Mx) * (0.5f * cam.H);
-            dA = -0.5f * Mxx; dB = -Mxy; dC = -0.5f * Myy;
-        }
+        // the accumulator holds raw moments of t = dL/d(power):  sum t dx, t dy, t dx^2, t dx dy, t dy^2   (render.cu)
+        const float4 r0 = a.splat[(size_t)i * SPLAT_F4], r1 = a.splat[(size_t)i * SPLAT_F4 + 1];
+        const float cA = r0.z, cB = r0.w, cC = r1.x;
+        const float Mx = A0.x, My = A0.y, Mxx = A0.z, Mxy = A0.w, Myy = A1.x;
+        const float d_m2x = (-cA * Mx - cB * My) * (0.5f * cam.W);
+        const float d_m2y = (-cC * My - cB * Mx) * (0.5f * cam.H);
+        const float dA = -0.5f * Mxx, dB = -Mxy, dC = -0.5f * Myy;
         const float d_w = A1.y;
         const float d_rgb[3] = {A1.z, A1.w, A2.x};
         const float d_invd = A2.y;
@@ -462,14 +458,14 @@ preprocess_bwd_kernel(const CamArgs ca, const PreBwdArgs a) {
     __shared__ CamParams cam;
     GSB_DYNAMIC_SMEM(float, sh_rows);
     load_cam(ca, cam);
-    const int row0 = blockIdx.x * PRE_THREADS;
-    const int nrows = min(PRE_THREADS, a.P - row0);
+    const int row0 = a.p_begin + blockIdx.x * PRE_THREADS;      // gaussians [p_begin, p_end) of this launch
+    const int nrows = min(PRE_THREADS, a.p_end - row0);
     const int shn = 3 * ca.sh_coeffs;
     const int nb = (ca.sh_degree + 1) * (ca.sh_degree + 1);
     if (a.shs) stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * nb);
     __syncthreads();
     const int i = row0 + threadIdx.x;
-    const bool live = i < a.P;
+    const bool live = i < a.p_end;
     const int M = cam.sh_coeffs;
     float *sh_row = sh_rows + threadIdx.x * sh_row_stride(shn);
     ViewGrad g;
@@ -507,15 +503,15 @@ preprocess_bwd_batch_kernel(const CamArgsBatch cb, const PreBwdArgs a, const Pre
     __shared__ CamParams cams[GSB_MAX_VIEWS];
     GSB_DYNAMIC_SMEM(float, sh_rows);
     for (int v = 0; v < cb.V; ++v) load_cam(cb.cam[v], cams[v]);
-    const int row0 = blockIdx.x * PRE_THREADS;
-    const int nrows = min(PRE_THREADS, a.P - row0);
+    const int row0 = a.p_begin + blockIdx.x * PRE_THREADS;      // gaussians [p_begin, p_end) of this launch
+    const int nrows = min(PRE_THREADS, a.p_end - row0);
     const int shn = 3 * cb.cam[0].sh_coeffs;
     const int nb = (cb.cam[0].sh_degree + 1) * (cb.cam[0].sh_degree + 1);
     float *grad_rows = sh_rows + PRE_THREADS * sh_row_stride(shn);
     if (a.shs) stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * nb);
     __syncthreads();
     const int i = row0 + threadIdx.x;
-    const bool live = i < a.P;
+    const bool live = i < a.p_end;
     const int M = cb.cam[0].sh_coeffs;
     const float *sh_row = sh_rows + threadIdx.x * sh_row_stride(shn);
     float *gr = grad_rows + threadIdx.x * sh_row_stride(shn);
@@ -597,8 +593,8 @@ int launch_preprocess_fwd(const CamArgs &ca, const PreFwdArgs &a, bool debug, cu
 }
 
 int launch_preprocess_bwd(const CamArgs &ca, const PreBwdArgs &a, bool accumulate, bool debug, cudaStream_t stream) {
-    if (a.P <= 0) return GSB_OK;
-    const int grid = (int)ceil_div(a.P, PRE_THREADS);
+    if (a.P <= 0 || a.p_end <= a.p_begin) return GSB_OK;
+    const int grid = (int)ceil_div(a.p_end - a.p_begin, PRE_THREADS);
     const size_t smem = a.shs ? (size_t)PRE_THREADS * ((3 * ca.sh_coeffs) | 1) * sizeof(float) : 0;
     if (accumulate) {
         if (smem > 48 * 1024) GSB_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -620,8 +616,8 @@ int launch_preprocess_fwd_batch(const CamArgsBatch &cb, const PreFwdArgs &a, con
 
 int launch_preprocess_bwd_batch(const CamArgsBatch &cb, const PreBwdArgs &a, const PreBwdBatchStrides &st, bool accumulate, bool debug,
                                 cudaStream_t stream) {
-    if (a.P <= 0) return GSB_OK;
-    const int grid = (int)ceil_div(a.P, PRE_THREADS);
+    if (a.P <= 0 || a.p_end <= a.p_begin) return GSB_OK;
+    const int grid = (int)ceil_div(a.p_end - a.p_begin, PRE_THREADS);
     const size_t smem = a.shs ? 2 * (size_t)PRE_THREADS * ((3 * cb.cam[0].sh_coeffs) | 1) * sizeof(float) : 0;
     if (accumulate) {
         if (smem > 40 * 1024) GSB_CUDA(cudaFuncSetAttribute(preprocess_bwd_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1,107 +1,88 @@
-// render.cu -- one-pixel-per-thread blend kernels.  The DEFAULT forward kernel (K6) lives here:
-// render_fwd_pc_kernel (8x4 pixel patch per warp, sub-tile culling, log2-domain exponent; fwd variant 6).
-// render_fwd_kernel / render_bwd_kernel are the round's first versions (back-to-front recursion with butterfly
-// reductions), kept as the A/B baseline of DESIGN.md section 4; render_fwd_pc2_kernel is a rejected experiment.
+// render.cu -- the blend kernels (K6 forward, K7 backward).  One launch covers all V views of a batch
+// (blockIdx.y = view, blockIdx.x = position in the tile order), so the V tails of a per-view launch sequence
+// collapse into one.
 //
-// Replaces FORWARD::renderCUDA / BACKWARD::renderCUDA of the reference's
-// cuda_rasterizer/{forward,backward}.cu (named in BASELINE.json north_star; absent from
-// /root/reference).  Blend rules restated in oracle/gs_oracle.c.
+// Replaces FORWARD::renderCUDA / BACKWARD::renderCUDA of the reference's cuda_rasterizer/{forward,backward}.cu
+// (named in BASELINE.json north_star; absent from /root/reference).  Blend rules restated in
+// oracle/gs_oracle.c.
 //
-// Data movement: a tile's sorted gaussian ids are contiguous in point_list; the 48-byte splat
-// records they point to are gathered from the L2-resident record table (P * 48 B) into shared
-// memory 256 at a time.  One 16x16 tile per CTA; a warp owns an 8x4 pixel patch so that a gaussian
-// which misses the patch is skipped by the whole warp.
+// Data movement: a tile's sorted gaussian ids are contiguous in point_list; the 48-byte splat records they point
+// to are gathered from the L2-resident record table (P * 48 B) into shared memory, 256 (forward) / 128 (backward)
+// at a time.  One 16x16 tile per CTA.  While a record is staged its 2 ln(255 o) ellipse is intersected with the
+// eight 8x4 patches of the tile (patch_cull.cuh); every warp walks only the records that reach its own pixels.
+//
+// Forward (render_fwd_kernel): one pixel per thread, a warp owns an 8x4 patch; exponent in the log2 domain (conic
+// pre-scaled while staging): one MUFU.EX2 per (pixel, gaussian).
+//
+// Backward (render_bwd_kernel): 2x2 pixels per thread (a warp owns a 16x8 band), so the shared-memory reads, loop
+// overhead and the cross-lane reduction of the ten per-gaussian gradient terms are paid once per four pixels; the
+// two pixels of a row share every per-gaussian operand and run as packed f32x2 instructions (FFMA2).  The pass walks
+// FRONT to back with two scalars of state per pixel (T and the running dL-weighted front colour F) instead of the
+// ten the back-to-front recursion carries:
+//     dL/dalpha_k = T_k g_k - (S - F_k) / (1 - alpha_k),   g_k = dLdC . c_k + dLdD / z_k,
+//     S = dLdC . C_out + dLdD D_out,   F_k = sum_{j<=k} alpha_j T_j g_j
+// (algebraically the recursion of oracle/gs_oracle.c; background enters through C_out).  The geometric gradient
+// terms are accumulated as raw moments of d(power) (sum t dx, t dy, t dx^2, t dx dy, t dy^2) and turned into
+// mean / conic gradients once per gaussian in preprocess_bwd.
+// The round-1 history of both kernels (v0 one-pixel back-to-front pair, scalar 2x2, patch-slot and prefetch
+// variants, all measured slower) is in git (render.cu / render_mp.cu / render_ps.cu before round 2) and DESIGN.md.
 #include "blend_common.cuh"
 
 namespace gsb {
 
-constexpr int RB = 256;  // gaussians staged per round
+constexpr int RB = 256;  // gaussians staged per round, forward
 
-__device__ __forceinline__ void pixel_of_thread(const int tile_x, const int tile_y, int &px, int &py) {
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    px = tile_x * TILE + (w & 1) * 8 + (l & 7);
-    py = tile_y * TILE + (w >> 1) * 4 + (l >> 3);
+// per-view base pointers of a batched launch (blockIdx.y = view)
+struct FwdView {
+    const uint2 *ranges;
+    const uint32_t *point_list, *order;
+    const float4 *splat;
+    const float *bg;
+    float *out_color, *out_invdepth, *final_T;
+    uint32_t *n_contrib;
+};
+
+__device__ __forceinline__ const float *select_bg(const float *const (&bg)[GSB_MAX_VIEWS], const int v) {
+    const float *p = bg[0];
+#pragma unroll
+    for (int k = 1; k < GSB_MAX_VIEWS; ++k)
+        if (k == v) p = bg[k];
+    return p;
 }
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ FwdView fwd_view(const RenderFwdArgs &a) {
+    const size_t v = blockIdx.y;
+    FwdView f;
+    f.ranges = a.ranges + v * a.sv_ranges;
+    f.point_list = a.point_list + v * a.sv_list;
+    f.order = a.tile_order ? a.tile_order + v * a.sv_ranges : nullptr;
+    f.splat = a.splat + v * a.sv_splat;
+    f.bg = select_bg(a.bg, (int)v);
+    f.out_color = a.out_color + v * a.sv_color;
+    f.out_invdepth = a.out_invdepth + v * a.sv_depth;
+    f.final_T = a.final_T + v * a.sv_image;
+    f.n_contrib = a.n_contrib + v * a.sv_image;
+    return f;
+}
+
+__global__ void __launch_bounds__(256, 6)
 render_fwd_kernel(const RenderFwdArgs a) {
-    __shared__ float4 s0[RB], s1[RB], s2[RB];
-    const int tile = blockIdx.x;
-    const int tile_x = tile % a.gx, tile_y = tile / a.gx;
-    int px, py;
-    pixel_of_thread(tile_x, tile_y, px, py);
-    const bool inside = px < a.W && py < a.H;
-    const float fx = (float)px, fy = (float)py;
-    const uint2 range = a.ranges[tile];
-    const int todo = (int)(range.y - range.x);
-    const int rounds = (todo + RB - 1) / RB;
-
-    bool done = !inside;
-    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
-    uint32_t contributor = 0, last = 0;
-
-    for (int rd = 0; rd < rounds; ++rd) {
-        if (__syncthreads_count(done) == 256) break;
-        const int idx = rd * RB + threadIdx.x;
-        if (idx < todo) {
-            const uint32_t g = a.point_list[range.x + idx];
-            const float4 *rec = a.splat + (size_t)g * SPLAT_F4;
-            s0[threadIdx.x] = __ldg(rec);
-            s1[threadIdx.x] = __ldg(rec + 1);
-            s2[threadIdx.x] = __ldg(rec + 2);
-        }
-        __syncthreads();
-        const int n = min(RB, todo - rd * RB);
-        for (int j = 0; !done && j < n; ++j) {
-            ++contributor;
-            const float4 q0 = s0[j];
-            const float4 q1 = s1[j];
-            const float dx = q0.x - fx, dy = q0.y - fy;
-            const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
-            if (power > 0.0f) continue;
-            const float alpha = fminf(ALPHA_MAX, q1.y * __expf(power));
-            if (alpha < ALPHA_MIN) continue;
-            const float test_T = T * (1.0f - alpha);
-            if (test_T < T_STOP) { done = true; continue; }
-            const float4 q2 = s2[j];
-            const float w = alpha * T;
-            C0 += q1.z * w; C1 += q1.w * w; C2 += q2.x * w;
-            Dp += q2.y * w;
-            T = test_T;
-            last = contributor;
-        }
-    }
-    if (inside) {
-        const size_t pid = (size_t)py * a.W + px, HW = (size_t)a.W * a.H;
-        a.final_T[pid] = T;
-        a.n_contrib[pid] = last;
-        a.out_color[pid] = C0 + T * __ldg(a.bg);
-        a.out_color[HW + pid] = C1 + T * __ldg(a.bg + 1);
-        a.out_color[2 * HW + pid] = C2 + T * __ldg(a.bg + 2);
-        a.out_invdepth[pid] = Dp;
-    }
-}
-
-// forward with sub-tile culling: each warp (8x4 patch) walks only the staged gaussians whose cull ellipse
-// meets its patch (patch_cull.cuh).  Blend arithmetic identical to render_fwd_kernel.
-template <int MINB, bool PREFETCH>
-__global__ void __launch_bounds__(256, MINB)
-render_fwd_pc_kernel(const RenderFwdArgs a) {
     __shared__ float4 s0[RB], s1[RB];
     __shared__ float2 s2[RB];
     __shared__ uint8_t smask[RB];
     __shared__ uint8_t slist[8][RB];
-    const int tile = blockIdx.x;
+    const FwdView f = fwd_view(a);
+    const int tile = f.order ? (int)f.order[blockIdx.x] : (int)blockIdx.x;
     const int tile_x = tile % a.gx, tile_y = tile / a.gx;
-    int px, py;
-    pixel_of_thread(tile_x, tile_y, px, py);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const int px = tile_x * TILE + (w & 1) * 8 + (l & 7);
+    const int py = tile_y * TILE + (w >> 1) * 4 + (l >> 3);
     const bool inside = px < a.W && py < a.H;
     const float fx = (float)px, fy = (float)py;
     const float ox = (float)(tile_x * TILE), oy = (float)(tile_y * TILE);
-    const uint2 range = a.ranges[tile];
+    const uint2 range = f.ranges[tile];
     const int todo = (int)(range.y - range.x);
     const int rounds = (todo + RB - 1) / RB;
-    const int w = threadIdx.x >> 5;
 
     bool done = !inside;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
@@ -111,8 +92,8 @@ render_fwd_pc_kernel(const RenderFwdArgs a) {
         if (__syncthreads_count(done) == 256) break;
         const int idx = rd * RB + threadIdx.x;
         if (idx < todo) {
-            const uint32_t g = a.point_list[range.x + idx];
-            const float4 *rec = a.splat + (size_t)g * SPLAT_F4;
+            const uint32_t g = f.point_list[range.x + idx];
+            const float4 *rec = f.splat + (size_t)g * SPLAT_F4;
             float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
             const float4 q2 = __ldg(rec + 2);
             smask[threadIdx.x] = (uint8_t)patch_mask(q0.x, q0.y, q0.z, q0.w, q1.x, q2.z, ox, oy);
@@ -122,21 +103,11 @@ render_fwd_pc_kernel(const RenderFwdArgs a) {
         __syncthreads();
         const int n = min(RB, todo - rd * RB);
         const int cnt = compact_hits(smask, n, 1u << w, slist[w]);
-        // PREFETCH: the next list entry's record is read from shared memory while the current one is blended
-        int jn = 0;
-        float4 q0n = make_float4(0.f, 0.f, 0.f, 0.f), q1n = q0n;
-        if (PREFETCH && cnt > 0) { jn = slist[w][0]; q0n = s0[jn]; q1n = s1[jn]; }
         for (int k = 0; !done && k < cnt; ++k) {
-            int j;
-            float4 q0, q1;
-            if (PREFETCH) {
-                j = jn; q0 = q0n; q1 = q1n;
-                if (k + 1 < cnt) { jn = slist[w][k + 1]; q0n = s0[jn]; q1n = s1[jn]; }
-            } else {
-                j = slist[w][k]; q0 = s0[j]; q1 = s1[j];
-            }
+            const int j = slist[w][k];
+            const float4 q0 = s0[j], q1 = s1[j];
             const float dx = q0.x - fx, dy = q0.y - fy;
-            // same operation order as render_mp.cu / render_ps.cu, so forward and backward agree bit for bit on alpha
+            // same operation order as the backward kernel, so both passes agree bit for bit on alpha
             const float power = power2_at(__fmul_rn(__fmul_rn(q0.z, dx), dx), __fmul_rn(__fmul_rn(q1.x, dy), dy), __fmul_rn(q0.w, dx), dy);
             if (power > 0.0f) continue;
             const float alpha = fminf(ALPHA_MAX, __fmul_rn(q1.y, ex2_approx(power)));
@@ -153,279 +124,246 @@ render_fwd_pc_kernel(const RenderFwdArgs a) {
     }
     if (inside) {
         const size_t pid = (size_t)py * a.W + px, HW = (size_t)a.W * a.H;
-        a.final_T[pid] = T;
-        a.n_contrib[pid] = last;
-        a.out_color[pid] = C0 + T * __ldg(a.bg);
-        a.out_color[HW + pid] = C1 + T * __ldg(a.bg + 1);
-        a.out_color[2 * HW + pid] = C2 + T * __ldg(a.bg + 2);
-        a.out_invdepth[pid] = Dp;
+        f.final_T[pid] = T;
+        f.n_contrib[pid] = last;
+        f.out_color[pid] = C0 + T * __ldg(f.bg);
+        f.out_color[HW + pid] = C1 + T * __ldg(f.bg + 1);
+        f.out_color[2 * HW + pid] = C2 + T * __ldg(f.bg + 2);
+        f.out_invdepth[pid] = Dp;
     }
 }
 
-// Forward, two pixels per lane: a warp owns one 16x4 band of the tile (both 8x4 patches of that band); lane l
-// blends pixels (l & 7, l >> 3) of the left and of the right patch, i.e. two pixels 8 columns apart that share dy and
-// every per-gaussian operand, so their FP32 arithmetic runs as packed f32x2 instructions (FFMA2).  Culling stays at
-// patch granularity through the staged 8-bit mask: a warp walks the gaussians that reach either of its two patches.
-__global__ void __launch_bounds__(128)
-render_fwd_pc2_kernel(const RenderFwdArgs a) {
-    constexpr int NT = 128;
-    __shared__ float4 s0[RB], s1[RB];
-    __shared__ float2 s2[RB];
-    __shared__ uint8_t smask[RB];
-    __shared__ uint8_t slist[4][RB];
-    const int tile = blockIdx.x;
-    const int tile_x = tile % a.gx, tile_y = tile / a.gx;
-    const int t = threadIdx.x, w = t >> 5, l = t & 31;
-    const int px0 = tile_x * TILE + (l & 7), py = tile_y * TILE + 4 * w + (l >> 3);
-    const float fx0 = (float)px0, fy = (float)py;
-    const float ox = (float)(tile_x * TILE), oy = (float)(tile_y * TILE);
-    const uint2 range = a.ranges[tile];
-    const int todo = (int)(range.y - range.x);
-    const int rounds = (todo + RB - 1) / RB;
+// Backward.  Arithmetic per lane is IEEE round-to-nearest; the packed instructions compute exactly what their scalar
+// counterparts would.
+template <bool DEPTH, int MINB>
+__global__ void __launch_bounds__(64, MINB)
+render_bwd_kernel(const RenderBwdArgs a) {
+    constexpr int NT = 64;
+    __shared__ float4 s0[MP_R], s1[MP_R];
+    __shared__ float2 s2[MP_R];
+    __shared__ uint32_t sid[MP_R];
+    __shared__ uint32_t s_max;
+    __shared__ uint8_t smask[MP_R];
+    __shared__ uint8_t slist[2][MP_R];
+    const size_t v = blockIdx.y;
+    const uint2 *const ranges = a.ranges + v * a.sv_ranges;
+    const uint32_t *const point_list = a.point_list + v * a.sv_list;
+    const float4 *const splat = a.splat + v * a.sv_splat;
+    const uint32_t *const n_contrib = a.n_contrib + v * a.sv_image;
+    const float *const dL_dcolor = a.dL_dcolor + v * a.sv_color;
+    const float *const out_color = a.out_color + v * a.sv_color;
+    float *const dacc = a.dacc + v * a.sv_dacc;
+    const uint32_t want = 0xfu << (4 * (threadIdx.x >> 5));
+    const int tile = a.tile_order ? (int)a.tile_order[v * a.sv_ranges + blockIdx.x] : (int)blockIdx.x;
+    const int ox = (tile % a.gx) * TILE, oy = (tile / a.gx) * TILE;
+    const int t = threadIdx.x;
+    const int px0 = ox + 2 * (t & 7), py0 = oy + 2 * (t >> 3);
+    const float fx0 = (float)px0, fy0 = (float)py0;
+    const uint2 range = ranges[tile];
+    const size_t HW = (size_t)a.W * a.H;
 
-    bool done0 = !(px0 < a.W && py < a.H), done1 = !(px0 + 8 < a.W && py < a.H);
-    f32x2 T = pk1(1.0f), C0 = pk1(0.f), C1 = C0, C2 = C0, Dp = C0;
-    uint32_t last0 = 0, last1 = 0;
+    // per-pixel state, packed by row: element c of row r is pixel (px0 + c, py0 + r)
+    f32x2 T[2], F[2], S[2], dL0[2], dL1[2], dL2[2], dLd[2];
+    uint32_t last[4];
+    uint32_t my_max = 0;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        float vS[2] = {0.f, 0.f}, v0[2] = {0.f, 0.f}, v1[2] = {0.f, 0.f}, v2[2] = {0.f, 0.f}, vd[2] = {0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int px = px0 + c, py = py0 + r;
+            last[2 * r + c] = 0u;
+            if (px < a.W && py < a.H) {
+                const size_t pid = (size_t)py * a.W + px;
+                last[2 * r + c] = n_contrib[pid];
+                v0[c] = dL_dcolor[pid]; v1[c] = dL_dcolor[HW + pid]; v2[c] = dL_dcolor[2 * HW + pid];
+                vS[c] = v0[c] * out_color[pid] + v1[c] * out_color[HW + pid] + v2[c] * out_color[2 * HW + pid];
+                if (DEPTH) { vd[c] = a.dL_dinvdepth[v * a.sv_depth + pid]; vS[c] += vd[c] * a.out_invdepth[v * a.sv_depth + pid]; }
+            }
+            my_max = max(my_max, last[2 * r + c]);
+        }
+        T[r] = pk1(1.0f); F[r] = pk1(0.0f); S[r] = pk(vS[0], vS[1]);
+        dL0[r] = pk(v0[0], v0[1]); dL1[r] = pk(v1[0], v1[1]); dL2[r] = pk(v2[0], v2[1]); dLd[r] = pk(vd[0], vd[1]);
+    }
+    if (t == 0) s_max = 0;
+    __syncthreads();
+    my_max = __reduce_max_sync(0xffffffffu, my_max);
+    if ((t & 31) == 0) atomicMax(&s_max, my_max);
+    __syncthreads();
+    const int todo = (int)s_max;
+    const int my_todo = (int)my_max;
     const f32x2 one2 = pk1(1.0f);
 
-    for (int rd = 0; rd < rounds; ++rd) {
-        if (__syncthreads_and(done0 && done1)) break;
-        const int n = min(RB, todo - rd * RB);
+    for (int base = 0; base < todo; base += MP_R) {
+        __syncthreads();
+        const int n = min(MP_R, todo - base);
         for (int k = t; k < n; k += NT) {
-            const uint32_t g = a.point_list[range.x + rd * RB + k];
-            const float4 *rec = a.splat + (size_t)g * SPLAT_F4;
+            const uint32_t g = point_list[range.x + base + k];
+            const float4 *rec = splat + (size_t)g * SPLAT_F4;
             float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
             const float4 q2 = __ldg(rec + 2);
-            smask[k] = (uint8_t)patch_mask(q0.x, q0.y, q0.z, q0.w, q1.x, q2.z, ox, oy);
+            smask[k] = (uint8_t)patch_mask(q0.x, q0.y, q0.z, q0.w, q1.x, q2.z, (float)ox, (float)oy);
             stage_scale(q0, q1);
-            s0[k] = q0; s1[k] = q1; s2[k] = make_float2(q2.x, q2.y);
+            s0[k] = q0; s1[k] = q1; s2[k] = make_float2(q2.x, q2.y); sid[k] = g;
         }
         __syncthreads();
-        const int cnt = compact_hits(smask, n, 3u << (2 * w), slist[w]);
-        for (int k = 0; k < cnt; ++k) {
-            // warp-uniform exit: the vote below needs all 32 lanes, so a lane may not leave on its own
-            if (__all_sync(0xffffffffu, done0 && done1)) break;
-            const int j = slist[w][k];
-            const float4 q0 = s0[j];
-            const float4 q1 = s1[j];
-            const f32x2 dx2 = pk(q0.x - fx0, q0.x - (fx0 + 8.0f));
-            const float dy = q0.y - fy;
-            const float Cyy = __fmul_rn(__fmul_rn(q1.x, dy), dy);
+        const int nw = max(0, min(n, my_todo - base));
+        const int cnt = compact_hits(smask, nw, want, slist[t >> 5]);
+        for (int kk = 0; kk < cnt; ++kk) {
+            const int j = (int)slist[t >> 5][kk];
+            const float4 q0 = s0[j], q1 = s1[j];
+            const uint32_t pos = (uint32_t)(base + j + 1);
+            // column-packed terms (shared by both rows): dx, A' dx^2, B' dx
+            const f32x2 dx2 = pk(q0.x - fx0, q0.x - (fx0 + 1.0f));   // same rounding as the forward kernel
             const f32x2 Axx2 = mul2(mul2(pk1(q0.z), dx2), dx2);
-            const f32x2 p2 = fma2(mul2(pk1(q0.w), dx2), pk1(dy), add2(Axx2, pk1(Cyy)));   // power2_at, both columns
-            float p0, p1;
-            unpk(p2, p0, p1);
-            const float al0 = fminf(ALPHA_MAX, __fmul_rn(q1.y, ex2_approx(p0)));
-            const float al1 = fminf(ALPHA_MAX, __fmul_rn(q1.y, ex2_approx(p1)));
-            const bool v0 = (p0 <= 0.0f) && (al0 >= ALPHA_MIN) && !done0;
-            const bool v1 = (p1 <= 0.0f) && (al1 >= ALPHA_MIN) && !done1;
-            if (!__any_sync(0xffffffffu, v0 || v1)) continue;
-            const f32x2 al2 = pk(al0, al1);
-            const f32x2 tT = mul2(T, sub2(one2, al2));
-            float t0, t1;
-            unpk(tT, t0, t1);
-            const bool stop0 = v0 && (t0 < T_STOP), stop1 = v1 && (t1 < T_STOP);
-            done0 = done0 || stop0; done1 = done1 || stop1;
-            const bool u0 = v0 && !stop0, u1 = v1 && !stop1;
-            const f32x2 wgt = mul2(pk(u0 ? al0 : 0.0f, u1 ? al1 : 0.0f), T);
-            const float2 q2 = s2[j];
-            C0 = fma2(pk1(q1.z), wgt, C0); C1 = fma2(pk1(q1.w), wgt, C1); C2 = fma2(pk1(q2.x), wgt, C2);
-            Dp = fma2(pk1(q2.y), wgt, Dp);
-            float T0, T1;
-            unpk(T, T0, T1);
-            T = pk(u0 ? t0 : T0, u1 ? t1 : T1);
-            const uint32_t pos = (uint32_t)(rd * RB + j + 1);
-            last0 = u0 ? pos : last0; last1 = u1 ? pos : last1;
-        }
-    }
-    const float bg0 = __ldg(a.bg), bg1 = __ldg(a.bg + 1), bg2 = __ldg(a.bg + 2);
-    const size_t HW = (size_t)a.W * a.H;
-    float Tl, Th, c0l, c0h, c1l, c1h, c2l, c2h, dl, dh;
-    unpk(T, Tl, Th); unpk(C0, c0l, c0h); unpk(C1, c1l, c1h); unpk(C2, c2l, c2h); unpk(Dp, dl, dh);
-    if (py < a.H) {
-        if (px0 < a.W) {
-            const size_t pid = (size_t)py * a.W + px0;
-            a.final_T[pid] = Tl; a.n_contrib[pid] = last0;
-            a.out_color[pid] = c0l + Tl * bg0; a.out_color[HW + pid] = c1l + Tl * bg1; a.out_color[2 * HW + pid] = c2l + Tl * bg2;
-            a.out_invdepth[pid] = dl;
-        }
-        if (px0 + 8 < a.W) {
-            const size_t pid = (size_t)py * a.W + px0 + 8;
-            a.final_T[pid] = Th; a.n_contrib[pid] = last1;
-            a.out_color[pid] = c0h + Th * bg0; a.out_color[HW + pid] = c1h + Th * bg1; a.out_color[2 * HW + pid] = c2h + Th * bg2;
-            a.out_invdepth[pid] = dh;
-        }
-    }
-}
-
-__device__ __forceinline__ float warp_sum(float v) {
+            const f32x2 Bx2 = mul2(pk1(q0.w), dx2);
+            float dy[2], Cyy[2];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// 8 values per lane -> lane L ends with the warp total of value (L >> 2): 9 shuffles instead of 40.
-// Each xor step halves the number of values a lane carries: the lane keeps the half selected by its own
-// bit and adds the partner's copy of that half.
-__device__ __forceinline__ float warp_reduce8_transposed(const float v0, const float v1, const float v2, const float v3,
-                                                         const float v4, const float v5, const float v6, const float v7) {
-    const int lane = threadIdx.x & 31;
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-    const float k0 = (b4 ? v4 : v0) + __shfl_xor_sync(0xffffffffu, b4 ? v0 : v4, 16);
-    const float k1 = (b4 ? v5 : v1) + __shfl_xor_sync(0xffffffffu, b4 ? v1 : v5, 16);
-    const float k2 = (b4 ? v6 : v2) + __shfl_xor_sync(0xffffffffu, b4 ? v2 : v6, 16);
-    const float k3 = (b4 ? v7 : v3) + __shfl_xor_sync(0xffffffffu, b4 ? v3 : v7, 16);
-    const float m0 = (b3 ? k2 : k0) + __shfl_xor_sync(0xffffffffu, b3 ? k0 : k2, 8);
-    const float m1 = (b3 ? k3 : k1) + __shfl_xor_sync(0xffffffffu, b3 ? k1 : k3, 8);
-    float r = (b2 ? m1 : m0) + __shfl_xor_sync(0xffffffffu, b2 ? m0 : m1, 4);
-    r += __shfl_xor_sync(0xffffffffu, r, 2);
-    r += __shfl_xor_sync(0xffffffffu, r, 1);
-    return r;  // value index = 4*b4 + 2*b3 + b2 = lane >> 2
-}
-
-// 2 values per lane -> lanes 0..15 end with the total of v0, lanes 16..31 with the total of v1: 5 shuffles
-__device__ __forceinline__ float warp_reduce2_transposed(const float v0, const float v1) {
-    const bool b4 = threadIdx.x & 16;
-    float r = (b4 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, b4 ? v0 : v1, 16);
-    r += __shfl_xor_sync(0xffffffffu, r, 8);
-    r += __shfl_xor_sync(0xffffffffu, r, 4);
-    r += __shfl_xor_sync(0xffffffffu, r, 2);
-    r += __shfl_xor_sync(0xffffffffu, r, 1);
-    return r;
-}
-
-// per-pixel threads; the 10 per-gaussian gradient terms are reduced over the warp and added to the
-// per-gaussian accumulator.  VARIANT 0: butterfly all-reduce, lane 0 issues 10 atomics.
-// VARIANT 1: transposed reduction (14 shuffles), 8 + 2 lanes issue one atomic each.
-template <int VARIANT>
-__global__ void __launch_bounds__(256)
-render_bwd_kernel(const RenderBwdArgs a) {
-    __shared__ float4 s0[RB], s1[RB], s2[RB];
-    __shared__ uint32_t sid[RB];
-    __shared__ uint32_t s_max;
-    const int tile = blockIdx.x;
-    const int tile_x = tile % a.gx, tile_y = tile / a.gx;
-    int px, py;
-    pixel_of_thread(tile_x, tile_y, px, py);
-    const bool inside = px < a.W && py < a.H;
-    const float fx = (float)px, fy = (float)py;
-    const uint2 range = a.ranges[tile];
-    const size_t pid = (size_t)py * a.W + px, HW = (size_t)a.W * a.H;
-
-    const float T_final = inside ? a.final_T[pid] : 0.f;
-    const uint32_t last = inside ? a.n_contrib[pid] : 0u;
-    float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f, dLd = 0.f;
-    if (inside) {
-        dLp0 = a.dL_dcolor[pid]; dLp1 = a.dL_dcolor[HW + pid]; dLp2 = a.dL_dcolor[2 * HW + pid];
-        if (a.dL_dinvdepth) dLd = a.dL_dinvdepth[pid];
-    }
-    const float bg_dot = __ldg(a.bg) * dLp0 + __ldg(a.bg + 1) * dLp1 + __ldg(a.bg + 2) * dLp2;
-    const float ddx = 0.5f * a.W, ddy = 0.5f * a.H;
-
-    // the deepest position any pixel of the tile reached
-    if (threadIdx.x == 0) s_max = 0;
-    __syncthreads();
-    const uint32_t wmax = __reduce_max_sync(0xffffffffu, last);
-    if ((threadIdx.x & 31) == 0) atomicMax(&s_max, wmax);
-    __syncthreads();
-    const int todo = (int)s_max;  // positions todo .. 1 (1-based) are visited back to front
-    const int rounds = (todo + RB - 1) / RB;
-
-    float T = T_final;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accd = 0.f;
-    float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, ld = 0.f, last_alpha = 0.f;
-
-    for (int rd = 0; rd < rounds; ++rd) {
-        __syncthreads();
-        const int k = rd * RB + threadIdx.x;  // k-th from the back
-        if (k < todo) {
-            const uint32_t g = a.point_list[range.x + (todo - 1 - k)];
-            const float4 *rec = a.splat + (size_t)g * SPLAT_F4;
-            sid[threadIdx.x] = g;
-            s0[threadIdx.x] = __ldg(rec);
-            s1[threadIdx.x] = __ldg(rec + 1);
-            s2[threadIdx.x] = __ldg(rec + 2);
-        }
-        __syncthreads();
-        const int n = min(RB, todo - rd * RB);
-        for (int j = 0; j < n; ++j) {
-            const uint32_t pos = (uint32_t)(todo - (rd * RB + j));  // 1-based position in the tile list
-            const float4 q0 = s0[j];
-            const float4 q1 = s1[j];
-            const float dx = q0.x - fx, dy = q0.y - fy;
-            const float power = -0.5f * (q0.z * dx * dx + q1.x * dy * dy) - q0.w * dx * dy;
-            const float G = __expf(power);
-            const float alpha = fminf(ALPHA_MAX, q1.y * G);
-            const bool valid = (pos <= last) && (power <= 0.0f) && (alpha >= ALPHA_MIN);
-            if (!__any_sync(0xffffffffu, valid)) continue;
-            float g_mx = 0.f, g_my = 0.f, g_A = 0.f, g_B = 0.f, g_C = 0.f, g_o = 0.f, g_r = 0.f, g_g = 0.f, g_b = 0.f, g_d = 0.f;
-            if (valid) {
-                const float4 q2 = s2[j];
-                T = T / (1.0f - alpha);
-                const float w = alpha * T;
-                acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = q1.z;
-                acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = q1.w;
-                acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = q2.x;
-                accd = last_alpha * ld + (1.f - last_alpha) * accd; ld = q2.y;
-                float dL_dalpha = (q1.z - acc0) * dLp0 + (q1.w - acc1) * dLp1 + (q2.x - acc2) * dLp2 + (q2.y - accd) * dLd;
-                g_r = w * dLp0; g_g = w * dLp1; g_b = w * dLp2; g_d = w * dLd;
-                dL_dalpha *= T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-                const float dL_dpow = q1.y * G * dL_dalpha;
-                g_mx = dL_dpow * (-q0.z * dx - q0.w * dy) * ddx;
-                g_my = dL_dpow * (-q1.x * dy - q0.w * dx) * ddy;
-                g_A = dL_dpow * (-0.5f * dx * dx);
-                g_B = dL_dpow * (-dx * dy);
-                g_C = dL_dpow * (-0.5f * dy * dy);
-                g_o = G * dL_dalpha;
+            for (int r = 0; r < 2; ++r) {
+                dy[r] = q0.y - (fy0 + (float)r);
+                Cyy[r] = __fmul_rn(__fmul_rn(q1.x, dy[r]), dy[r]);
             }
-            float *d = a.dacc + (size_t)sid[j] * DACC_STRIDE;
-            if (VARIANT == 0) {
-                g_mx = warp_sum(g_mx); g_my = warp_sum(g_my); g_A = warp_sum(g_A); g_B = warp_sum(g_B); g_C = warp_sum(g_C);
-                g_o = warp_sum(g_o); g_r = warp_sum(g_r); g_g = warp_sum(g_g); g_b = warp_sum(g_b); g_d = warp_sum(g_d);
-                if ((threadIdx.x & 31) == 0) {
-                    atomicAdd(d + 0, g_mx); atomicAdd(d + 1, g_my); atomicAdd(d + 2, g_A); atomicAdd(d + 3, g_B);
-                    atomicAdd(d + 4, g_C); atomicAdd(d + 5, g_o); atomicAdd(d + 6, g_r); atomicAdd(d + 7, g_g);
-                    atomicAdd(d + 8, g_b); atomicAdd(d + 9, g_d);
+            float G[4], al[4];
+            bool valid[4];
+            bool any = false;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                // power2_at(Axx, Cyy, Bx, dy) = fma(Bx, dy, Axx + Cyy), both columns at once
+                const f32x2 p2 = fma2(Bx2, pk1(dy[r]), add2(Axx2, pk1(Cyy[r])));
+                float p[2];
+                unpk(p2, p[0], p[1]);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int i = 2 * r + c;
+                    G[i] = ex2_approx(p[c]);
+                    al[i] = fminf(ALPHA_MAX, __fmul_rn(q1.y, G[i]));
+                    valid[i] = (p[c] <= 0.0f) && (al[i] >= ALPHA_MIN) && (pos <= last[i]);
+                    any = any || valid[i];
                 }
+            }
+            if (!__any_sync(0xffffffffu, any)) continue;
+            const float2 q2 = s2[j];
+            f32x2 m_x = pk1(0.f), m_y = m_x, m_xx = m_x, m_xy = m_x, m_yy = m_x, g_o = m_x, g_r = m_x, g_g = m_x, g_b = m_x, g_d = m_x;
+            const f32x2 cr = pk1(q1.z), cg = pk1(q1.w), cb = pk1(q2.x), cd = pk1(q2.y), op2 = pk1(q1.y);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int i0 = 2 * r, i1 = 2 * r + 1;
+                // invalid lanes: alpha = 0 and G = 0 make every contribution below exactly zero
+                const f32x2 ai = pk(valid[i0] ? al[i0] : 0.0f, valid[i1] ? al[i1] : 0.0f);
+                const f32x2 Gm = pk(valid[i0] ? G[i0] : 0.0f, valid[i1] ? G[i1] : 0.0f);
+                const f32x2 w = mul2(ai, T[r]);
+                f32x2 g = fma2(dL2[r], cb, fma2(dL1[r], cg, mul2(dL0[r], cr)));
+                if (DEPTH) g = fma2(dLd[r], cd, g);
+                F[r] = fma2(w, g, F[r]);
+                g_r = fma2(w, dL0[r], g_r); g_g = fma2(w, dL1[r], g_g); g_b = fma2(w, dL2[r], g_b);
+                if (DEPTH) g_d = fma2(w, dLd[r], g_d);
+                const f32x2 om = sub2(one2, ai);
+                float om0, om1;
+                unpk(om, om0, om1);
+                const f32x2 rcp = pk(rcp_approx(om0), rcp_approx(om1));
+                // dL/dalpha = T g - (S - F) / (1 - alpha); multiplied by G (0 for invalid lanes) wherever it is used
+                const f32x2 dLda = sub2(mul2(T[r], g), mul2(sub2(S[r], F[r]), rcp));
+                T[r] = mul2(T[r], om);
+                const f32x2 Gd = mul2(Gm, dLda);
+                g_o = add2(g_o, Gd);
+                const f32x2 tt = mul2(op2, Gd);
+                const f32x2 dy2 = pk1(dy[r]);
+                const f32x2 u = mul2(tt, dx2), vv = mul2(tt, dy2);
+                m_x = add2(m_x, u); m_y = add2(m_y, vv);
+                m_xx = fma2(u, dx2, m_xx); m_xy = fma2(u, dy2, m_xy); m_yy = fma2(vv, dy2, m_yy);
+            }
+            const int lane = t & 31;
+            float *d = dacc + (size_t)sid[j] * DACC_STRIDE;
+            // both shuffle networks are issued before either atomic so that their (independent) chains overlap
+            const float ra = reduce8_transposed(hsum(m_x), hsum(m_y), hsum(m_xx), hsum(m_xy), hsum(m_yy), hsum(g_o), hsum(g_r), hsum(g_g));
+            float rb;
+            if (DEPTH) {
+                rb = reduce2_transposed(hsum(g_b), hsum(g_d));
             } else {
-                const int lane = threadIdx.x & 31;
-                const float ra = warp_reduce8_transposed(g_mx, g_my, g_A, g_B, g_C, g_o, g_r, g_g);
-                const float rb = warp_reduce2_transposed(g_b, g_d);
-                if ((lane & 3) == 0) atomicAdd(d + (lane >> 2), ra);
+                rb = hsum(g_b);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) rb += __shfl_xor_sync(0xffffffffu, rb, o);
+            }
+            if ((lane & 3) == 0) atomicAdd(d + (lane >> 2), ra);
+            if (DEPTH) {
                 if ((lane & 15) == 1) atomicAdd(d + 8 + (lane >> 4), rb);
+            } else {
+                if (lane == 1) atomicAdd(d + 8, rb);
             }
         }
     }
 }
 
-int launch_render_fwd(const RenderFwdArgs &a, int variant, bool debug, cudaStream_t stream) {
-    const int tiles = a.gx * a.gy;
-    if (tiles <= 0) return GSB_OK;
-    if (variant == 4) {
-        GSB_LAUNCH("render_fwd", debug, stream, (render_fwd_pc_kernel<1, false>), tiles, 256, 0, a);
-    } else if (variant == 7) {   // 6 CTAs/SM + shared-memory prefetch of the next record
-        GSB_LAUNCH("render_fwd", debug, stream, (render_fwd_pc_kernel<6, true>), tiles, 256, 0, a);
-    } else if (variant == 9) {   // two pixels per lane, packed f32x2 arithmetic
-        GSB_LAUNCH("render_fwd", debug, stream, render_fwd_pc2_kernel, tiles, 128, 0, a);
-    } else if (variant == 6) {   // register budget for 6 CTAs (48 warps) per SM
-        GSB_LAUNCH("render_fwd", debug, stream, (render_fwd_pc_kernel<6, false>), tiles, 256, 0, a);
-    } else if (variant == 8) {   // 8 CTAs (64 warps) per SM
-        GSB_LAUNCH("render_fwd", debug, stream, (render_fwd_pc_kernel<8, false>), tiles, 256, 0, a);
-    } else {
-        GSB_LAUNCH("render_fwd", debug, stream, render_fwd_kernel, tiles, 256, 0, a);
+// Tile order for the blend launches: tiles by DESCENDING list length (longest-processing-time-first), so that the heavy
+// tiles start in the first wave and the light ones fill the tail.  One block per view: a counting sort of the tiles on
+// a 256-bin quantisation of their list length.
+__global__ void __launch_bounds__(256)
+tile_order_kernel(const uint2 *__restrict__ ranges, const int num_tiles, uint32_t *__restrict__ order) {
+    __shared__ uint32_t cnt[256], warp_sums[8];
+    ranges += (size_t)blockIdx.x * num_tiles; order += (size_t)blockIdx.x * num_tiles;
+    cnt[threadIdx.x] = 0u;
+    __syncthreads();
+    // bin 0 = longest: 255 - min(255, len / 16 rounded into 0..255 with a log-ish top)
+    auto bin_of = [](const uint2 r) {
+        const uint32_t len = r.y - r.x;
+        const uint32_t q = len < 2048u ? (len >> 4) : min(255u, 128u + ((len - 2048u) >> 7));
+        return 255u - q;
+    };
+    for (int t = threadIdx.x; t < num_tiles; t += 256) atomicAdd(&cnt[bin_of(ranges[t])], 1u);
+    __syncthreads();
+    // exclusive scan of the 256 bins
+    const uint32_t c = cnt[threadIdx.x];
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)(threadIdx.x & 31) >= o) incl += n;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t basev = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) basev += warp_sums[w];
+    __syncthreads();
+    cnt[threadIdx.x] = basev + incl - c;
+    __syncthreads();
+    // placement (order inside a bin is irrelevant: the permutation only schedules CTAs, results do not depend on it)
+    for (int t = threadIdx.x; t < num_tiles; t += 256) order[atomicAdd(&cnt[bin_of(ranges[t])], 1u)] = (uint32_t)t;
+}
+
+static int check_views(const char *what, int V, int tiles) {
+    if (V < 1 || V > GSB_MAX_VIEWS || tiles > 0x7fffffff / GSB_MAX_VIEWS) {
+        set_error("%s: bad launch geometry (V=%d, tiles=%d)", what, V, tiles);
+        return GSB_ERR_ARGUMENT;
     }
     return GSB_OK;
 }
 
-int launch_render_bwd(const RenderBwdArgs &a, int variant, bool debug, cudaStream_t stream) {
+int launch_tile_order(const uint2 *ranges, int V, int num_tiles, uint32_t *order, bool debug, cudaStream_t stream) {
+    if (num_tiles <= 0) return GSB_OK;
+    int rc = check_views("tile_order", V, num_tiles);
+    if (rc) return rc;
+    GSB_LAUNCH("tile_order", debug, stream, tile_order_kernel, V, 256, 0, ranges, num_tiles, order);
+    return GSB_OK;
+}
+
+int launch_render_fwd(const RenderFwdArgs &a, bool debug, cudaStream_t stream) {
     const int tiles = a.gx * a.gy;
     if (tiles <= 0) return GSB_OK;
-    if (variant == 0) {
-        GSB_LAUNCH("render_bwd", debug, stream, render_bwd_kernel<0>, tiles, 256, 0, a);
+    int rc = check_views("render_fwd", a.V, tiles);
+    if (rc) return rc;
+    GSB_LAUNCH("render_fwd", debug, stream, render_fwd_kernel, dim3(tiles, a.V), 256, 0, a);
+    return GSB_OK;
+}
+
+int launch_render_bwd(const RenderBwdArgs &a, bool debug, cudaStream_t stream) {
+    const int tiles = a.gx * a.gy;
+    if (tiles <= 0) return GSB_OK;
+    int rc = check_views("render_bwd", a.V, tiles);
+    if (rc) return rc;
+    if (a.dL_dinvdepth) {
+        GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_kernel<true, 12>), dim3(tiles, a.V), 64, 0, a);
     } else {
-        GSB_LAUNCH("render_bwd", debug, stream, render_bwd_kernel<1>, tiles, 256, 0, a);
+        GSB_LAUNCH("render_bwd", debug, stream, (render_bwd_kernel<false, 16>), dim3(tiles, a.V), 64, 0, a);
     }
     return GSB_OK;
 }

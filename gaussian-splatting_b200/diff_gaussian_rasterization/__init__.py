@@ -44,7 +44,7 @@ class _State(Structure):
     _fields_ = [("P", c_int32), ("num_tiles", c_int32), ("num_rendered", c_int64), ("num_visible", c_int64),
                 ("binning_capacity", c_int64), ("geom", c_void_p), ("geom_bytes", c_size_t), ("binning", c_void_p), ("binning_bytes", c_size_t),
                 ("image", c_void_p), ("image_bytes", c_size_t), ("splat", c_void_p), ("point_list", c_void_p),
-                ("ranges", c_void_p), ("final_T", c_void_p), ("n_contrib", c_void_p)]
+                ("ranges", c_void_p), ("final_T", c_void_p), ("n_contrib", c_void_p), ("tile_order", c_void_p)]
 
 
 class _Grads(Structure):
@@ -54,6 +54,9 @@ class _Grads(Structure):
 
 
 _ALLOC_FN = CFUNCTYPE(c_void_p, c_void_p, c_int32, c_size_t)
+_CHUNK_FN = CFUNCTYPE(None, c_void_p, c_int32, c_int32, c_int32)     # gsb_chunk_fn(ctx, chunk, p_begin, p_end)
+ABI_VERSION = 6
+COUNT_SLOTS = 17        # gsb_forward_batch_async: V counts (up to 16) + their running maximum in slot 16
 BUF_GEOM, BUF_BINNING, BUF_IMAGE = 0, 1, 2
 
 
@@ -89,6 +92,13 @@ def _load(path: Optional[str] = None):
     lib.gsb_backward_batch.restype = c_int32
     lib.gsb_backward_batch.argtypes = [c_int32, POINTER(_Settings), POINTER(_Inputs), POINTER(_State), c_void_p, c_void_p,
                                        c_void_p, c_void_p, POINTER(_Grads), c_int32, _ALLOC_FN, c_void_p, c_void_p]
+    lib.gsb_forward_batch_async.restype = c_int32
+    lib.gsb_forward_batch_async.argtypes = [c_int32, POINTER(_Settings), POINTER(_Inputs), c_void_p, c_void_p, c_void_p, c_int64,
+                                            c_void_p, _ALLOC_FN, c_void_p, POINTER(_State), c_void_p]
+    lib.gsb_backward_batch_chunked.restype = c_int32
+    lib.gsb_backward_batch_chunked.argtypes = [c_int32, POINTER(_Settings), POINTER(_Inputs), POINTER(_State), c_void_p, c_void_p,
+                                               c_void_p, c_void_p, POINTER(_Grads), c_int32, c_int32, _CHUNK_FN, c_void_p,
+                                               _ALLOC_FN, c_void_p, c_void_p]
     lib.gsb_mark_visible.restype = c_int32
     lib.gsb_mark_visible.argtypes = [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.gsb_sort_pairs.restype = c_int32
@@ -118,8 +128,8 @@ def _load(path: Optional[str] = None):
     lib.gsb_densify_apply.argtypes = [POINTER(_DensifyArgs), c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.gsb_knn_mean_dist2.restype = c_int32
     lib.gsb_knn_mean_dist2.argtypes = [c_void_p, c_int64, c_void_p, _ALLOC_FN, c_void_p, c_void_p]
-    if lib.gsb_abi_version() != 5:
-        raise ImportError(f"{_LIB_PATH}: ABI version {lib.gsb_abi_version()} != 5")
+    if lib.gsb_abi_version() != ABI_VERSION:
+        raise ImportError(f"{_LIB_PATH}: ABI version {lib.gsb_abi_version()} != {ABI_VERSION} (rebuild: make -C gaussian-splatting_b200/csrc)")
     return lib
 
 
@@ -418,8 +428,7 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
         _check(rc, arena)
         # next estimate: this count + 25 %, rounded up to 1 Mi instances and never shrinking, so that buffer sizes
         # settle after the first few views instead of following every view's own count
-        want = ((int(st.num_rendered * 1.25) + 65536 + (1 << 20) - 1) >> 20) << 20
-        _capacity_hints[hkey] = max(want, _capacity_hints.get(hkey, 0))
+        _capacity_hints[hkey] = max(capacity_for(st.num_rendered), _capacity_hints.get(hkey, 0))
     pack = dict(state=st, geom=arena.bufs.get(BUF_GEOM), binning=arena.bufs.get(BUF_BINNING),
                 image=arena.bufs.get(BUF_IMAGE), num_rendered=int(st.num_rendered), sh_coeffs=M)
     return color, radii, invdepth, pack
@@ -455,8 +464,13 @@ def _backward_impl(pack, rs, means3D, sh, colors_precomp, opacities, scales, rot
 MAX_BATCH_VIEWS = 16
 
 
-def _forward_batch_impl(means3D, sh, opacities, scales, rotations, settings_list):
-    """View-batch forward (gsb_forward_batch): returns (color[V,3,H,W], radii[V,P], invdepth[V,1,H,W], pack)."""
+def _forward_batch_impl(means3D, sh, opacities, scales, rotations, settings_list, async_counts: Optional[torch.Tensor] = None,
+                        capacity: int = 0):
+    """View-batch forward (gsb_forward_batch): returns (color[V,3,H,W], radii[V,P], invdepth[V,1,H,W], pack).
+
+    ``async_counts`` (int64 device tensor of COUNT_SLOTS elements) switches to gsb_forward_batch_async: no host
+    synchronisation; ``capacity`` instances per view are final, the counts and their running maximum stay on the device
+    (the caller polls ``async_counts[16]`` later: gaussian_renderer.AsyncCapacity)."""
     _require_cuda(means3D)
     dev = means3D.device
     V, P = len(settings_list), int(means3D.shape[0])
@@ -472,24 +486,37 @@ def _forward_batch_impl(means3D, sh, opacities, scales, rotations, settings_list
         stream = _current_stream(dev)
         arena = _Arena(dev, stream)
         states = (_State * V)()
-        hkey = (P, H, W, dev.index, "batch")
-        hint = _capacity_hints.get(hkey, 0) if speculative_binning else 0
-        rc = _C.gsb_forward_batch(V, cs, byref(ci), color.data_ptr(), radii.data_ptr(), invdepth.data_ptr(), hint, arena.cb,
-                                  None, states, stream)
-        _check(rc, arena)
-        dmax = max(int(states[v].num_rendered) for v in range(V))
-        want = ((int(dmax * 1.25) + 65536 + (1 << 20) - 1) >> 20) << 20
-        _capacity_hints[hkey] = max(want, _capacity_hints.get(hkey, 0))
+        if async_counts is not None:
+            if async_counts.dtype != torch.int64 or async_counts.numel() < COUNT_SLOTS or not async_counts.is_contiguous():
+                raise ValueError("async_counts: contiguous int64 tensor of COUNT_SLOTS elements on the gaussians' device")
+            rc = _C.gsb_forward_batch_async(V, cs, byref(ci), color.data_ptr(), radii.data_ptr(), invdepth.data_ptr(), int(capacity),
+                                            async_counts.data_ptr(), arena.cb, None, states, stream)
+            _check(rc, arena)
+        else:
+            hkey = (P, H, W, dev.index, "batch")
+            hint = _capacity_hints.get(hkey, 0) if speculative_binning else 0
+            rc = _C.gsb_forward_batch(V, cs, byref(ci), color.data_ptr(), radii.data_ptr(), invdepth.data_ptr(), hint, arena.cb,
+                                      None, states, stream)
+            _check(rc, arena)
+            dmax = max(int(states[v].num_rendered) for v in range(V))
+            _capacity_hints[hkey] = max(capacity_for(dmax), _capacity_hints.get(hkey, 0))
     pack = dict(states=states, V=V, geom=arena.bufs.get(BUF_GEOM), binning=arena.bufs.get(BUF_BINNING),
                 image=arena.bufs.get(BUF_IMAGE), num_rendered=[int(states[v].num_rendered) for v in range(V)], sh_coeffs=M,
                 keep=keep)
     return color, radii, invdepth, pack
 
 
+def capacity_for(count: int) -> int:
+    """Instance capacity for an observed per-view count: + 25 %, + 64 Ki, rounded up to 1 Mi."""
+    return ((int(count * 1.25) + 65536 + (1 << 20) - 1) >> 20) << 20
+
+
 def _backward_batch_impl(pack, settings_list, means3D, sh, opacities, scales, rotations, out_color, out_invdepth,
-                         grad_color, grad_invdepth, grads: dict, accumulate: bool):
+                         grad_color, grad_invdepth, grads: dict, accumulate: bool, n_chunks: int = 1, on_chunk=None):
     """View-batch backward (gsb_backward_batch).  grads: tensors holding / receiving the gradient SUMMED over the views
-    (means2D, if present, is [V,P,3] and per view)."""
+    (means2D, if present, is [V,P,3] and per view).  ``n_chunks`` > 1: gsb_backward_batch_chunked -- the last kernel runs in
+    gaussian-range chunks and ``on_chunk(chunk, p_begin, p_end)`` is called after each chunk has been enqueued (rows
+    [p_begin, p_end) of every gradient are final in stream order from there on)."""
     dev = means3D.device
     V, P = pack["V"], int(means3D.shape[0])
     with _device_ctx(dev):
@@ -502,10 +529,27 @@ def _backward_batch_impl(pack, settings_list, means3D, sh, opacities, scales, ro
         g.dL_dscales, g.dL_drotations = _ptr(grads.get("scales")), _ptr(grads.get("rotations"))
         stream = _current_stream(dev)
         arena = _Arena(dev, stream)
-        rc = _C.gsb_backward_batch(V, cs, byref(ci), pack["states"], out_color.data_ptr(), out_invdepth.data_ptr(),
-                                   grad_color.data_ptr(), _ptr(grad_invdepth), byref(g), int(bool(accumulate)), arena.cb, None,
-                                   stream)
-        _check(rc, arena)
+        if n_chunks > 1 or on_chunk is not None:
+            err = []
+
+            def _cb(_ctx, chunk, p0, p1):
+                try:
+                    if on_chunk is not None and not err:
+                        on_chunk(int(chunk), int(p0), int(p1))
+                except Exception as e:  # never let an exception cross the C ABI
+                    err.append(e)
+            cb = _CHUNK_FN(_cb)
+            rc = _C.gsb_backward_batch_chunked(V, cs, byref(ci), pack["states"], out_color.data_ptr(), out_invdepth.data_ptr(),
+                                               grad_color.data_ptr(), _ptr(grad_invdepth), byref(g), int(bool(accumulate)),
+                                               int(n_chunks), cb, None, arena.cb, None, stream)
+            _check(rc, arena)
+            if err:
+                raise err[0]
+        else:
+            rc = _C.gsb_backward_batch(V, cs, byref(ci), pack["states"], out_color.data_ptr(), out_invdepth.data_ptr(),
+                                       grad_color.data_ptr(), _ptr(grad_invdepth), byref(g), int(bool(accumulate)), arena.cb, None,
+                                       stream)
+            _check(rc, arena)
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,

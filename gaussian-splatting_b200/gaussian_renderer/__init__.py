@@ -21,7 +21,8 @@ import torch
 import diff_gaussian_rasterization as _dgr
 from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
 
-__all__ = ["render", "render_views", "render_views_backward", "GradientBucket", "shard_views"]
+__all__ = ["render", "render_views", "render_views_backward", "GradientBucket", "AsyncCapacity", "shard_views",
+           "pin_to_gpu_numa_node"]
 
 
 def _eval_sh(deg, sh, dirs):
@@ -116,10 +117,74 @@ def _settings_for(cam, pc, pipe, bg_color, scaling_modifier):
         debug=bool(getattr(pipe, "debug", False)), antialiasing=bool(getattr(pipe, "antialiasing", False)))
 
 
+class AsyncCapacity:
+    """Instance-capacity bookkeeping of the SYNC-FREE view-batch step (gsb_forward_batch_async).
+
+    The synchronous path reads the V instance counts back every batch to size the binning buffers: one host wait per
+    step, which caps how far the host can run ahead of the device at less than one step -- so any host hiccup (a 20-140 ms
+    scheduling stall was seen on 8-GPU boxes, SCALE_r01.json) lands on the device timeline of EVERY rank through the
+    all-reduce.  Here the capacity is fixed up front, the counts stay on the device together with their running maximum,
+    and the host only looks at that maximum when it chooses to (``check()``: end of an epoch / every N steps).  A step
+    whose count exceeded the capacity rendered from truncated lists; ``check()`` then returns False, grows the capacity,
+    and the caller re-runs from its last good state (in steady state the counts drift by a few percent per densification
+    interval against 25 % of slack, so this is rare; right after densify_and_prune call ``reset()`` and run one
+    synchronous step)."""
+
+    def __init__(self, device, capacity: int = 0):
+        self.counts = torch.zeros(_dgr.COUNT_SLOTS, dtype=torch.int64, device=device)
+        self.capacity = int(capacity)
+
+    def learn(self, num_rendered: Sequence[int]) -> None:
+        """Size the capacity from the counts a synchronous step observed."""
+        self.capacity = max(self.capacity, _dgr.capacity_for(max(int(n) for n in num_rendered)))
+
+    def observed_max(self) -> int:
+        """Largest per-view count since the last reset (synchronises with the device)."""
+        return int(self.counts[_dgr.COUNT_SLOTS - 1].item())
+
+    def check(self) -> bool:
+        seen = self.observed_max()
+        if seen > self.capacity:
+            self.capacity = _dgr.capacity_for(seen)
+            self.counts.zero_()
+            return False
+        return True
+
+    def reset(self) -> None:
+        self.capacity = 0
+        self.counts.zero_()
+
+
+def pin_to_gpu_numa_node(device_index: int) -> Optional[list]:
+    """Restrict this process to the CPU cores that are local to its GPU (one process per GPU: without it the launch
+    thread migrates across sockets and shares cores with the other ranks' threads).  Uses NVML's ideal-affinity mask;
+    returns the core list, or None when NVML / sched_setaffinity are unavailable.  Never raises."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = device_index
+        if vis and all(x.strip().isdigit() for x in vis.split(",")):
+            idx = int(vis.split(",")[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cores = [64 * w + b for w in range(words) for b in range(64) if (int(mask[w]) >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch.Tensor, loss_fn, *,
                           scaling_modifier: float = 1.0, densify_stats: Optional[dict] = None,
                           keep_images: bool = False, loss_returns_grad: bool = False, batched: bool = True,
-                          overwrite: bool = False) -> dict:
+                          overwrite: bool = False, capacity: Optional[AsyncCapacity] = None, grad_chunks: int = 1,
+                          on_grad_chunk=None) -> dict:
     """Fused view-batch training step: forward + loss + backward for every camera, with the per-gaussian
     gradients of ALL views summed in place.
 
@@ -168,8 +233,13 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
         for c0 in range(0, len(cams_all), _dgr.MAX_BATCH_VIEWS):
             chunk = cams_all[c0:c0 + _dgr.MAX_BATCH_VIEWS]
             rss = [_settings_for(cm, pc, pipe, bg_color, scaling_modifier) for cm in chunk]
+            use_async = capacity is not None and capacity.capacity > 0
             color, radii, invdepth, pack = _dgr._forward_batch_impl(c["means3D"], c["shs"], c["opacities"], c["scales"],
-                                                                    c["rotations"], rss)
+                                                                    c["rotations"], rss,
+                                                                    async_counts=capacity.counts if use_async else None,
+                                                                    capacity=capacity.capacity if use_async else 0)
+            if capacity is not None and not use_async:
+                capacity.learn(pack["num_rendered"])
             g_color = torch.empty_like(color)
             g_depth = None
             for k in range(len(chunk)):
@@ -198,8 +268,10 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
             vg = dict(grads)
             if densify_stats is not None:
                 vg["means2D"] = torch.empty((len(chunk), P, 3), dtype=torch.float32, device=dev)
+            last_chunk = c0 + _dgr.MAX_BATCH_VIEWS >= len(cams_all)     # gradients are final only after the last view chunk
             _dgr._backward_batch_impl(pack, rss, c["means3D"], c["shs"], c["opacities"], c["scales"], c["rotations"], color,
-                                      invdepth, g_color, g_depth, vg, accumulate=not (overwrite and c0 == 0))
+                                      invdepth, g_color, g_depth, vg, accumulate=not (overwrite and c0 == 0),
+                                      n_chunks=grad_chunks if last_chunk else 1, on_chunk=on_grad_chunk if last_chunk else None)
             torch.maximum(radii_max, radii.max(dim=0).values, out=radii_max)
             if densify_stats is not None:
                 vis = radii > 0                                               # [V,P]
@@ -279,6 +351,31 @@ class GradientBucket:
 
     def zero_(self):
         self.flat.zero_()
+
+    def all_reduce_rows(self, p_begin: int, p_end: int, group=None):
+        """Asynchronous all-reduce of gaussians [p_begin, p_end) of every parameter's gradient (each a contiguous row
+        range), issued as ONE coalesced NCCL launch.  Ordered after the work enqueued so far on the current stream and
+        running on the process group's own stream, i.e. concurrently with whatever the caller enqueues next.  Returns a
+        list of handles for ``wait_all``; empty for world size 1."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return []
+        segs = [p.grad[p_begin:p_end] for p in self.params if p_end > p_begin]
+        if not segs:
+            return []
+        manager = getattr(dist, "_coalescing_manager", None)
+        if manager is None:      # older torch: one launch per segment
+            return [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True) for t in segs]
+        with manager(group=group, async_ops=True) as cm:
+            for t in segs:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return [cm]
+
+    @staticmethod
+    def wait_all(handles) -> None:
+        """The current stream waits for the reductions (no host block)."""
+        for h in handles:
+            h.wait()
 
     def all_reduce(self, group=None, average: bool = False):
         """One collective for all per-gaussian gradients.  No-op for world size 1."""

@@ -1,10 +1,12 @@
 /*
  * gs_b200.h -- C ABI of libgs_b200.so, the B200 (sm_100a) differentiable 3D-Gaussian-splatting
  * rasterizer.  Plain C: raw device pointers, explicit sizes, explicit stream, int error codes.
- * No torch types, no exceptions, no hidden global state except a per-device pinned read-back slot
- * (+ its event), the launch counter, the kernel-timing records and the tuning options.
- * Threading: one host thread per device at a time (the reference calls it from its single training
- * thread, train.py); calls for DIFFERENT devices may come from different processes (one per GPU).
+ * No torch types, no exceptions.  Process-wide state, all of it listed here: the tuning options
+ * (gsb_set_option: set them before the first call and leave them alone while calls are in flight),
+ * the launch counter and the kernel-timing records (diagnostics, mutex-guarded).  Per host thread:
+ * the last error string and one pinned read-back slot + event per device.
+ * Threading: any number of host threads may call concurrently (different streams / devices); the
+ * reference calls from its single training thread (train.py), one process per GPU.
  *
  * What each entry point replaces in the reference (graphdeco-inria/gaussian-splatting):
  * the reference reaches this path ONLY through the python package imported at
@@ -41,7 +43,7 @@
 extern "C" {
 #endif
 
-#define GSB_ABI_VERSION 5
+#define GSB_ABI_VERSION 6
 
 /* error codes (0 = ok); gsb_last_error() holds the message of the calling thread's last failure */
 #define GSB_OK 0
@@ -112,6 +114,7 @@ typedef struct GsbState {
     const void *ranges;       /* [num_tiles] uint2 [begin, end) into point_list */
     const float *final_T;     /* [H*W] */
     const uint32_t *n_contrib; /* [H*W] */
+    const void *tile_order;   /* [num_tiles] uint32 blend-launch order of the tiles, or NULL (option tile_order) */
 } GsbState;
 
 /* gradient outputs of the autograd.Function's backward; NULL pointers are skipped */
@@ -156,6 +159,29 @@ int32_t gsb_backward_batch(int32_t V, const GsbSettings *settings, const GsbInpu
                            const float *out_color, const float *out_invdepth, const float *dL_dcolor,
                            const float *dL_dinvdepth, const GsbGrads *grads, int32_t accumulate,
                            gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream);
+
+/* gsb_forward_batch without ANY host synchronisation (what lets the host enqueue whole training steps ahead of the
+ * device, and what a CUDA-graph capture of the step needs).  `capacity` (> 0) is the per-view instance capacity of the
+ * binning buffers and is final: there is no read-back and no repair.  counts_dev: device array of 17 uint64 owned by the
+ * caller; the call leaves the V instance counts in counts_dev[0..V) and folds them into the running maximum
+ * counts_dev[16] (zero it once).  A view whose count exceeds `capacity` is rendered from a TRUNCATED list (no out-of-
+ * bounds access): the caller polls counts_dev[16] whenever convenient (e.g. every N steps) and, if it ever exceeded the
+ * capacity, discards those steps and re-runs them with a larger one.  states[v].num_rendered is -1 (device-only). */
+int32_t gsb_forward_batch_async(int32_t V, const GsbSettings *settings, const GsbInputs *in, float *out_color,
+                                int32_t *out_radii, float *out_invdepth, int64_t capacity, uint64_t *counts_dev,
+                                gsb_alloc_fn alloc, void *alloc_ctx, GsbState *states, void *cuda_stream);
+
+/* gsb_backward_batch with the last kernel (preprocess backward, which writes the gradient tensors) cut into n_chunks
+ * gaussian ranges.  After chunk c has been ENQUEUED, on_chunk(ctx, c, p_begin, p_end) is called on the host: rows
+ * [p_begin, p_end) of every gradient tensor are final once the work enqueued so far on the stream completes, so the
+ * caller can record an event and start reducing that range on another stream (data-parallel all-reduce overlapped with
+ * the remaining chunks).  on_chunk may be NULL. */
+typedef void (*gsb_chunk_fn)(void *ctx, int32_t chunk, int32_t p_begin, int32_t p_end);
+int32_t gsb_backward_batch_chunked(int32_t V, const GsbSettings *settings, const GsbInputs *in, const GsbState *states,
+                                   const float *out_color, const float *out_invdepth, const float *dL_dcolor,
+                                   const float *dL_dinvdepth, const GsbGrads *grads, int32_t accumulate,
+                                   int32_t n_chunks, gsb_chunk_fn on_chunk, void *chunk_ctx, gsb_alloc_fn alloc,
+                                   void *alloc_ctx, void *cuda_stream);
 
 /* Frustum test only (GaussianRasterizer.markVisible): present[i] = 1 if view-space z > 0.2 */
 int32_t gsb_mark_visible(int32_t P, const float *means3D, const float *viewmatrix,
@@ -258,7 +284,8 @@ void gsb_reset_launch_count(void);
 /* CUDA-event time of the launches of kernel `name` ("" = all) recorded on their launching stream since
  * the last reset, while option "time_kernels" was 1 (blend kernels) or 2 (all).  Synchronises on the events. */
 int32_t gsb_kernel_time(const char *name, double *total_ms, int64_t *launches, int32_t reset);
-/* tuning knobs (integers), e.g. gsb_set_option("render_variant", 1); returns 0 if known */
+/* tuning knobs (integers): "cull", "fused_ranges", "sort_big_ipt", "sort_variant", "sort_small", "tile_order",
+ * "time_kernels"; returns 0 if known */
 int32_t gsb_set_option(const char *name, int32_t value);
 
 #ifdef __cplusplus

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in decl:
         assert hasattr(lib, name), f"{name} declared in include/ but not exported"
     lib.gsb_abi_version.restype = ctypes.c_int32
-    assert lib.gsb_abi_version() == 5
+    assert lib.gsb_abi_version() == 6
 
 
 def test_struct_sizes_match_header():
@@ -36,7 +36,7 @@ def test_struct_sizes_match_header():
     # LP64 layouts of include/gs_b200.h
     assert ctypes.sizeof(dgr._Settings) == 80
     assert ctypes.sizeof(dgr._Inputs) == 64
-    assert ctypes.sizeof(dgr._State) == 120
+    assert ctypes.sizeof(dgr._State) == 128
     assert ctypes.sizeof(dgr._Grads) == 64
     assert ctypes.sizeof(dgr._AdamArgs) == 104
     assert ctypes.sizeof(dgr._DensifyArgs) == 80

@@ -194,3 +194,71 @@ def test_fused_ranges_option(on_host):
         _check(scene, TO.make_camera(80, 48, sh_degree=2, bg=(0.2, 0.1, 0.3)), "sh")
     finally:
         dgr.set_option("fused_ranges", 0)
+
+
+def _batch_step(scene, cams, gts, bg, **kw):
+    import bench
+    from gaussian_renderer import GradientBucket, render_views_backward
+    pc = bench.BenchGaussians(scene, 3, "cpu")
+    bucket = GradientBucket(pc.parameters())
+    out = render_views_backward(cams, pc, bench.Pipe(), bg, lambda img, d, i: (img - gts[i]).abs().mean() + 0.1 * d.mean(),
+                                keep_images=True, **kw)
+    return out["losses"].numpy(), bucket.flat.numpy().copy(), [im.numpy().copy() for im in out["images"]], bucket
+
+
+def _batch_inputs(n=300, seed=51, views=2, W=48, H=32):
+    import bench
+    scene = TO.make_scene(n, seed=seed, log_scale_mean=-2.6)
+    cams = [bench.BenchCamera(W, H, math.radians(60.0), *bench.view_pose(i, 3.0), "cpu") for i in range(views)]
+    gts = [torch.rand(3, H, W, generator=torch.Generator().manual_seed(i)) for i in range(views)]
+    return scene, cams, gts, torch.tensor([0.1, 0.2, 0.3])
+
+
+def test_sync_free_view_batch_step(on_host):
+    """gsb_forward_batch_async: same images and gradients as the synchronous call; the counts and their running maximum
+    stay on the device; a capacity that is too small truncates the lists without touching memory out of bounds and is
+    reported by AsyncCapacity.check(), which also grows the capacity for the re-run."""
+    from gaussian_renderer import AsyncCapacity
+    scene, cams, gts, bg = _batch_inputs()
+    l0, g0, im0, _ = _batch_step(scene, cams, gts, bg)
+    cap = AsyncCapacity("cpu")
+    cap.learn([1000, 3000])
+    assert cap.capacity == 1 << 20 and cap.observed_max() == 0
+    cap.capacity = 4096                          # the emulation walks every block of the capacity-sized launches: keep it small
+    l2, g2, im2, _ = _batch_step(scene, cams, gts, bg, capacity=cap)           # no read-back
+    for a, b in zip(im0, im2):
+        assert np.array_equal(a, b)
+    assert np.array_equal(l0, l2) and np.abs(g0 - g2).max() <= 1e-5 * np.abs(g0).max()
+    seen = cap.observed_max()
+    assert 0 < seen <= cap.capacity and cap.check()
+    counts = cap.counts.numpy()
+    assert counts[:2].max() == seen and counts[2:16].sum() == 0
+    # overflow: lists truncated at the capacity, reported afterwards
+    small = AsyncCapacity("cpu", capacity=max(64, seen // 3))
+    _batch_step(scene, cams, gts, bg, capacity=small)
+    assert small.observed_max() == seen
+    assert not small.check() and small.capacity >= seen and small.observed_max() == 0
+
+
+def test_chunked_gradient_kernel_and_tile_order(on_host):
+    """gsb_backward_batch_chunked: the gradient-writing kernel in gaussian-range chunks gives the same gradients, and the
+    callback sees disjoint ranges covering [0, P) in order.  Option tile_order (heavy tiles first) leaves the images unchanged."""
+    dgr = on_host
+    scene, cams, gts, bg = _batch_inputs(n=600)
+    l0, g0, im0, _ = _batch_step(scene, cams, gts, bg, overwrite=True)
+    seen = []
+    dgr.set_option("tile_order", 1)
+    try:
+        l1, g1, im1, _ = _batch_step(scene, cams, gts, bg, overwrite=True, grad_chunks=2, on_grad_chunk=lambda c, a, b: seen.append((c, a, b)))
+        cam = TO.make_camera(48, 32, sh_degree=2)
+        small = TO.make_scene(150, seed=7, log_scale_mean=-2.2)
+        single = U.run_cuda(U.make_args(small, "sh"), cam, *_weights(cam), device="cpu")
+    finally:
+        dgr.set_option("tile_order", 0)
+    assert seen == [(0, 0, 512), (1, 512, 600)]
+    for a, b in zip(im0, im1):
+        assert np.array_equal(a, b)
+    assert np.array_equal(l0, l1) and np.abs(g0 - g1).max() <= 1e-5 * np.abs(g0).max()
+    ref = U.run_oracle(U.make_args(small, "sh"), cam, *_weights(cam))
+    U.assert_image_close(single["color"], ref["color"], "tile_order single view")
+    U.assert_grads_close(single["grads"], ref["grads"])
