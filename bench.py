@@ -19,9 +19,16 @@ over ranks (view-parallel, weak scaling: views per rank fixed).  Workload = BASE
 `roofline`: dominant kernel (render_bwd) -- algorithmic bytes / CUDA-event time on its launch stream.
 `cpu_baseline` / `--impl reference`: the CPU restatement of the path (oracle/gs_oracle.c, OpenMP over all
             host cores).  The reference's own rasterizer sources are absent from /root/reference
-            (SURVEY.md section 0), so there is no oracle/_ref and kind is "port".
+            (SURVEY.md section 0), so there is no oracle/_ref and kind is "port".  If a stock install of
+            the reference rasterizer ever appears under baseline/_ref (diff_gaussian_rasterization built
+            from the submodule the operator vendors), `--impl reference` times THAT on the GPU instead
+            (kind "reference-cuda").
+`single_view`: the drop-in path a user of the reference gets: one camera per iteration through
+            GaussianRasterizer.forward + loss.backward() (train.py:111-142), same workload.
 """
 import argparse
+import gc
+import importlib.util
 import json
 import math
 import os
@@ -62,6 +69,17 @@ def parse():
                     help="whole training iteration: the gaussians live in gaussian_store.GaussianModel (raw parameters) and "
                          "every step ends with its fused activation-backward + Adam step (outside the BASELINE metric)")
     ap.add_argument("--no-batch", action="store_true", help="views API view by view instead of gsb_forward_batch")
+    ap.add_argument("--sync", action="store_true",
+                    help="A/B: the synchronous view-batch call (one instance-count read-back per step) instead of the sync-free one")
+    ap.add_argument("--grad-chunks", type=int, default=-1,
+                    help="gaussian-range chunks of the gradient-writing kernel, each all-reduced while the next computes "
+                         "(default: 4 when world size > 1, else 1)")
+    ap.add_argument("--no-pin", action="store_true", help="do not pin the process to its GPU's NUMA-local cores")
+    ap.add_argument("--no-single-view", action="store_true", help="skip the drop-in single-view leg (render() + autograd)")
+    ap.add_argument("--workload", default="raster", choices=["raster", "train6m"],
+                    help="raster: the BASELINE metric (default).  train6m: BASELINE configs[3], the 6 M-gaussian training loop "
+                         "with densify/prune (tools/train_bench.py), reported as iterations/s")
+    ap.add_argument("--iterations", type=int, default=1000, help="train6m: iterations")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0)
     return ap.parse_args()
@@ -70,8 +88,9 @@ def parse():
 class BenchCamera:
     """The attributes render() reads from scene.cameras.Camera (/root/reference/scene/cameras.py:19-89)."""
 
-    def __init__(self, width, height, fovx, R, T, device):
-        from gaussian_renderer.synthetic import camera_matrices
+    def __init__(self, width, height, fovx, R, T, device, camera_matrices=None):
+        if camera_matrices is None:
+            from gaussian_renderer.synthetic import camera_matrices
         self.image_width, self.image_height = width, height
         self.FoVx = fovx
         self.FoVy = 2.0 * math.atan(math.tan(fovx / 2) * height / width)
@@ -251,16 +270,98 @@ def workload_config(a, world):
             "scene": f"xyz~U([-1,1]^3), log-scale~N({LOG_SCALE_MEAN},0.5), opacity=sigmoid(U(-2,4)), cameras on sphere r=3, seed 0"}
 
 
+def _load_synthetic():
+    """gaussian_renderer/synthetic.py by FILE PATH: importing the package would map libgs_b200.so into the reference arm."""
+    spec = importlib.util.spec_from_file_location("gsb_synthetic", os.path.join(PKG, "gaussian_renderer", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _stock_reference_rasterizer():
+    """The UNMODIFIED reference rasterizer, if the operator has installed it under baseline/_ref (its sources are absent
+    from /root/reference, so normally there is none).  Returns the imported module or None."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "diff_gaussian_rasterization")):
+        return None
+    saved = list(sys.path)
+    try:
+        sys.path.insert(0, ref_dir)
+        for name in [m for m in sys.modules if m.split(".")[0] == "diff_gaussian_rasterization"]:
+            del sys.modules[name]
+        import diff_gaussian_rasterization as stock
+        if os.path.realpath(os.path.dirname(stock.__file__)).startswith(os.path.realpath(ref_dir)) and hasattr(stock, "_C"):
+            return stock
+    except Exception:
+        pass
+    finally:
+        sys.path[:] = saved
+    return None
+
+
+def run_reference_cuda(a, stock, syn):
+    """--impl reference with a stock install present: the reference's own CUDA rasterizer through its own Python API,
+    one view per step, same scene / cameras / metric (kind "reference-cuda")."""
+    import torch
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    scene = {k: v.to(dev).requires_grad_(True) for k, v in syn.make_scene(a.gaussians, seed=0, log_scale_mean=LOG_SCALE_MEAN).items()}
+    V, H, W = a.views_per_rank, a.height, a.width
+    cams = []
+    for i in range(V):
+        R, T = syn.sphere_pose(i, 3.0)
+        fovx = math.radians(60.0)
+        fovy = 2.0 * math.atan(math.tan(fovx / 2) * H / W)
+        wvt, full, center = syn.camera_matrices(R, T, fovx, fovy)
+        cams.append((fovx, fovy, wvt.to(dev), full.to(dev), center.to(dev)))
+    gen = torch.Generator().manual_seed(1234)
+    gts = [torch.rand(3, H, W, generator=gen).to(dev) for _ in range(V)]
+    bg = torch.zeros(3, device=dev)
+
+    def one(i):
+        fovx, fovy, wvt, full, center = cams[i % V]
+        rs = stock.GaussianRasterizationSettings(image_height=H, image_width=W, tanfovx=math.tan(fovx * 0.5), tanfovy=math.tan(fovy * 0.5),
+                                                 bg=bg, scale_modifier=1.0, viewmatrix=wvt, projmatrix=full, sh_degree=a.sh_degree,
+                                                 campos=center, prefiltered=False, debug=False, antialiasing=False)
+        out = stock.GaussianRasterizer(raster_settings=rs)(
+            means3D=scene["means3D"], means2D=torch.zeros_like(scene["means3D"], requires_grad=True), shs=scene["shs"],
+            colors_precomp=None, opacities=scene["opacities"], scales=scene["scales"], rotations=scene["rotations"], cov3D_precomp=None)
+        (out[0].clamp(0, 1) - gts[i % V]).abs().mean().backward()
+
+    for i in range(max(a.warmup, 3) * V):
+        one(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps * V):
+        one(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    value = a.steps * V * H * W / 1e6 / (ms / 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(a, 1),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 0, "kind": "reference-cuda",
+                             "sample": f"{V} views per step through the stock diff_gaussian_rasterization in baseline/_ref (GPU)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(a):
     """--impl reference: the path's CPU implementation on the host cores, one view per step (bounded sample)."""
-    import torch
-    from gaussian_renderer.synthetic import make_scene
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    scene = make_scene(a.gaussians, seed=0, log_scale_mean=LOG_SCALE_MEAN)
-    R, T = view_pose(0, 3.0)
-    cam = BenchCamera(a.width, a.height, math.radians(60.0), R, T, "cpu")
+    syn = _load_synthetic()
+    stock = _stock_reference_rasterizer()
+    if stock is not None:
+        return run_reference_cuda(a, stock, syn)
+    from oracle.c_oracle import set_threads
+    nthreads = set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    scene = syn.make_scene(a.gaussians, seed=0, log_scale_mean=LOG_SCALE_MEAN)
+    R, T = syn.sphere_pose(0, 3.0)
+    cam = BenchCamera(a.width, a.height, math.radians(60.0), R, T, "cpu", camera_matrices=syn.camera_matrices)
     cs = oracle_settings(cam, a.sh_degree)
     times, nthreads = cpu_reference_pass(scene, cs, a.warmup + a.steps)
     timed = times[a.warmup:]
@@ -271,7 +372,8 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, max(1, a.gpus)),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": sample,
+                             "host_cpus": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
             "note": "CPU port of the path (oracle/gs_oracle.c, OpenMP); the reference's CUDA rasterizer sources "
@@ -284,17 +386,22 @@ def main():
     if a.impl == "reference":
         run_reference(a)
         return
+    if a.workload == "train6m":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import train_bench
+        return train_bench.bench_line(a)
     import torch
     import torch.distributed as dist
     from gaussian_renderer.synthetic import make_scene   # the oracle is only loaded by the cpu_baseline leg below
     import diff_gaussian_rasterization as dgr
-    from gaussian_renderer import GradientBucket, render, render_views_backward
+    from gaussian_renderer import AsyncCapacity, GradientBucket, pin_to_gpu_numa_node, render, render_views_backward
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the rasterizer has no CPU path (use --impl reference for the CPU port)")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    pinned_cores = None if a.no_pin else pin_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -304,6 +411,7 @@ def main():
             dgr.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     if world != a.gpus and rank == 0:
         print(f"# note: --gpus {a.gpus} but WORLD_SIZE {world}; using {world}", file=sys.stderr)
+    grad_chunks = a.grad_chunks if a.grad_chunks > 0 else (4 if world > 1 else 1)
 
     torch.manual_seed(0)
     scene = make_scene(a.gaussians, seed=0, log_scale_mean=LOG_SCALE_MEAN)
@@ -320,16 +428,7 @@ def main():
                                           position_lr_max_steps=30000, feature_lr=0.0025, opacity_lr=0.025, scaling_lr=0.005,
                                           rotation_lr=0.001, percent_dense=0.01))      # arguments/__init__.py:77-89
         del sc
-
-        class StoreBucket:           # the store's gradient buffer IS the all-reduce bucket
-            def zero_(self):
-                pc.grad.zero_()
-
-            def all_reduce(self):
-                if world > 1:
-                    dist.all_reduce(pc.grad, op=dist.ReduceOp.SUM)
-
-        bucket = StoreBucket()
+        bucket = pc.gradient_bucket()          # the store's gradient buffer IS the all-reduce bucket
     else:
         pc = BenchGaussians(scene, a.sh_degree, dev)
         bucket = GradientBucket(pc.parameters())
@@ -341,6 +440,7 @@ def main():
     gt_host = [torch.rand(3, H, W, generator=gen).pin_memory() for _ in range(V)]
     gt_dev = [g.to(dev) for g in gt_host]
     mpix_step = V * world * H * W / 1e6
+    capacity = None if (a.sync or a.api != "views" or a.no_batch) else AsyncCapacity(dev)
 
     # e2e leg: per-view host inputs.  The 24.9 MB target image of view i is copied from pinned memory on a side
     # stream into one of two staging buffers when view i STARTS, so the copy overlaps that view's forward kernels;
@@ -369,6 +469,7 @@ def main():
     def step(host_inputs: bool):
         if a.api != "views":
             bucket.zero_()
+        pending = []
         if a.api == "views":
             def loss_fn(img, _invdepth, i):
                 fused = dgr.l1_loss_and_grad if a.loss == "l1" else (lambda x, y: dgr.photometric_loss_and_grad(x, y, 0.2)[:2])
@@ -378,9 +479,19 @@ def main():
                     consumed[i % NS].record()
                     return res
                 return fused(img, gt_dev[i])
+
+            def on_chunk(_c, p0, p1):      # rows [p0, p1) of every gradient are final: reduce them while the next chunk computes
+                pending.extend(bucket.all_reduce_rows(p0, p1))
+            chunked = world > 1 and grad_chunks > 1 and not a.no_batch
             out = render_views_backward(HostCams() if host_inputs else cams, pc, pipe, bg, loss_fn, loss_returns_grad=True,
-                                        batched=not a.no_batch, overwrite=True)   # first chunk writes the bucket: no zeroing pass
+                                        batched=not a.no_batch, overwrite=True,   # first chunk writes the bucket: no zeroing pass
+                                        capacity=capacity, grad_chunks=grad_chunks if chunked else 1,
+                                        on_grad_chunk=on_chunk if chunked else None)
             total = out["losses"].sum()
+            if chunked:
+                GradientBucket.wait_all(pending)
+            else:
+                bucket.all_reduce()
         else:
             total = torch.zeros((), device=dev)
             for i, cam in enumerate(cams):
@@ -393,7 +504,7 @@ def main():
                 loss = (pkg["render"] - gt).abs().mean()
                 loss.backward()
                 total += loss.detach()
-        bucket.all_reduce()
+            bucket.all_reduce()
         if a.optimizer:
             pc.update_learning_rate(pc.step_count + 1)
             pc.optimizer_step()
@@ -408,24 +519,50 @@ def main():
     step_stats = {}
 
     def timed(host_inputs: bool, steps: int):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-        marks[0].record()
-        for k in range(steps):
-            step(host_inputs)
-            marks[k + 1].record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        """K steps between barrier + synchronize on both sides; CUDA events; max over ranks.  Also the wall time the HOST
+        needed to enqueue the K steps (how far it runs ahead of the device)."""
+        gc.collect()
+        gc.disable()        # a generation-2 collection in the launch thread is a multi-ms stall that every rank then waits for
+        try:
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+            t0 = time.perf_counter()
+            marks[0].record()
+            for k in range(steps):
+                step(host_inputs)
+                marks[k + 1].record()
+            host_ms = (time.perf_counter() - t0) * 1e3
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+        finally:
+            gc.enable()
         per_step = [marks[k].elapsed_time(marks[k + 1]) for k in range(steps)]
         step_stats[host_inputs] = {"min": round(min(per_step), 3), "median": round(statistics.median(per_step), 3),
-                                   "max": round(max(per_step), 3)}
+                                   "max": round(max(per_step), 3), "host_enqueue_ms_per_step": round(host_ms / steps, 3)}
         ms = torch.tensor([marks[0].elapsed_time(marks[steps])], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
+
+    def measured(host_inputs: bool):
+        """One timed leg.  The sync-free path validates its instance capacity AFTER the region (one read of the running
+        maximum); a region that overflowed rendered from truncated lists and is re-run with the grown capacity."""
+        runs = []
+        for _try in range(3):
+            ms = timed(host_inputs, a.steps)
+            ok = capacity is None or capacity.check()
+            if world > 1:
+                flag = torch.tensor([0 if ok else 1], device=dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+                ok = int(flag.item()) == 0
+            runs.append({"ms_total": round(ms, 3), **step_stats[host_inputs], "capacity_ok": ok})
+            if ok:
+                break
+            step(host_inputs)       # synchronous-equivalent warm step with the new capacity
+        return ms, runs
 
     # ---- device-resident leg ----
     # the sampler starts BEFORE the warm-up: nvidia-smi's own start-up disturbs the driver for a second or two
@@ -433,23 +570,17 @@ def main():
     if rank == 0:
         sampler.start()
     # untimed warm-up: at least 3 steps (contract) and at least 5 so that buffer sizes / the caching allocator settle
+    # (the first step of the sync-free path is synchronous and learns the instance capacity)
     for _ in range(max(a.warmup, 8)):
         step(False)
     torch.cuda.synchronize()
     dgr.set_option("time_kernels", 1)
-    # A shared host occasionally stalls the launching thread for tens to hundreds of ms (seen as ONE step of 40-700 ms
-    # among steps of 15.4 ms).  Such a leg is re-measured (at most twice) and every attempt is reported.
-    attempts = []
-    for _try in range(3):
-        dgr.kernel_time("", reset=True)
-        dgr.reset_launch_count()
-        sampler.mark("start")
-        ms_total = timed(False, a.steps)
-        sampler.mark("end")
-        attempts.append({"ms_total": round(ms_total, 3), **step_stats[False]})
-        if step_stats[False]["max"] <= 1.5 * step_stats[False]["median"]:
-            break
-    launches = dgr.launch_count()
+    dgr.kernel_time("", reset=True)
+    dgr.reset_launch_count()
+    sampler.mark("start")
+    ms_total, attempts = measured(False)
+    sampler.mark("end")
+    launches = dgr.launch_count() // len(attempts)
     bwd_ms, bwd_n = dgr.kernel_time("render_bwd")
     fwd_ms, fwd_n = dgr.kernel_time("render_fwd", reset=True)
     dgr.set_option("time_kernels", 0)
@@ -459,35 +590,55 @@ def main():
     # ---- end-to-end leg (host inputs) ----
     for _ in range(max(a.warmup, 3)):
         step(True)
-    e2e_attempts = []
-    for _try in range(3):
-        ms_e2e = timed(True, a.steps)
-        e2e_attempts.append({"ms_total": round(ms_e2e, 3), **step_stats[True]})
-        if step_stats[True]["max"] <= 1.5 * step_stats[True]["median"]:
-            break
+    ms_e2e, e2e_attempts = measured(True)
     e2e_value = mpix_step * a.steps / (ms_e2e / 1e3)
     h2d = V * (3 * H * W * 4 + 4 * 35)
     d2h = 4
 
-    # ---- instance statistics + per-kernel breakdown of one view (outside the timed regions) ----
-    with torch.no_grad():
-        rs = dgr.GaussianRasterizationSettings(H, W, math.tan(cams[0].FoVx * 0.5), math.tan(cams[0].FoVy * 0.5), bg, 1.0,
-                                               cams[0].world_view_transform, cams[0].full_proj_transform, a.sh_degree,
-                                               cams[0].camera_center, False, False, False)
-        _, radii, _, pack = dgr._forward_impl(pc.get_xyz.detach(), pc.get_features.detach(), None, pc.get_opacity.detach().reshape(-1),
-                                              pc.get_scaling.detach(), pc.get_rotation.detach(), None, rs)
-        sv = dgr.state_views(pack, H, W)
-        D = int(pack["num_rendered"])
-        lens = (sv["ranges"][:, 1] - sv["ranges"][:, 0]).float()
-        nc = sv["n_contrib"]
-        gy, gx = (H + 15) // 16, (W + 15) // 16
-        pad = torch.zeros(gy * 16, gx * 16, dtype=nc.dtype, device=dev)
-        pad[:H, :W] = nc
-        tile_max = pad.view(gy, 16, gx, 16).permute(0, 2, 1, 3).reshape(gy * gx, 256).max(dim=1).values
-        D_visited = int(tile_max.sum().item())
-        stats = {"P_visible": int((radii > 0).sum().item()), "D": D, "D_visited_bwd": D_visited,
-                 "tile_list_mean": float(lens.mean().item()), "tile_list_max": int(lens.max().item()),
-                 "n_contrib_mean": float(nc.float().mean().item())}
+    # ---- drop-in single-view leg: GaussianRasterizer.forward + loss.backward() per camera (train.py:111-142) ----
+    single_view = None
+    if not a.no_single_view and not a.optimizer:
+        def one_view(i):
+            pkg = render(cams[i % V], pc, pipe, bg)
+            (pkg["render"] - gt_dev[i % V]).abs().mean().backward()
+        for i in range(2 * V):
+            one_view(i)
+        torch.cuda.synchronize()
+        n_sv = max(V, min(a.steps * V, 64))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gc.collect(); gc.disable()
+        e0.record()
+        for i in range(n_sv):
+            one_view(i)
+        e1.record()
+        torch.cuda.synchronize()
+        gc.enable()
+        sv_ms = e0.elapsed_time(e1) / n_sv
+        single_view = {"value": H * W / 1e6 / (sv_ms / 1e3), "unit": UNIT, "ms_per_view": sv_ms, "views_timed": n_sv,
+                       "api": "gaussian_renderer.render() -> GaussianRasterizer.forward + loss.backward(), one camera per iteration, "
+                              "per rank (not aggregated over ranks)"}
+
+    # ---- instance statistics of every view of the step + per-kernel breakdown (outside the timed regions) ----
+    def view_stats(cam):
+        with torch.no_grad():
+            rs = dgr.GaussianRasterizationSettings(H, W, math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5), bg, 1.0,
+                                                   cam.world_view_transform, cam.full_proj_transform, a.sh_degree,
+                                                   cam.camera_center, False, False, False)
+            _, radii, _, pack = dgr._forward_impl(pc.get_xyz.detach(), pc.get_features.detach(), None, pc.get_opacity.detach().reshape(-1),
+                                                  pc.get_scaling.detach(), pc.get_rotation.detach(), None, rs)
+            sv = dgr.state_views(pack, H, W)
+            lens = (sv["ranges"][:, 1] - sv["ranges"][:, 0]).float()
+            nc = sv["n_contrib"]
+            gy, gx = (H + 15) // 16, (W + 15) // 16
+            pad = torch.zeros(gy * 16, gx * 16, dtype=nc.dtype, device=dev)
+            pad[:H, :W] = nc
+            tile_max = pad.view(gy, 16, gx, 16).permute(0, 2, 1, 3).reshape(gy * gx, 256).max(dim=1).values
+            return {"P_visible": int((radii > 0).sum().item()), "D": int(pack["num_rendered"]), "D_visited_bwd": int(tile_max.sum().item()),
+                    "tile_list_mean": float(lens.mean().item()), "tile_list_max": int(lens.max().item()),
+                    "n_contrib_mean": float(nc.float().mean().item())}
+    per_view = [view_stats(c) for c in cams]
+    stats = dict(per_view[0])
+    stats["all_views"] = {"D": [p["D"] for p in per_view], "D_visited_bwd": [p["D_visited_bwd"] for p in per_view]}
     dgr.set_option("time_kernels", 2)
     dgr.kernel_time("", reset=True)
     for _ in range(2):
@@ -495,7 +646,8 @@ def main():
     torch.cuda.synchronize()
     breakdown = {}
     for name in ("preprocess_fwd", "sort_hist", "sort_rowscan", "sort_scatter", "scan_reduce", "scan_partials",
-                 "scan_apply", "emit", "tile_ranges", "ranges_from_counts", "render_fwd", "render_bwd", "preprocess_bwd", "adam_step"):
+                 "scan_apply", "count_max", "emit", "tile_ranges", "ranges_from_counts", "tile_order", "render_fwd", "render_bwd",
+                 "preprocess_bwd", "adam_step"):
         t, n = dgr.kernel_time(name)
         breakdown[name] = round(t / (2 * V), 4)
     dgr.kernel_time("", reset=True)
@@ -508,10 +660,15 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (render_bwd); byte counts per DESIGN.md ----
+    # ---- roofline of the dominant kernel (render_bwd); byte counts per DESIGN.md section 4 ----
+    # One launch blends all V views of the step.  Algorithmic bytes: per visited instance id 4 + record 48 + 10 float atomics 40;
+    # per pixel n_contrib 4 + dL/dcolor 12 + forward colour 12.  Forward: id 4 + record 48; per pixel colour 12 + depth 4 + T 4 + count 4.
     npix = H * W
-    bytes_bwd = D_visited * (4 + 48 + 40) + npix * 24
-    bytes_fwd = D_visited * (4 + 48) + npix * 24
+    batched_launch = a.api == "views" and not a.no_batch
+    dv_sum = sum(p["D_visited_bwd"] for p in per_view)
+    views_per_launch = V if batched_launch else 1
+    bytes_bwd = (dv_sum * (4 + 48 + 40) + V * npix * 28) * views_per_launch // V
+    bytes_fwd = (dv_sum * (4 + 48) + V * npix * 24) * views_per_launch // V
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -530,7 +687,8 @@ def main():
     achieved = bytes_bwd / (bwd_avg_ms * 1e-3) / 1e9 if bwd_avg_ms > 0 else 0.0
     roofline = {"kernel": "render_bwd", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
-                "algorithmic_bytes_per_launch": bytes_bwd, "avg_launch_ms": bwd_avg_ms, "launches_timed": bwd_n,
+                "algorithmic_bytes_per_launch": bytes_bwd, "views_per_launch": views_per_launch, "avg_launch_ms": bwd_avg_ms,
+                "launches_timed": bwd_n,
                 # what actually bounds the blend kernels: warp instructions issued (ncu count of the
                 # committed capture) over the live launch time, against 148 SMs x 4 schedulers x the sampled SM clock
                 "issue": (lambda wi, ms, mhz: None if not (wi and ms and mhz) else
@@ -543,6 +701,8 @@ def main():
 
     cpu = None
     if not a.no_cpu_baseline and world == 1:
+        from oracle.c_oracle import set_threads
+        set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
         cs = oracle_settings(cams[0], a.sh_degree)
         t0 = time.perf_counter()
         times, nthreads = cpu_reference_pass(scene, cs, 1)
@@ -551,17 +711,27 @@ def main():
             more, _ = cpu_reference_pass(scene, cs, reps)
             times += more
         cpu = {"value": (H * W / 1e6) * len(times) / sum(times), "unit": UNIT, "cores": nthreads, "kind": "port",
-               "sample": f"{len(times)} full view(s) of the same workload, forward+backward, oracle/gs_oracle.c"}
+               "sample": f"{len(times)} full view(s) of the same workload, forward+backward, oracle/gs_oracle.c",
+               "host_cpus": os.cpu_count()}
 
+    cfg = workload_config(a, world)
+    cfg.update({"sync_free": capacity is not None, "grad_chunks": grad_chunks if world > 1 else 1,
+                "pinned_cores": None if not pinned_cores else f"{pinned_cores[0]}-{pinned_cores[-1]} ({len(pinned_cores)})",
+                "instance_capacity": None if capacity is None else capacity.capacity})
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(a, world), "roofline": roofline,
+            "dtype": "f32", "data": "synthetic", "config": cfg, "roofline": roofline,
             "cpu_baseline": cpu, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps},
+                                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / a.steps,
+                                         "d2h_is": "the step's loss scalar (float32)",
+                                         "h2d_is": "per view: 3xHxW float32 target image + camera matrices, from pinned host memory"},
+            "single_view": single_view,
             "gpu_launches": launches, "clocks": clocks,
             "step_ms": {"resident": step_stats.get(False), "e2e": step_stats.get(True)},
             "attempts": {"resident": attempts, "e2e": e2e_attempts,
-                         "rule": "a leg with a step > 1.5x its median step (host stall) is re-measured, at most twice; the last attempt is reported"}, "scene_stats": stats, "kernel_ms_per_view": breakdown}
+                         "rule": "one timed region per leg; it is repeated only if the sync-free path's instance capacity turned out "
+                                 "too small (capacity_ok false), never because of timing"},
+            "scene_stats": stats, "kernel_ms_per_view": breakdown}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -729,8 +729,8 @@ int32_t gsb_l1_loss_grad(const float *image, const float *target, int64_t n, flo
 }
 
 int32_t gsb_photometric_loss_grad(const float *image, const float *target, int32_t channels, int32_t height, int32_t width,
-                                  float lambda_dssim, float *grad_out, float *loss_accum, gsb_alloc_fn alloc, void *alloc_ctx,
-                                  void *cuda_stream) {
+                                  float lambda_dssim, int32_t clamp_input, float *grad_out, float *loss_accum, gsb_alloc_fn alloc,
+                                  void *alloc_ctx, void *cuda_stream) {
     if (channels < 0 || height < 0 || width < 0 || !alloc ||
         ((size_t)channels * height * width > 0 && (!image || !target || !grad_out || !loss_accum))) {
         set_error("gsb_photometric_loss_grad: bad argument");
@@ -740,7 +740,7 @@ int32_t gsb_photometric_loss_grad(const float *image, const float *target, int32
     if (n == 0) return GSB_OK;
     float *maps = static_cast<float *>(do_alloc(alloc, alloc_ctx, GSB_BUF_SCRATCH2, 3 * n * sizeof(float)));
     if (!maps) return GSB_ERR_ALLOC;
-    return launch_photometric_loss_grad(image, target, channels, height, width, lambda_dssim, grad_out, loss_accum, maps,
+    return launch_photometric_loss_grad(image, target, channels, height, width, lambda_dssim, clamp_input != 0, grad_out, loss_accum, maps,
                                         static_cast<cudaStream_t>(cuda_stream));
 }
 
@@ -751,12 +751,18 @@ static bool store_fits_u32(int64_t P, int32_t sh_coeffs, int32_t n_children) {
 
 int32_t gsb_adam_step(const GsbAdamArgs *a, void *cuda_stream) {
     if (!a || a->P < 0 || a->sh_coeffs < 1 || !store_fits_u32(a->P, a->sh_coeffs, 0) ||
-        (a->P > 0 && (!a->params || !a->grads || !a->exp_avg || !a->exp_avg_sq)) || !(a->bias2_sqrt > 0.0f)) {
+        (a->P > 0 && (!a->params || !a->grads || !a->exp_avg || !a->exp_avg_sq)) || (a->skip_groups & ~0x3f)) {
         set_error("gsb_adam_step: bad argument");
         return GSB_ERR_ARGUMENT;
     }
+    for (int g = 0; g < 6; ++g)
+        if (!((a->skip_groups >> g) & 1) && !(a->bias2_sqrt[g] > 0.0f)) {
+            set_error("gsb_adam_step: bias2_sqrt[%d] must be > 0", g);
+            return GSB_ERR_ARGUMENT;
+        }
+    if ((a->skip_groups & 0x3f) == 0x3f) return GSB_OK;
     return launch_adam_step(a->P, a->sh_coeffs, a->params, a->grads, a->exp_avg, a->exp_avg_sq, a->act, a->visible, a->step_size,
-                            a->beta1, a->beta2, a->eps, a->bias2_sqrt, static_cast<cudaStream_t>(cuda_stream));
+                            a->beta1, a->beta2, a->eps, a->bias2_sqrt, (uint32_t)a->skip_groups, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int32_t gsb_activate(int64_t P, int32_t sh_coeffs, const float *params, float *act, void *cuda_stream) {

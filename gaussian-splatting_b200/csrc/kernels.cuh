@@ -109,13 +109,13 @@ int launch_render_bwd(const RenderBwdArgs &a, bool debug, cudaStream_t stream);
 int launch_tile_order(const uint2 *ranges, int V, int num_tiles, uint32_t *order, bool debug, cudaStream_t stream);
 int launch_l1_loss_grad(const float *img, const float *gt, int64_t n, float scale, float *grad, float *loss_accum,
                         cudaStream_t stream);
-int launch_photometric_loss_grad(const float *img, const float *gt, int C, int H, int W, float lambda_dssim, float *grad,
-                                 float *loss_accum, float *maps, cudaStream_t stream);
+int launch_photometric_loss_grad(const float *img, const float *gt, int C, int H, int W, float lambda_dssim, bool clamp_input,
+                                 float *grad, float *loss_accum, float *maps, cudaStream_t stream);
 
 // optimizer step and densification on the flat store (optim.cu, densify.cu)
 int launch_adam_step(int64_t P, int sh_coeffs, float *params, const float *grads, float *m, float *v, float *act,
-                     const uint8_t *visible, const float step_size[6], float beta1, float beta2, float eps, float bias2_sqrt,
-                     cudaStream_t stream);
+                     const uint8_t *visible, const float step_size[6], float beta1, float beta2, float eps, const float bias2_sqrt[6],
+                     uint32_t skip_groups, cudaStream_t stream);
 int launch_activate(int64_t P, int sh_coeffs, const float *params, float *act, cudaStream_t stream);
 size_t densify_scratch_bytes(int64_t P, int n_children);
 // exclusive scan of n uint32 (in == out allowed); partials: scan_u32_partials(n) words; *total receives the sum

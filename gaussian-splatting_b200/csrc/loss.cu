@@ -65,7 +65,8 @@ constexpr float SSIM_C1 = 0.01f * 0.01f, SSIM_C2 = 0.03f * 0.03f;
 
 __global__ void __launch_bounds__(SSIM_NT)
 ssim_maps_kernel(const float *__restrict__ img, const float *__restrict__ gt, const int H, const int W, float *__restrict__ M1,
-                 float *__restrict__ M2, float *__restrict__ M3, float *loss_accum, const float w_l1, const float w_ssim) {
+                 float *__restrict__ M2, float *__restrict__ M3, float *loss_accum, const float w_l1, const float w_ssim,
+                 const float lo, const float hi) {
     __shared__ float sx[SSIM_SY][SSIM_SX + 1], sy[SSIM_SY][SSIM_SX + 1];
     __shared__ float h[5][SSIM_SY][SSIM_TX + 1];
     __shared__ float red[2][8];
@@ -76,7 +77,7 @@ ssim_maps_kernel(const float *__restrict__ img, const float *__restrict__ gt, co
         const int gx = x0 + lx - SSIM_R, gy = y0 + ly - SSIM_R;
         float a = 0.f, b = 0.f;
         if (gx >= 0 && gx < W && gy >= 0 && gy < H) {
-            a = fminf(fmaxf(img[plane + (size_t)gy * W + gx], 0.0f), 1.0f);
+            a = fminf(fmaxf(img[plane + (size_t)gy * W + gx], lo), hi);     // [0, 1], or the whole float range (no clamp)
             b = __ldg(gt + plane + (size_t)gy * W + gx);
         }
         sx[ly][lx] = a; sy[ly][lx] = b;
@@ -155,7 +156,7 @@ ssim_maps_kernel(const float *__restrict__ img, const float *__restrict__ gt, co
 __global__ void __launch_bounds__(SSIM_NT)
 ssim_grad_kernel(const float *__restrict__ img, const float *__restrict__ gt, const int H, const int W,
                  const float *__restrict__ M1, const float *__restrict__ M2, const float *__restrict__ M3,
-                 float *__restrict__ grad, const float w_l1, const float w_ssim) {
+                 float *__restrict__ grad, const float w_l1, const float w_ssim, const float lo, const float hi) {
     __shared__ float s[3][SSIM_SY][SSIM_SX + 1];
     __shared__ float h[3][SSIM_SY][SSIM_TX + 1];
     const int x0 = blockIdx.x * SSIM_TX, y0 = blockIdx.y * SSIM_TY, c = blockIdx.z;
@@ -210,24 +211,25 @@ ssim_grad_kernel(const float *__restrict__ img, const float *__restrict__ gt, co
         if (gx >= W || gy >= H) continue;
         const size_t pid = plane + (size_t)gy * W + gx;
         const float raw = img[pid], y = __ldg(gt + pid);
-        const float x = fminf(fmaxf(raw, 0.0f), 1.0f);
+        const float x = fminf(fmaxf(raw, lo), hi);
         const float dssim = g[0][o] + 2.f * x * g[1][o] + y * g[2][o];
         const float d = x - y;
         const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
         const float gv = w_l1 * sgn - w_ssim * dssim;
-        grad[pid] = (raw >= 0.0f && raw <= 1.0f) ? gv : 0.0f;
+        grad[pid] = (raw >= lo && raw <= hi) ? gv : 0.0f;
     }
 }
 
-int launch_photometric_loss_grad(const float *img, const float *gt, int C, int H, int W, float lambda_dssim, float *grad,
-                                 float *loss_accum, float *maps, cudaStream_t stream) {
+int launch_photometric_loss_grad(const float *img, const float *gt, int C, int H, int W, float lambda_dssim, bool clamp_input,
+                                 float *grad, float *loss_accum, float *maps, cudaStream_t stream) {
     if (C <= 0 || H <= 0 || W <= 0) return GSB_OK;
     const size_t n = (size_t)C * H * W;
     const float w_l1 = (1.0f - lambda_dssim) / (float)n, w_ssim = lambda_dssim / (float)n;
     float *M1 = maps, *M2 = maps + n, *M3 = maps + 2 * n;
+    const float lo = clamp_input ? 0.0f : -3.402823466e+38f, hi = clamp_input ? 1.0f : 3.402823466e+38f;
     const dim3 grid((W + SSIM_TX - 1) / SSIM_TX, (H + SSIM_TY - 1) / SSIM_TY, C);
-    GSB_LAUNCH("ssim_maps", false, stream, ssim_maps_kernel, grid, SSIM_NT, 0, img, gt, H, W, M1, M2, M3, loss_accum, w_l1, w_ssim);
-    GSB_LAUNCH("ssim_grad", false, stream, ssim_grad_kernel, grid, SSIM_NT, 0, img, gt, H, W, M1, M2, M3, grad, w_l1, w_ssim);
+    GSB_LAUNCH("ssim_maps", false, stream, ssim_maps_kernel, grid, SSIM_NT, 0, img, gt, H, W, M1, M2, M3, loss_accum, w_l1, w_ssim, lo, hi);
+    GSB_LAUNCH("ssim_grad", false, stream, ssim_grad_kernel, grid, SSIM_NT, 0, img, gt, H, W, M1, M2, M3, grad, w_l1, w_ssim, lo, hi);
     return GSB_OK;
 }
 

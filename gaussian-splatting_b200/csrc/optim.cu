@@ -18,19 +18,20 @@ struct AdamK {
     const float *g;
     float *m, *v, *act;
     const uint8_t *vis;
-    float ss[6];
-    float b1, b2, eps, bc2s;
+    float ss[6], bc2s[6];              // per group: lr / (1 - beta1^t), sqrt(1 - beta2^t) -- every group has its own step count t
+    uint32_t skip;                     // bit g: group g is left untouched (its parameter was just replaced: grad None in the reference)
+    float b1, b2, eps;
 };
 
 struct AdamCoef {
-    float omb1, b2, omb2, eps, bc2s;
+    float omb1, b2, omb2, eps;
 };
 
-__device__ __forceinline__ void adam_update(float &p, float &m, float &v, const float g, const float ss, const AdamCoef &c) {
+__device__ __forceinline__ void adam_update(float &p, float &m, float &v, const float g, const float ss, const float bc2s, const AdamCoef &c) {
     m = m + c.omb1 * (g - m);                       // exp_avg.lerp_(grad, 1 - beta1)
     v = v * c.b2;                                   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2)
     v = v + (c.omb2 * g) * g;
-    const float denom = sqrtf(v) / c.bc2s + c.eps;  // (exp_avg_sq.sqrt() / sqrt(bias_correction2)).add_(eps)
+    const float denom = sqrtf(v) / bc2s + c.eps;  // (exp_avg_sq.sqrt() / sqrt(bias_correction2)).add_(eps)
     p = p + (-ss) * (m / denom);                    // param.addcdiv_(exp_avg, denom, value = -lr / bias_correction1)
 }
 
@@ -38,23 +39,28 @@ __device__ __forceinline__ float sigmoidf_(const float x) { return 1.0f / (1.0f 
 
 __global__ void __launch_bounds__(AD_THREADS)
 adam_step_kernel(const AdamK a) {
-    const AdamCoef c{1.0f - a.b1, a.b2, 1.0f - a.b2, a.eps, a.bc2s};
+    const AdamCoef c{1.0f - a.b1, a.b2, 1.0f - a.b2, a.eps};
     if (blockIdx.x < a.elem_blocks) {
         // ---- xyz, features, opacity, scaling: one stored float per item; element index == item index ----
         const uint32_t base = blockIdx.x * (AD_THREADS * AD_UNROLL) + threadIdx.x;
-        float p[AD_UNROLL], g[AD_UNROLL], m[AD_UNROLL], v[AD_UNROLL], ss[AD_UNROLL];
+        float p[AD_UNROLL], g[AD_UNROLL], m[AD_UNROLL], v[AD_UNROLL], ss[AD_UNROLL], bc[AD_UNROLL];
         int kind[AD_UNROLL];   // -1 skip, 0 identity, 1 sigmoid, 2 exp
 #pragma unroll
         for (int u = 0; u < AD_UNROLL; ++u) {
             const uint32_t e = base + u * AD_THREADS;
             kind[u] = -1;
             if (e >= a.E) continue;
-            uint32_t gi;
-            if (e < a.e_feat) { gi = e / 3u; kind[u] = 0; ss[u] = a.ss[0]; }
-            else if (e < a.e_op) { const uint32_t j = e - a.e_feat; gi = j / a.F; kind[u] = 0; ss[u] = (j - gi * a.F) < 3u ? a.ss[1] : a.ss[2]; }
-            else if (e < a.e_sc) { gi = e - a.e_op; kind[u] = 1; ss[u] = a.ss[3]; }
-            else { gi = (e - a.e_sc) / 3u; kind[u] = 2; ss[u] = a.ss[4]; }
-            if (a.vis && !a.vis[gi]) { kind[u] = -1; continue; }
+            uint32_t gi, skip;     // (static indices only: a dynamic index into the kernel parameters would copy them to local memory)
+            if (e < a.e_feat) { gi = e / 3u; kind[u] = 0; ss[u] = a.ss[0]; bc[u] = a.bc2s[0]; skip = a.skip & 1u; }
+            else if (e < a.e_op) {
+                const uint32_t j = e - a.e_feat;
+                gi = j / a.F; kind[u] = 0;
+                const bool dc = (j - gi * a.F) < 3u;
+                ss[u] = dc ? a.ss[1] : a.ss[2]; bc[u] = dc ? a.bc2s[1] : a.bc2s[2]; skip = dc ? (a.skip & 2u) : (a.skip & 4u);
+            }
+            else if (e < a.e_sc) { gi = e - a.e_op; kind[u] = 1; ss[u] = a.ss[3]; bc[u] = a.bc2s[3]; skip = a.skip & 8u; }
+            else { gi = (e - a.e_sc) / 3u; kind[u] = 2; ss[u] = a.ss[4]; bc[u] = a.bc2s[4]; skip = a.skip & 16u; }
+            if (skip || (a.vis && !a.vis[gi])) { kind[u] = -1; continue; }
             p[u] = a.p[e]; g[u] = a.g[e]; m[u] = a.m[e]; v[u] = a.v[e];
         }
 #pragma unroll
@@ -64,7 +70,7 @@ adam_step_kernel(const AdamK a) {
             float gr = g[u];
             if (kind[u] == 1) { const float y = sigmoidf_(p[u]); gr = (gr * (1.0f - y)) * y; }      // sigmoid_backward
             else if (kind[u] == 2) gr = gr * expf(p[u]);                                              // exp backward
-            adam_update(p[u], m[u], v[u], gr, ss[u], c);
+            adam_update(p[u], m[u], v[u], gr, ss[u], bc[u], c);
             a.p[e] = p[u]; a.m[e] = m[u]; a.v[e] = v[u];
             if (a.act) {
                 if (kind[u] == 1) a.act[e - a.e_op] = sigmoidf_(p[u]);
@@ -75,7 +81,7 @@ adam_step_kernel(const AdamK a) {
     }
     // ---- rotation: one quaternion per item (normalize couples its four components) ----
     const uint32_t i = (blockIdx.x - a.elem_blocks) * AD_THREADS + threadIdx.x;
-    if (i >= a.P || (a.vis && !a.vis[i])) return;
+    if (i >= a.P || ((a.skip >> 5) & 1u) || (a.vis && !a.vis[i])) return;
     const size_t o = (size_t)a.E + 4u * (size_t)i;
     float q[4], g[4], m[4], v[4];
 #pragma unroll
@@ -93,7 +99,7 @@ adam_step_kernel(const AdamK a) {
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        adam_update(q[k], m[k], v[k], gr[k], a.ss[5], c);
+        adam_update(q[k], m[k], v[k], gr[k], a.ss[5], a.bc2s[5], c);
         a.p[o + k] = q[k]; a.m[o + k] = m[k]; a.v[o + k] = v[k];
     }
     if (a.act) {
@@ -120,16 +126,17 @@ activate_kernel(const uint32_t P, const float *__restrict__ opacity, const float
 }
 
 int launch_adam_step(int64_t P, int sh_coeffs, float *params, const float *grads, float *m, float *v, float *act,
-                     const uint8_t *visible, const float step_size[6], float beta1, float beta2, float eps, float bias2_sqrt,
-                     cudaStream_t stream) {
+                     const uint8_t *visible, const float step_size[6], float beta1, float beta2, float eps, const float bias2_sqrt[6],
+                     uint32_t skip_groups, cudaStream_t stream) {
     if (P == 0) return GSB_OK;
     AdamK a;
     a.P = (uint32_t)P; a.F = 3u * (uint32_t)sh_coeffs;
     a.e_feat = 3u * a.P; a.e_op = a.e_feat + a.F * a.P; a.e_sc = a.e_op + a.P; a.E = a.e_sc + 3u * a.P;
     a.elem_blocks = (uint32_t)ceil_div((int64_t)a.E, AD_THREADS * AD_UNROLL);
     a.p = params; a.g = grads; a.m = m; a.v = v; a.act = act; a.vis = visible;
-    for (int k = 0; k < 6; ++k) a.ss[k] = step_size[k];
-    a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.bc2s = bias2_sqrt;
+    for (int k = 0; k < 6; ++k) { a.ss[k] = step_size[k]; a.bc2s[k] = bias2_sqrt[k]; }
+    a.skip = skip_groups;
+    a.b1 = beta1; a.b2 = beta2; a.eps = eps;
     const uint32_t blocks = a.elem_blocks + (uint32_t)ceil_div(P, AD_THREADS);
     GSB_LAUNCH("adam_step", false, stream, adam_step_kernel, blocks, AD_THREADS, 0, a);
     return GSB_OK;

@@ -61,9 +61,9 @@ BUF_GEOM, BUF_BINNING, BUF_IMAGE = 0, 1, 2
 
 
 class _AdamArgs(Structure):          # GsbAdamArgs (include/gs_b200.h)
-    _fields_ = [("P", c_int64), ("sh_coeffs", c_int32), ("reserved", c_int32), ("params", c_void_p), ("grads", c_void_p),
+    _fields_ = [("P", c_int64), ("sh_coeffs", c_int32), ("skip_groups", c_int32), ("params", c_void_p), ("grads", c_void_p),
                 ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p), ("act", c_void_p), ("visible", c_void_p),
-                ("step_size", c_float * 6), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("bias2_sqrt", c_float)]
+                ("step_size", c_float * 6), ("bias2_sqrt", c_float * 6), ("beta1", c_float), ("beta2", c_float), ("eps", c_float)]
 
 
 class _DensifyArgs(Structure):       # GsbDensifyArgs
@@ -106,7 +106,7 @@ def _load(path: Optional[str] = None):
     lib.gsb_l1_loss_grad.restype = c_int32
     lib.gsb_l1_loss_grad.argtypes = [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p]
     lib.gsb_photometric_loss_grad.restype = c_int32
-    lib.gsb_photometric_loss_grad.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_void_p, c_void_p,
+    lib.gsb_photometric_loss_grad.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_int32, c_void_p, c_void_p,
                                               _ALLOC_FN, c_void_p, c_void_p]
     lib.gsb_last_error.restype = c_char_p
     lib.gsb_abi_version.restype = c_int32
@@ -189,23 +189,27 @@ def l1_loss_and_grad(image: torch.Tensor, target: torch.Tensor, loss_accum: Opti
     return loss_accum, grad
 
 
-def photometric_loss_and_grad(image: torch.Tensor, target: torch.Tensor, lambda_dssim: float = 0.2):
+def photometric_loss_and_grad(image: torch.Tensor, target: torch.Tensor, lambda_dssim: float = 0.2, clamp_input: bool = True):
     """The reference training step's loss (train.py:120-126) fused with its gradient:
-    ``(1 - lambda) * mean|x - y| + lambda * (1 - SSIM(x, y))`` with ``x = clamp(image, 0, 1)``; image / target [C,H,W].
+    ``(1 - lambda) * mean|x - y| + lambda * (1 - SSIM(x, y))`` with ``x = clamp(image, 0, 1)`` (render()'s clamp and its
+    gradient mask; ``clamp_input=False``: x = image); image / target [C,H,W].
     Returns (loss[1], dloss/dimage, parts) with parts = tensor [loss, mean L1, mean SSIM] (device, no sync)."""
     _require_cuda(image)
     img, gt = _f32c(image), _f32c(target)
     C, H, W = (int(v) for v in img.shape[-3:])
     grad = torch.empty_like(img)
-    acc = torch.tensor([float(lambda_dssim), 0.0, 0.0], dtype=torch.float32).to(img.device, non_blocking=True)
+    # accumulators [loss - lambda, sum |x - y|, sum SSIM]: created on the device (a host-side tensor would be a pageable copy,
+    # i.e. a host synchronisation in every training step)
+    acc = torch.zeros(3, dtype=torch.float32, device=img.device)
+    acc[:1] += float(lambda_dssim)
     with _device_ctx(img.device):
         stream = _current_stream(img.device)
         arena = _Arena(img.device, stream)
-        rc = _C.gsb_photometric_loss_grad(img.data_ptr(), gt.data_ptr(), C, H, W, float(lambda_dssim), grad.data_ptr(),
-                                          acc.data_ptr(), arena.cb, None, stream)
+        rc = _C.gsb_photometric_loss_grad(img.data_ptr(), gt.data_ptr(), C, H, W, float(lambda_dssim), int(bool(clamp_input)),
+                                          grad.data_ptr(), acc.data_ptr(), arena.cb, None, stream)
     _check(rc, arena)
     n = float(C * H * W)
-    parts = acc / torch.tensor([1.0, n, n], dtype=torch.float32, device=img.device)
+    parts = torch.stack((acc[0], acc[1] / n, acc[2] / n))
     return acc[:1], grad, parts
 
 
@@ -231,17 +235,21 @@ def _stream_of(t: torch.Tensor):
 
 
 def adam_step(params, grads, exp_avg, exp_avg_sq, act, P: int, sh_coeffs: int, step_size, beta1: float, beta2: float,
-              eps: float, bias2_sqrt: float, visible: Optional[torch.Tensor] = None) -> None:
-    """gsb_adam_step over the flat store (layout: include/gs_b200.h); every tensor float32, contiguous, same device."""
+              eps: float, bias2_sqrt, visible: Optional[torch.Tensor] = None, skip_groups: int = 0) -> None:
+    """gsb_adam_step over the flat store (layout: include/gs_b200.h); every tensor float32, contiguous, same device.
+    ``step_size`` / ``bias2_sqrt``: six values (xyz, f_dc, f_rest, opacity, scaling, rotation; a scalar bias2_sqrt is
+    broadcast); ``skip_groups``: bit mask of groups to leave untouched."""
     a = _AdamArgs()
-    a.P, a.sh_coeffs, a.reserved = int(P), int(sh_coeffs), 0
+    a.P, a.sh_coeffs, a.skip_groups = int(P), int(sh_coeffs), int(skip_groups)
     a.params, a.grads, a.exp_avg, a.exp_avg_sq = params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr()
     a.act = act.data_ptr() if act is not None else None
     if visible is not None:
         visible = visible.to(torch.uint8).contiguous()
     a.visible = visible.data_ptr() if visible is not None else None
     a.step_size = (c_float * 6)(*[float(v) for v in step_size])
-    a.beta1, a.beta2, a.eps, a.bias2_sqrt = float(beta1), float(beta2), float(eps), float(bias2_sqrt)
+    b2 = [float(bias2_sqrt)] * 6 if isinstance(bias2_sqrt, (int, float)) else [float(v) for v in bias2_sqrt]
+    a.bias2_sqrt = (c_float * 6)(*b2)
+    a.beta1, a.beta2, a.eps = float(beta1), float(beta2), float(eps)
     stream = _stream_of(params)
     with _device_ctx(params.device):
         _check(_C.gsb_adam_step(byref(a), stream))

@@ -198,7 +198,7 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
     ``loss_fn(image[3,H,W] (clamped to [0,1] like render() does), invdepth[1,H,W], view_index) -> scalar``, or,
     with ``loss_returns_grad=True``, ``loss_fn(raw_image, invdepth, view_index) -> (loss, dL/d raw_image[, dL/d invdepth])``
     for a loss that brings its own gradient (e.g. ``diff_gaussian_rasterization.l1_loss_and_grad``); no autograd then.
-    Returns {"losses": [V] tensor, "radii_max": [P] int32, "images": list (if keep_images)}.
+    Returns {"losses": [V] tensor, "radii_max": [P] int32, "num_rendered": per-view instance counts, "images": list (if keep_images)}.
 
     ``overwrite=True``: the gradient buffers are WRITTEN by the first chunk of views instead of added to, so the
     caller does not have to zero them first (saves one memset and one read pass over the 59 floats/gaussian).
@@ -225,7 +225,7 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
         m2d = torch.empty((P, 3), dtype=torch.float32, device=dev)
     c = {k: _dgr._f32c(v.detach()) for k, v in inputs.items()}
     c["opacities"] = c["opacities"].reshape(-1) if c["opacities"] is not None else None
-    losses, images = [], []
+    losses, images, num_rendered = [], [], []
     radii_max = torch.zeros((P,), dtype=torch.int32, device=dev)
     cams_all = list(viewpoint_cameras) if batched else None
     if batched and cams_all and all(int(cm.image_height) == int(cams_all[0].image_height) and
@@ -240,6 +240,7 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
                                                                     capacity=capacity.capacity if use_async else 0)
             if capacity is not None and not use_async:
                 capacity.learn(pack["num_rendered"])
+            num_rendered.extend(pack["num_rendered"])
             g_color = torch.empty_like(color)
             g_depth = None
             for k in range(len(chunk)):
@@ -282,6 +283,7 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
         rs = _settings_for(cam, pc, pipe, bg_color, scaling_modifier)
         color, radii, invdepth, pack = _dgr._forward_impl(c["means3D"], c["shs"], None, c["opacities"], c["scales"],
                                                           c["rotations"], None, rs)
+        num_rendered.append(pack["num_rendered"])
         if loss_returns_grad:
             res = loss_fn(color, invdepth, vi)
             loss, g_img = res[0], res[1]
@@ -318,7 +320,10 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
             chain_g.append(g.view_as(v))
     if chain_t:
         torch.autograd.backward(chain_t, chain_g)
-    out = {"losses": torch.stack(losses) if losses else torch.zeros(0, device=dev), "radii_max": radii_max}
+    if hasattr(pc, "gradients_ready"):      # gaussian_store.GaussianModel: its gradient buffer now belongs to the current parameters
+        pc.gradients_ready()
+    out = {"losses": torch.stack(losses) if losses else torch.zeros(0, device=dev), "radii_max": radii_max,
+           "num_rendered": num_rendered}      # per view; -1 on the sync-free path (known to the device only)
     if keep_images:
         out["images"] = images
     return out

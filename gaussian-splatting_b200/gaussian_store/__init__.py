@@ -30,6 +30,49 @@ import diff_gaussian_rasterization as _dgr
 
 __all__ = ["GaussianModel", "expon_lr", "store_offsets"]
 
+
+class _StoreBucket:
+    """GaussianModel.grad as the data-parallel bucket: one all-reduce for everything, or row ranges of the five groups
+    (xyz | features | opacity | scaling | rotation) as one coalesced launch (overlapped with the chunked gradient kernel)."""
+
+    def __init__(self, model):
+        self.m = model
+
+    def zero_(self):
+        self.m.grad.zero_()
+
+    def _segments(self, p0, p1):
+        m = self.m
+        o, P, M = store_offsets(m.P, m.sh_coeffs), m.P, m.sh_coeffs
+        widths = (("xyz", 3), ("features", 3 * M), ("opacity", 1), ("scaling", 3), ("rotation", 4))
+        return [m.grad[o[n] + w * p0:o[n] + w * p1] for n, w in widths if p1 > p0]
+
+    def all_reduce_rows(self, p_begin: int, p_end: int, group=None):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return []
+        segs = self._segments(p_begin, p_end)
+        if not segs:
+            return []
+        manager = getattr(dist, "_coalescing_manager", None)
+        if manager is None:
+            return [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True) for t in segs]
+        with manager(group=group, async_ops=True) as cm:
+            for t in segs:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return [cm]
+
+    @staticmethod
+    def wait_all(handles) -> None:
+        for h in handles:
+            h.wait()
+
+    def all_reduce(self, group=None):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.m.grad, op=dist.ReduceOp.SUM, group=group)
+        return self.m.grad
+
 GROUPS = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")
 
 
@@ -63,7 +106,11 @@ class GaussianModel:
         self.max_radii2D = self.xyz_gradient_accum = self.denom = None
         self.percent_dense = 0.0
         self.spatial_lr_scale = 0.0
-        self.step_count = 0
+        self.step_count = 0                                   # optimizer_step() calls that updated at least one group
+        self.group_steps = {n: 0 for n in GROUPS}             # torch.optim.Adam keeps one step count PER PARAMETER
+        self._skip_next = set()                               # groups whose parameter was replaced since the last backward
+        self.densify_seed = 0                                 # seed of the split-sample draws (identical on every data-parallel rank)
+        self._densify_calls = 0
         self.lr: Dict[str, float] = {}
         self.betas, self.eps = (0.9, 0.999), 1e-15
         self._xyz_sched = None
@@ -196,6 +243,8 @@ class GaussianModel:
                                lr_final=g("position_lr_final") * self.spatial_lr_scale,
                                lr_delay_mult=g("position_lr_delay_mult"), max_steps=int(g("position_lr_max_steps")))
         self.step_count = 0
+        self.group_steps = {n: 0 for n in GROUPS}
+        self._skip_next = set()
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
 
@@ -204,21 +253,45 @@ class GaussianModel:
         return self.lr["xyz"]
 
     def step_sizes(self):
-        """(step_size per group, sqrt(1 - beta2^t)) of the NEXT step, as torch.optim.Adam computes them in double."""
-        t = self.step_count + 1
+        """(step_size, sqrt(1 - beta2^t)) per group for the NEXT step, as torch.optim.Adam computes them in double, each
+        group with its own step count."""
         if self.optimizer_type == "sparse_adam":
             # [RECALL, UNVERIFIED_VS_REFERENCE] the accel branch's SparseGaussianAdam applies no bias correction
-            return [self.lr[n] for n in GROUPS], 1.0
-        bc1 = 1.0 - self.betas[0] ** t
-        return [self.lr[n] / bc1 for n in GROUPS], math.sqrt(1.0 - self.betas[1] ** t)
+            return [self.lr[n] for n in GROUPS], [1.0] * len(GROUPS)
+        t = {n: self.group_steps[n] + 1 for n in GROUPS}
+        return ([self.lr[n] / (1.0 - self.betas[0] ** t[n]) for n in GROUPS],
+                [math.sqrt(1.0 - self.betas[1] ** t[n]) for n in GROUPS])
 
     def optimizer_step(self, visible: Optional[torch.Tensor] = None):
         """``optimizer.step()``: consumes ``self.grad`` (dLoss/d activated), updates the store and both moments in place and
-        rewrites the activated tensors.  ``visible`` ([P] bool): rows with False are left untouched (train.py:181-183)."""
+        rewrites the activated tensors.  ``visible`` ([P] bool): rows with False are left untouched (train.py:181-183).
+
+        Groups whose parameter ``densify_and_prune`` / ``reset_opacity`` replaced AFTER the gradients were computed are
+        SKIPPED: in the reference the fresh nn.Parameter has ``grad is None`` when train.py:178-186 reaches
+        ``optimizer.step()``, so Adam neither updates it, nor decays its moments, nor advances its step count.  The store
+        cannot see a backward pass happen, so the contract is explicit: whoever fills ``self.grad`` calls
+        ``gradients_ready()`` afterwards (``gaussian_renderer.render_views_backward`` does); replacements made after that
+        call are the ones skipped here."""
+        skip = sum(1 << k for k, n in enumerate(GROUPS) if n in self._skip_next)
+        self._skip_next = set()
+        if skip == (1 << len(GROUPS)) - 1:
+            return
         ss, b2s = self.step_sizes()
         _dgr.adam_step(self.store, self.grad, self.exp_avg, self.exp_avg_sq, self.act, self.P, self.sh_coeffs, ss, self.betas[0],
-                       self.betas[1], self.eps, b2s, visible)
+                       self.betas[1], self.eps, b2s, visible, skip_groups=skip)
+        for k, n in enumerate(GROUPS):
+            if not (skip >> k) & 1:
+                self.group_steps[n] += 1
         self.step_count += 1
+
+    def gradients_ready(self):
+        """``self.grad`` now holds the gradients of the CURRENT parameters (a backward pass has just run): replacements made
+        before this point no longer make ``optimizer_step`` skip anything."""
+        self._skip_next = set()
+
+    def gradient_bucket(self):
+        """The gradient buffer as the data-parallel bucket (same interface as gaussian_renderer.GradientBucket)."""
+        return _StoreBucket(self)
 
     def zero_grad(self):
         self.grad.zero_()
@@ -237,13 +310,19 @@ class GaussianModel:
         ``torch.normal(mean=0, std=stds)`` with the same shape).  ``unit_samples``: the standard normals to use instead, a
         tensor [n_children * n_split, 3] or a callable ``rows -> tensor`` (tests replaying a recorded draw)."""
         dev = self.store.device
+        if self.P == 0:
+            return {"n_clone": 0, "n_split": 0, "n_pruned": 0, "P": 0}
         args, keep, (n_clone, n_split, n_pruned, P_new) = _dgr.densify_plan(
             self.store, self.exp_avg, self.exp_avg_sq, self.xyz_gradient_accum, self.denom, self.P, self.sh_coeffs, n_children,
             max_grad, self.percent_dense * extent, min_opacity, 0.1 * extent if max_screen_size else -1.0)
         if not n_split:
             unit = None
         elif unit_samples is None:
-            unit = torch.randn((n_children * n_split, 3), device=dev)
+            # Data-parallel replicas must draw IDENTICAL children: a dedicated generator seeded from (densify_seed, number of
+            # densifications so far) instead of the process-wide one, whose state depends on everything else a rank has drawn.
+            gen = torch.Generator(device=dev)
+            gen.manual_seed((int(self.densify_seed) * 1000003 + self._densify_calls) & 0x7FFFFFFFFFFFFFFF)
+            unit = torch.randn((n_children * n_split, 3), device=dev, generator=gen)
         else:
             unit = unit_samples(n_children * n_split) if callable(unit_samples) else unit_samples
             unit = unit.to(device=dev, dtype=torch.float32).reshape(n_children * n_split, 3).contiguous()
@@ -261,6 +340,8 @@ class GaussianModel:
         self.xyz_gradient_accum = torch.zeros((P_new, 1), device=dev)
         self.denom = torch.zeros((P_new, 1), device=dev)
         self.max_radii2D = torch.zeros(P_new, device=dev)
+        self._densify_calls += 1
+        self._skip_next = set(GROUPS)          # every parameter was replaced: the pending optimizer_step() is a no-op (see there)
         return {"n_clone": n_clone, "n_split": n_split, "n_pruned": n_pruned, "P": P_new}
 
     def reset_opacity(self):
@@ -272,6 +353,7 @@ class GaussianModel:
             self.store[a:a + n] = torch.log(y / (1.0 - y))
             self.exp_avg[a:a + n] = 0.0
             self.exp_avg_sq[a:a + n] = 0.0
+        self._skip_next.add("opacity")         # replace_tensor_to_optimizer: a fresh parameter, grad None until the next backward
         self._reactivate()
 
     # ---- point_cloud.ply (save_ply :239-256, load_ply :263-314) --------------------------------------------------------
@@ -295,6 +377,7 @@ class GaussianModel:
                     exp_avg=self.exp_avg.clone(), exp_avg_sq=self.exp_avg_sq.clone(), max_radii2D=self.max_radii2D.clone(),
                     xyz_gradient_accum=None if self.xyz_gradient_accum is None else self.xyz_gradient_accum.clone(),
                     denom=None if self.denom is None else self.denom.clone(), step_count=self.step_count, lr=dict(self.lr),
+                    group_steps=dict(self.group_steps), densify_seed=self.densify_seed, densify_calls=self._densify_calls,
                     xyz_sched=self._xyz_sched, percent_dense=self.percent_dense, spatial_lr_scale=self.spatial_lr_scale)
 
     def restore(self, state: dict):
@@ -309,6 +392,9 @@ class GaussianModel:
         self.xyz_gradient_accum = None if state["xyz_gradient_accum"] is None else state["xyz_gradient_accum"].clone()
         self.denom = None if state["denom"] is None else state["denom"].clone()
         self.step_count, self.lr, self._xyz_sched = int(state["step_count"]), dict(state["lr"]), state["xyz_sched"]
+        self.group_steps = dict(state.get("group_steps") or {n: self.step_count for n in GROUPS})
+        self.densify_seed, self._densify_calls = int(state.get("densify_seed", 0)), int(state.get("densify_calls", 0))
+        self._skip_next = set()
         self.percent_dense, self.spatial_lr_scale = float(state["percent_dense"]), float(state["spatial_lr_scale"])
         self._reactivate()
         return self

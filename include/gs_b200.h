@@ -200,13 +200,14 @@ int32_t gsb_l1_loss_grad(const float *image, const float *target, int64_t n, flo
                          float *loss_accum, void *cuda_stream);
 
 /* The reference training step's photometric loss fused with its gradient:
- *   loss = (1 - lambda) * mean|x - y| + lambda * (1 - SSIM(x, y)),  x = clamp(image, 0, 1)
+ *   loss = (1 - lambda) * mean|x - y| + lambda * (1 - SSIM(x, y)),  x = clamp(image, 0, 1) when clamp_input != 0 (render()'s
+ *   clamp, gaussian_renderer/__init__.py:119, with its gradient mask) and x = image otherwise (the fused_ssim drop-in)
  * (train.py:120-126, utils/loss_utils.py:40-86; 11x11 gaussian window, sigma 1.5, zero padding).  image / target are
  * [channels, height, width]; grad_out = d loss / d image; loss_accum[0] += loss - lambda (add lambda on the host side,
  * or pre-load it), loss_accum[1] += sum|x - y| * (1-lambda > 0), loss_accum[2] += sum of the SSIM map. */
 int32_t gsb_photometric_loss_grad(const float *image, const float *target, int32_t channels, int32_t height,
-                                  int32_t width, float lambda_dssim, float *grad_out, float *loss_accum,
-                                  gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream);
+                                  int32_t width, float lambda_dssim, int32_t clamp_input, float *grad_out,
+                                  float *loss_accum, gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream);
 
 /* ---- Training state around the path -------------------------------------
  * The gaussians' RAW parameters live in ONE flat float buffer ("store"), group after group, each group [P, width]
@@ -221,16 +222,17 @@ int32_t gsb_photometric_loss_grad(const float *image, const float *target, int32
 typedef struct GsbAdamArgs {
     int64_t P;
     int32_t sh_coeffs;
-    int32_t reserved;
+    int32_t skip_groups;      /* bit g set: group g (order below) is left untouched -- the reference's optimizer.step() skips a
+                                 parameter that densify_and_prune / reset_opacity has just replaced (its .grad is None) */
     float *params;            /* store, updated in place */
     const float *grads;       /* dLoss/d activated, same layout */
     float *exp_avg;
     float *exp_avg_sq;
     float *act;               /* rewritten from the updated parameters; may be NULL */
     const uint8_t *visible;   /* NULL = every gaussian; else rows with visible[i] == 0 are left untouched */
-    float step_size[6];       /* lr_g / (1 - beta1^t) for xyz, f_dc, f_rest, opacity, scaling, rotation */
+    float step_size[6];       /* lr_g / (1 - beta1^t_g) for xyz, f_dc, f_rest, opacity, scaling, rotation */
+    float bias2_sqrt[6];      /* sqrt(1 - beta2^t_g); t_g is the group's OWN step count (torch.optim.Adam keeps one per parameter) */
     float beta1, beta2, eps;
-    float bias2_sqrt;         /* sqrt(1 - beta2^t) */
 } GsbAdamArgs;
 
 /* torch.optim.Adam (no weight decay, no amsgrad; scene/gaussian_model.py:176-199, train.py:178-186) over the six parameter

@@ -47,6 +47,8 @@ def lib():
         L.gso_n_contrib.restype = POINTER(c_int)
         L.gso_n_contrib.argtypes = [c_void_p]
         L.gso_threads.restype = c_int
+        L.gso_set_threads.restype = None
+        L.gso_set_threads.argtypes = [c_int]
         _lib = L
     return _lib
 
@@ -134,3 +136,9 @@ class COracle:
 
 def threads() -> int:
     return int(lib().gso_threads())
+
+
+def set_threads(n: int) -> int:
+    """OpenMP thread count of the oracle's loops (torchrun exports OMP_NUM_THREADS=1); returns the count in effect."""
+    lib().gso_set_threads(int(n))
+    return threads()

@@ -182,6 +182,15 @@ int gso_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the timed CPU legs of bench.py ask for the cores explicitly */
+void gso_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 void gso_free(GsoState *s) {
     if (!s) return;
     free(s->depth); free(s->xy); free(s->conic_o); free(s->rgb); free(s->cov3d); free(s->radii);

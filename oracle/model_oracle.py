@@ -72,20 +72,38 @@ class ModelOracle:
         return expon_lr(iteration, o["position_lr_init"] * self.scale, o["position_lr_final"] * self.scale,
                         o["position_lr_delay_mult"], int(o["position_lr_max_steps"]))
 
-    def step(self, iteration: int, act_grads: Dict[str, torch.Tensor]) -> None:
-        """One optimizer step given dLoss/d(activated tensors): autograd chains them to the raw parameters."""
+    def backward(self, iteration: int, act_grads: Dict[str, torch.Tensor]) -> None:
+        """``loss.backward()`` of train.py:144 given dLoss/d(activated tensors): autograd chains them to the raw parameters."""
         for grp in self.adam.param_groups:
             if grp["name"] == "xyz":
                 grp["lr"] = self.lr_xyz(iteration)
         act = self.activated()
         names = list(act_grads)
         torch.autograd.backward([act[n] for n in names], [act_grads[n].reshape(act[n].shape) for n in names])
+
+    def optimizer_step(self) -> None:
+        """train.py:178-186.  A parameter that densify_and_prune / reset_opacity replaced since the backward pass has
+        ``grad is None`` and is skipped by torch.optim.Adam: no update, no moment decay, no step-count increment."""
         self.adam.step()
         self.adam.zero_grad(set_to_none=True)
 
-    # --- optimizer-state surgery -----------------------------------------------------------------------------------
-    def _rebuild(self, fn_param, fn_moment) -> None:
+    def step(self, iteration: int, act_grads: Dict[str, torch.Tensor]) -> None:
+        self.backward(iteration, act_grads)
+        self.optimizer_step()
+
+    def steps(self) -> Dict[str, float]:
+        out = {}
         for grp in self.adam.param_groups:
+            st = self.adam.state.get(grp["params"][0])
+            out[grp["name"]] = float(st["step"]) if st is not None and "step" in st else 0.0
+        return out
+
+    # --- optimizer-state surgery -----------------------------------------------------------------------------------
+    def _rebuild(self, fn_param, fn_moment, only=None) -> None:
+        """Replaces the parameter (a fresh nn.Parameter: grad None) and moments of every group, or of the group ``only``."""
+        for grp in self.adam.param_groups:
+            if only is not None and grp["name"] != only:
+                continue
             old = grp["params"][0]
             st = self.adam.state.pop(old, None)
             new = torch.nn.Parameter(fn_param(grp["name"], old.detach()))
@@ -108,7 +126,7 @@ class ModelOracle:
     def reset_opacity(self) -> None:
         a = torch.minimum(torch.sigmoid(self.p["opacity"].detach()), torch.tensor(0.01))
         new = torch.log(a / (1.0 - a))
-        self._rebuild(lambda n, t: new if n == "opacity" else t, lambda n, t: torch.zeros_like(t) if n == "opacity" else t)
+        self._rebuild(lambda n, t: new, lambda n, t: torch.zeros_like(t), only="opacity")   # replace_tensor_to_optimizer :302-314
 
     # --- densification -----------------------------------------------------------------------------------------------
     def densify_and_prune(self, max_grad: float, min_opacity: float, extent: float, max_screen_size: Optional[float],

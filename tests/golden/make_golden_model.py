@@ -72,7 +72,7 @@ pc.training_setup(opt)
 # A loss whose gradient w.r.t. the ACTIVATED tensors is w + u * act (state dependent, reproducible by the tests)
 names = ("xyz", "features", "opacity", "scaling", "rotation")
 shapes = {"xyz": (3,), "features": (16, 3), "opacity": (1,), "scaling": (3,), "rotation": (4,)}
-MAXP = 2 * P0
+MAXP = 4 * P0
 W = {n: torch.randn(MAXP, *shapes[n], generator=g) * 1e-3 for n in names}
 U = {n: torch.randn(MAXP, *shapes[n], generator=g) * 1e-3 for n in names}
 for n in names:
@@ -155,6 +155,59 @@ pc.densify_and_prune(opt.densify_grad_threshold, 0.005, EXTENT, None, torch.zero
 snapshot("d2")
 out["d2_P"] = np.int64(pc.get_xyz.shape[0])
 print("densify 2: P", P, "->", pc.get_xyz.shape[0])
+
+# ---- train.py order (train.py:139-190): loss.backward() FIRST, then densify_and_prune / reset_opacity replace parameters (a
+# fresh nn.Parameter has .grad None), THEN optimizer.step(): torch.optim.Adam skips every replaced parameter -- no update, no
+# moment decay, no increment of that parameter's own step counter (which drives its bias correction from then on).
+def backward_only(iteration):
+    pc.update_learning_rate(iteration)
+    act = activated()
+    P = pc.get_xyz.shape[0]
+    loss = sum((W[n][:P] * act[n]).sum() + 0.5 * (U[n][:P] * act[n] ** 2).sum() for n in names)
+    loss.backward()
+
+
+def snapshot_steps(tag):
+    for grp in pc.optimizer.param_groups:
+        st = pc.optimizer.state.get(grp["params"][0], None)
+        out[f"{tag}_step_{grp['name']}"] = np.float64(float(st["step"]) if st is not None and "step" in st else 0.0)
+
+
+it += 1
+backward_only(it)
+P = pc.get_xyz.shape[0]
+assert P <= MAXP
+denom3 = torch.randint(0, 3, (P, 1), generator=g).float()
+accum3 = torch.rand(P, 1, generator=g) * 0.0004 * denom3
+pc.xyz_gradient_accum, pc.denom = accum3.clone(), denom3.clone()
+out.update(dens3_accum=accum3.numpy(), dens3_denom=denom3.numpy())
+torch.manual_seed(79)
+pc.densify_and_prune(opt.densify_grad_threshold, 0.005, EXTENT, 20, torch.zeros(P).int())
+pc.optimizer.step()                                   # every parameter was just replaced: a no-op
+pc.optimizer.zero_grad(set_to_none=True)
+snapshot("t1")
+snapshot_steps("t1")
+out["t1_P"] = np.int64(pc.get_xyz.shape[0])
+print("densify 3 (train.py order): P", P, "->", pc.get_xyz.shape[0])
+assert pc.get_xyz.shape[0] <= MAXP
+
+it += 1
+train_step(it)
+snapshot("t2")
+snapshot_steps("t2")
+
+it += 1
+backward_only(it)
+pc.reset_opacity()                                    # only the opacity parameter is replaced
+pc.optimizer.step()                                   # five groups step, opacity does not
+pc.optimizer.zero_grad(set_to_none=True)
+snapshot("t3")
+snapshot_steps("t3")
+
+it += 1
+train_step(it)                                        # opacity's step counter now lags the others by two
+snapshot("t4")
+snapshot_steps("t4")
 
 for k in ("position_lr_init", "position_lr_final", "position_lr_delay_mult", "position_lr_max_steps", "feature_lr", "opacity_lr",
           "scaling_lr", "rotation_lr", "percent_dense", "densify_grad_threshold"):

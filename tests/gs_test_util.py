@@ -70,6 +70,7 @@ def run_oracle(args, cam, wc=None, wd=None):
 
 
 def assert_image_close(a, b, what):
+    """Returns (max abs err, fraction of values beyond FWD_ABS_TOL).  ``count_flips`` gives the count itself."""
     err = np.abs(a - b)
     bad = err > FWD_ABS_TOL
     frac = float(bad.mean())
@@ -78,18 +79,48 @@ def assert_image_close(a, b, what):
     return float(err.max()), frac
 
 
-def assert_grads_close(g, ref, tol=GRAD_REL_TOL, flips=0.0):
-    """Relative to each tensor's max magnitude.  `flips`: extra absolute slack per tensor scale when the forward
-    comparison saw threshold flips (each flip perturbs a few gradient entries)."""
-    worst = {}
+def count_flips(a, b) -> int:
+    """Pixels (any channel) whose forward value differs by more than FWD_ABS_TOL: threshold flips."""
+    bad = np.abs(a - b) > FWD_ABS_TOL
+    return int(bad.reshape(-1, bad.shape[-2], bad.shape[-1]).any(axis=0).sum())
+
+
+# A flipped (pixel, gaussian) pair perturbs the gradient rows of that gaussian and, much more weakly, of the gaussians behind
+# it in that pixel.  Entries allowed beyond the tight bound per counted flip and per float of the tensor's row:
+FLIP_FANOUT = 8
+FLIP_GRAD_REL = 5e-3    # ... and none of them may exceed this (relative to the tensor's max magnitude)
+
+
+def grad_error_stats(g, ref, tol=GRAD_REL_TOL):
+    """Per gradient tensor: max-norm relative error (|v - r|_max / |r|_max), relative L2 error, the number of entries beyond
+    tol * |r|_max, and the element-wise relative error with an absolute floor of 1e-3 * rms(r) at its 99.9th percentile."""
+    out = {}
     for k, r in ref.items():
         if r is None:
             continue
-        v = g.get("shs" if k == "shs" else k)
+        v = g.get(k)
         assert v is not None, f"missing gradient {k}"
-        v = v.reshape(r.shape)
-        scale = np.abs(r).max() + 1e-20
-        rel = np.abs(v - r).max() / scale
-        worst[k] = float(rel)
-        assert rel <= tol + flips, f"grad {k}: rel err {rel:.3e} (scale {scale:.3e})"
-    return worst
+        v = v.reshape(r.shape).astype(np.float64)
+        r64 = r.astype(np.float64)
+        scale = np.abs(r64).max() + 1e-20
+        err = np.abs(v - r64)
+        rms = float(np.sqrt((r64 ** 2).mean())) + 1e-30
+        elem = err / (np.abs(r64) + 1e-3 * rms)
+        out[k] = {"rel_max": float(err.max() / scale), "rel_l2": float(np.sqrt((err ** 2).sum()) / (np.sqrt((r64 ** 2).sum()) + 1e-30)),
+                  "n_beyond_tol": int((err > tol * scale).sum()), "row_floats": int(np.prod(r.shape[1:])) if r.ndim > 1 else 1,
+                  "elementwise_rel_p999": float(np.quantile(elem, 0.999)) if elem.size else 0.0, "scale": float(scale)}
+    return out
+
+
+def assert_grads_close(g, ref, tol=GRAD_REL_TOL, flips=0):
+    """Every entry within tol * (the tensor's max magnitude), EXCEPT at most FLIP_FANOUT * flips rows' worth of entries per
+    tensor, which must stay within FLIP_GRAD_REL.  ``flips`` is the COUNTED number of forward threshold flips
+    (count_flips), so with an exact forward match the bound is the plain 1e-4.  Returns {tensor: rel_max}."""
+    flips = int(flips)
+    stats = grad_error_stats(g, ref, tol)
+    for k, st in stats.items():
+        allowed = FLIP_FANOUT * flips * st["row_floats"]
+        assert st["n_beyond_tol"] <= allowed, (f"grad {k}: {st['n_beyond_tol']} entries beyond {tol:g} x max (allowed {allowed} for "
+                                                f"{flips} counted flips); rel_max {st['rel_max']:.3e}, scale {st['scale']:.3e}")
+        assert st["rel_max"] <= (FLIP_GRAD_REL if flips else tol), f"grad {k}: rel err {st['rel_max']:.3e} with {flips} flips"
+    return {k: st["rel_max"] for k, st in stats.items()}

@@ -38,7 +38,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(dgr._Inputs) == 64
     assert ctypes.sizeof(dgr._State) == 128
     assert ctypes.sizeof(dgr._Grads) == 64
-    assert ctypes.sizeof(dgr._AdamArgs) == 104
+    assert ctypes.sizeof(dgr._AdamArgs) == 128
     assert ctypes.sizeof(dgr._DensifyArgs) == 80
 
 
@@ -53,7 +53,7 @@ def test_ctypes_mirrors_agree_with_the_c_compiler(tmp_path):
         pytest.skip("no C compiler")
     sys.path.insert(0, os.path.join(ROOT, "gaussian-splatting_b200"))
     import diff_gaussian_rasterization as dgr
-    probes = {"GsbAdamArgs": (dgr._AdamArgs, ["P", "params", "visible", "step_size", "beta1", "bias2_sqrt"]),
+    probes = {"GsbAdamArgs": (dgr._AdamArgs, ["P", "skip_groups", "params", "visible", "step_size", "bias2_sqrt", "beta1", "eps"]),
               "GsbDensifyArgs": (dgr._DensifyArgs, ["P", "n_children", "params", "denom", "grad_threshold", "world_limit", "scratch"]),
               "GsbSettings": (dgr._Settings, []), "GsbInputs": (dgr._Inputs, []), "GsbState": (dgr._State, []), "GsbGrads": (dgr._Grads, [])}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gs_b200.h"', 'int main(void) {']

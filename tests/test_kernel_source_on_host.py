@@ -58,67 +58,8 @@ def test_scan_source_multi_tile(emul):
 
 
 def test_kernel_sources_replay_reference_fixture(on_host):
-    gold = {k: v for k, v in np.load(GOLD).items()}
-    opt = {k[4:]: float(v) for k, v in gold.items() if k.startswith("opt_")}
-    extent = float(gold["dens_extent"])
-    t = lambda k: torch.from_numpy(gold["init" + RAW_KEY[k]])
-    m = GaussianModel(3).create_from_tensors(t("xyz"), t("f_dc"), t("f_rest"), t("scaling"), t("rotation"), t("opacity"), extent)
-    m.training_setup(SimpleNamespace(**opt))
-
-    def step(it):
-        m.update_learning_rate(it)
-        act = {"xyz": m.get_xyz, "features": m.get_features, "opacity": m.get_opacity, "scaling": m.get_scaling,
-               "rotation": m.get_rotation}
-        for n in ACT:
-            g = torch.from_numpy(gold["w_" + n][:m.P]) + torch.from_numpy(gold["u_" + n][:m.P]) * act[n].detach()
-            act[n].grad.copy_(g.view_as(act[n]))
-        m.optimizer_step()
-
-    def check(tag):
-        raw = {"xyz": m._xyz, "f_dc": m._features_dc, "f_rest": m._features_rest, "opacity": m._opacity, "scaling": m._scaling,
-               "rotation": m._rotation}
-        for n in GROUPS:
-            ref = torch.from_numpy(gold[tag + RAW_KEY[n]])
-            assert tuple(raw[n].shape) == tuple(ref.shape), (tag, n, raw[n].shape, ref.shape)
-            torch.testing.assert_close(raw[n], ref, rtol=2e-6, atol=2e-6, msg=lambda s: f"{tag} {n}: {s}")
-        P, M, o = m.P, m.sh_coeffs, store_offsets(m.P, m.sh_coeffs)
-        for kind, buf in (("m", m.exp_avg), ("v", m.exp_avg_sq)):
-            feat = buf[o["features"]:o["opacity"]].view(P, M, 3)
-            got = {"xyz": buf[:3 * P].view(P, 3), "f_dc": feat[:, :1], "f_rest": feat[:, 1:], "opacity": buf[o["opacity"]:o["scaling"]].view(P, 1),
-                   "scaling": buf[o["scaling"]:o["rotation"]].view(P, 3), "rotation": buf[o["rotation"]:].view(P, 4)}
-            for n in GROUPS:
-                torch.testing.assert_close(got[n], torch.from_numpy(gold[f"{tag}_{kind}_{n}"]), rtol=1e-4,
-                                           atol=1e-9 if kind == "m" else 1e-13, msg=lambda s: f"{tag} {kind} {n}: {s}")
-
-    def densify(key, seed, max_screen):
-        m.xyz_gradient_accum = torch.from_numpy(gold[key + "_accum"]).clone()
-        m.denom = torch.from_numpy(gold[key + "_denom"]).clone()
-
-        def draw(rows):
-            torch.manual_seed(seed)
-            return torch.randn(rows, 3)
-
-        info = m.densify_and_prune(opt["densify_grad_threshold"], 0.005, extent, max_screen, unit_samples=draw)
-        assert info["P"] == int(gold["d_P" if key == "dens" else "d2_P"]), info
-        assert info["n_clone"] > 0 and info["n_split"] > 0
-
-    it = 0
-    for _ in range(3):
-        it += 1
-        step(it)
-    check("s3")
-    densify("dens", 77, 20)
-    check("d")
-    for _ in range(2):
-        it += 1
-        step(it)
-    check("s5")
-    m.reset_opacity()
-    it += 1
-    step(it)
-    check("s6")
-    densify("dens2", 78, None)
-    check("d2")
+    import model_replay as R
+    R.replay(R.StoreDriver(R.load_gold(), GaussianModel, "cpu"))
 
 
 def test_kernel_source_visible_mask(on_host):

@@ -1,6 +1,6 @@
 """Pins oracle/model_oracle.py against the fixture produced by the reference's own scene/gaussian_model.py + torch.optim.Adam
-(tests/golden/make_golden_model.py): three Adam steps, densify_and_prune with the size threshold, two steps, opacity
-reset, one step, densify_and_prune without the size threshold."""
+(tests/golden/make_golden_model.py); the sequence is tests/model_replay.py's, including train.py's own order (backward, then
+densify / opacity reset, then an optimizer.step() that skips the replaced parameters)."""
 import os
 
 import numpy as np
@@ -46,26 +46,6 @@ def check(m: ModelOracle, gold, tag, tol=2e-6):
                                        msg=lambda s: f"{tag} {kind} {n}: {s}")
 
 
-def replay(gold, model, step_fn, densify_fn, reset_fn, check_fn):
-    it = 0
-    for _ in range(3):
-        it += 1
-        step_fn(model, it)
-    check_fn(model, "s3")
-    densify_fn(model, "dens", 77, 20)
-    check_fn(model, "d")
-    for _ in range(2):
-        it += 1
-        step_fn(model, it)
-    check_fn(model, "s5")
-    reset_fn(model)
-    it += 1
-    step_fn(model, it)
-    check_fn(model, "s6")
-    densify_fn(model, "dens2", 78, None)
-    check_fn(model, "d2")
-
-
 def test_expon_lr_matches_reference_schedule(gold):
     o = opt_of(gold)
     scale = float(gold["dens_extent"])
@@ -76,21 +56,36 @@ def test_expon_lr_matches_reference_schedule(gold):
 
 
 def test_oracle_replays_reference_training_state(gold):
+    import model_replay as R
     o = opt_of(gold)
+    m = make_oracle(gold)
 
-    def step(m, it):
-        m.step(it, act_grads(gold, m.activated()))
+    class Drv:
+        def backward(self, it):
+            m.backward(it, act_grads(gold, m.activated()))
 
-    def densify(m, key, seed, max_screen):
-        m.grad_accum = torch.from_numpy(gold[key + "_accum"]).clone()
-        m.denom = torch.from_numpy(gold[key + "_denom"]).clone()
-        if key == "dens":
-            m.max_radii2D = torch.from_numpy(gold["dens_max_radii2D"]).clone()
-        torch.manual_seed(seed)
-        info = m.densify_and_prune(o["densify_grad_threshold"], 0.005, float(gold["dens_extent"]), max_screen)
-        assert info["n_clone"] > 0 and info["n_split"] > 0, info
-        assert info["n_pruned"] > 0 or key == "dens2", info      # first pass exercises every branch; after the reset none is transparent
-        assert info["P"] == int(gold["d_P" if key == "dens" else "d2_P"])
-        assert float(m.max_radii2D.abs().max()) == 0.0 and float(m.grad_accum.abs().max()) == 0.0
+        def opt_step(self):
+            m.optimizer_step()
 
-    replay(gold, make_oracle(gold), step, densify, lambda m: m.reset_opacity(), lambda m, tag: check(m, gold, tag))
+        def reset(self):
+            m.reset_opacity()
+
+        def densify(self, key, seed, max_screen):
+            m.grad_accum = torch.from_numpy(gold[key + "_accum"]).clone()
+            m.denom = torch.from_numpy(gold[key + "_denom"]).clone()
+            if key == "dens":
+                m.max_radii2D = torch.from_numpy(gold["dens_max_radii2D"]).clone()
+            torch.manual_seed(seed)
+            info = m.densify_and_prune(o["densify_grad_threshold"], 0.005, float(gold["dens_extent"]), max_screen)
+            assert info["n_clone"] > 0 and info["n_split"] > 0, info
+            assert info["n_pruned"] > 0 or key != "dens", info   # first pass exercises every branch
+            assert info["P"] == int(gold[R.DENS_P[key]])
+            assert float(m.max_radii2D.abs().max()) == 0.0 and float(m.grad_accum.abs().max()) == 0.0
+
+        def check(self, tag):
+            check(m, gold, tag)
+
+        def check_steps(self, tag):
+            assert {n: int(v) for n, v in m.steps().items()} == {n: int(gold[f"{tag}_step_{n}"]) for n in GROUPS}
+
+    R.replay(Drv())

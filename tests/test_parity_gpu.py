@@ -19,7 +19,11 @@ def _weights(cam, seed=5):
     return torch.randn(3, H, W, generator=gen).numpy(), torch.randn(1, H, W, generator=gen).numpy()
 
 
-def _check(scene, cam, mode, with_depth_grad=True, grad_slack=0.0):
+def _flips(got, ref):
+    return U.count_flips(got["color"], ref["color"]) + U.count_flips(got["invdepth"], ref["invdepth"])
+
+
+def _check(scene, cam, mode, with_depth_grad=True, grad_tol=U.GRAD_REL_TOL):
     args = U.make_args(scene, mode)
     wc, wd = _weights(cam)
     if not with_depth_grad:
@@ -27,10 +31,9 @@ def _check(scene, cam, mode, with_depth_grad=True, grad_slack=0.0):
     got = U.run_cuda(args, cam, wc, wd)
     ref = U.run_oracle(args, cam, wc, wd)
     assert (got["radii"] == ref["radii"]).all(), "radii differ"
-    mx, frac = U.assert_image_close(got["color"], ref["color"], "color")
+    U.assert_image_close(got["color"], ref["color"], "color")
     U.assert_image_close(got["invdepth"], ref["invdepth"], "invdepth")
-    slack = grad_slack + (5e-3 if frac > 0 else 0.0)
-    U.assert_grads_close(got["grads"], ref["grads"], flips=slack)
+    U.assert_grads_close(got["grads"], ref["grads"], tol=grad_tol, flips=_flips(got, ref))
     return got, ref
 
 
@@ -72,7 +75,7 @@ def test_camera_inside_the_cloud():
     """Points behind / beside the camera: near cull, frustum clamp of the Jacobian."""
     scene = TO.make_scene(4000, seed=36, log_scale_mean=-3.0)
     cam = TO.make_camera(160, 120, sh_degree=3, eye=(0.1, 0.05, -0.4))
-    _check(scene, cam, "sh", grad_slack=1e-3)
+    _check(scene, cam, "sh", grad_tol=1.1e-3)   # near-plane points: the float32 oracle itself is 1e-3 from float64 here
 
 
 def test_low_opacity_never_visible():
@@ -184,8 +187,8 @@ def test_full_size_properties_config2():
     got = U.run_cuda(args, cam, wc, wd)
     ref = U.run_oracle(args, cam, wc, wd)
     assert (got["radii"] == ref["radii"]).all()
-    mx, frac = U.assert_image_close(got["color"], ref["color"], "color")
-    U.assert_grads_close(got["grads"], ref["grads"], flips=5e-3 if frac > 0 else 0.0)
+    U.assert_image_close(got["color"], ref["color"], "color")
+    U.assert_grads_close(got["grads"], ref["grads"], flips=_flips(got, ref))
 
 
 def test_speculative_capacity_repair_path():
@@ -305,7 +308,7 @@ def test_full_size_config3_against_oracle():
     # gaussians are exactly zero
     vis = ref["radii"] > 0
     assert np.all(got["grads"]["means3D"][~vis] == 0) and np.all(got["grads"]["shs"][~vis] == 0)
-    U.assert_grads_close(got["grads"], ref["grads"], flips=5e-3 if frac > 0 else 0.0)
+    U.assert_grads_close(got["grads"], ref["grads"], flips=_flips(got, ref))
 
 
 @pytest.mark.parametrize("nviews", [1, 5])
@@ -429,10 +432,10 @@ def test_fused_photometric_loss_and_fused_ssim(shape, golden):
     if shape == (3, 37, 53):
         assert abs(float(loss.item()) - float(golden["loss_total"])) < 2e-6
         assert np.abs(grad.cpu().numpy() - golden["loss_grad"]).max() < 1e-4 * np.abs(golden["loss_grad"]).max()
-    # drop-in fused_ssim: mean SSIM with autograd, images already in [0,1]
-    a = img.clamp(0, 1).to(dev).requires_grad_(True)
+    # drop-in fused_ssim: mean SSIM with autograd, NO clamp (the input keeps its values outside [0,1], as in the reference's kernel)
+    a = img.to(dev).requires_grad_(True)
     v = fused_ssim.fused_ssim(a.unsqueeze(0), gt.to(dev).unsqueeze(0))
-    a_ref = img.clamp(0, 1).requires_grad_(True)
+    a_ref = img.clone().requires_grad_(True)
     v_ref = TO.ssim(a_ref, gt)
     assert abs(float(v.item()) - float(v_ref)) < 2e-6
     (ga,) = torch.autograd.grad(v, a)

@@ -54,9 +54,12 @@ def test_lr_schedule_and_step_sizes_match_reference():
         assert abs(m.update_learning_rate(it) - float(gold[tag + "_lr_xyz"])) < 1e-15
     assert m.lr["f_rest"] == opt["feature_lr"] / 20.0 and m.lr["opacity"] == opt["opacity_lr"]
     # torch.optim.Adam: step_size = lr / (1 - beta1^t), denom = sqrt(v) / sqrt(1 - beta2^t) + eps
-    m.step_count = 4
+    # ... with one step count PER GROUP (a parameter replaced by reset_opacity / densify misses the step that follows)
+    m.group_steps = {n: 4 for n in m.group_steps}
+    m.group_steps["opacity"] = 2
     ss, b2s = m.step_sizes()
-    assert ss[3] == opt["opacity_lr"] / (1 - 0.9 ** 5) and b2s == math.sqrt(1 - 0.999 ** 5)
+    assert ss[3] == opt["opacity_lr"] / (1 - 0.9 ** 3) and b2s[3] == math.sqrt(1 - 0.999 ** 3)
+    assert ss[4] == opt["scaling_lr"] / (1 - 0.9 ** 5) and b2s[4] == math.sqrt(1 - 0.999 ** 5)
     assert expon_lr(-1, 1e-3, 1e-5) == 0.0 and expon_lr(10, 0.0, 0.0) == 0.0
     assert abs(expon_lr(0, 1e-3, 1e-5, max_steps=100) - 1e-3) < 1e-18 and abs(expon_lr(100, 1e-3, 1e-5, max_steps=100) - 1e-5) < 1e-18
 

@@ -54,63 +54,8 @@ def _frac_bad(a, b, rtol, atol):
 
 
 def test_store_replays_reference_fixture():
-    gold = {k: v for k, v in np.load(GOLD).items()}
-    opt = {k[4:]: float(v) for k, v in gold.items() if k.startswith("opt_")}
-    extent = float(gold["dens_extent"])
-    dev = torch.device("cuda:0")
-    t = lambda k: torch.from_numpy(gold["init" + RAW_KEY[k]]).to(dev)
-    m = _model_cls()(3).create_from_tensors(t("xyz"), t("f_dc"), t("f_rest"), t("scaling"), t("rotation"), t("opacity"), extent)
-    m.training_setup(_opt_namespace(opt))
-
-    def step(it):
-        assert abs(m.update_learning_rate(it) - (float(gold[f"s{it}_lr_xyz"]) if f"s{it}_lr_xyz" in gold else m.lr["xyz"])) < 1e-15
-        act = {"xyz": m.get_xyz, "features": m.get_features, "opacity": m.get_opacity, "scaling": m.get_scaling,
-               "rotation": m.get_rotation}
-        for n in ACT:
-            g = torch.from_numpy(gold["w_" + n][:m.P]).to(dev) + torch.from_numpy(gold["u_" + n][:m.P]).to(dev) * act[n].detach()
-            act[n].grad.copy_(g.view_as(act[n]))
-        m.optimizer_step()
-
-    def check(tag):
-        raw, mom = _raw_of(m), _moments_of(m)
-        for n in GROUPS:
-            ref = torch.from_numpy(gold[tag + RAW_KEY[n]])
-            assert tuple(raw[n].shape) == tuple(ref.shape), (tag, n, raw[n].shape, ref.shape)
-            torch.testing.assert_close(raw[n].cpu(), ref, rtol=PARAM_TOL, atol=PARAM_TOL, msg=lambda s: f"{tag} {n}: {s}")
-            for kind in ("m", "v"):
-                r = torch.from_numpy(gold[f"{tag}_{kind}_{n}"])
-                torch.testing.assert_close(mom[kind][n].cpu(), r, rtol=MOMENT_RTOL, atol=1e-9 if kind == "m" else 1e-13,
-                                           msg=lambda s: f"{tag} {kind} {n}: {s}")
-
-    def densify(key, seed, max_screen):
-        m.xyz_gradient_accum = torch.from_numpy(gold[key + "_accum"]).to(dev)
-        m.denom = torch.from_numpy(gold[key + "_denom"]).to(dev)
-
-        def draw(rows):                       # what the reference's torch.normal consumed from the CPU generator
-            torch.manual_seed(seed)
-            return torch.randn(rows, 3)
-
-        info = m.densify_and_prune(opt["densify_grad_threshold"], 0.005, extent, max_screen, unit_samples=draw)
-        assert info["P"] == int(gold["d_P" if key == "dens" else "d2_P"]), info
-        assert float(m.max_radii2D.abs().max()) == 0.0 and float(m.xyz_gradient_accum.abs().max()) == 0.0
-
-    it = 0
-    for _ in range(3):
-        it += 1
-        step(it)
-    check("s3")
-    densify("dens", 77, 20)
-    check("d")
-    for _ in range(2):
-        it += 1
-        step(it)
-    check("s5")
-    m.reset_opacity()
-    it += 1
-    step(it)
-    check("s6")
-    densify("dens2", 78, None)
-    check("d2")
+    import model_replay as R
+    R.replay(R.StoreDriver(R.load_gold(), _model_cls(), torch.device("cuda:0"), param_tol=PARAM_TOL, moment_rtol=MOMENT_RTOL))
 
 
 def _random_state(P, seed, dev):

@@ -26,7 +26,7 @@ from gaussian_renderer.synthetic import camera_matrices, make_scene, sphere_pose
 from gaussian_store import GaussianModel  # noqa: E402
 
 
-def main():
+def parse(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gaussians", type=int, default=6_000_000)
     ap.add_argument("--width", type=int, default=1600)
@@ -40,8 +40,12 @@ def main():
     ap.add_argument("--opacity-reset-interval", type=int, default=3000)
     ap.add_argument("--max-gaussians", type=int, default=12_000_000, help="densification is skipped above this count")
     ap.add_argument("--log-scale-mean", type=float, default=-5.6)
-    a = ap.parse_args()
-    dev = torch.device("cuda:0")
+    return ap.parse_args(argv)
+
+
+def run(a) -> dict:
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
     torch.manual_seed(0)
     sc = {k: v.to(dev) for k, v in make_scene(a.gaussians, seed=0, log_scale_mean=a.log_scale_mean).items()}
     pc = GaussianModel(3)
@@ -67,7 +71,9 @@ def main():
     pipe = SimpleNamespace(convert_SHs_python=False, compute_cov3D_python=False, debug=False, antialiasing=False)
     bg = torch.zeros(3, device=dev)
     V = a.views_per_iteration
-    events, P_trace, dens_ms = [], [pc.P], []
+    P_trace, dens_ms, D_max = [pc.P], [], 0
+    dgr.reset_launch_count()
+    torch.cuda.reset_peak_memory_stats()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e_start = torch.cuda.Event(enable_timing=True)
@@ -82,9 +88,11 @@ def main():
         out = render_views_backward(views, pc, pipe, bg,
                                     lambda img, _d, i: dgr.photometric_loss_and_grad(img, tgt[i], opt.lambda_dssim)[:2],
                                     loss_returns_grad=True, overwrite=True, densify_stats=stats if it < a.densify_until else None)
+        D_max = max(D_max, max(out["num_rendered"]))
         if it < a.densify_until:
             torch.maximum(pc.max_radii2D, out["radii_max"].to(pc.max_radii2D.dtype), out=pc.max_radii2D)      # train.py:166
             if it > a.densify_from and it % a.densify_interval == 0 and pc.P < a.max_gaussians:
+                torch.cuda.synchronize()
                 d0 = time.perf_counter()
                 size_threshold = 20 if it > a.opacity_reset_interval else None
                 info = pc.densify_and_prune(opt.densify_grad_threshold, 0.005, extent, size_threshold)          # train.py:168-170
@@ -93,18 +101,47 @@ def main():
                 P_trace.append(info["P"])
             if it % a.opacity_reset_interval == 0:
                 pc.reset_opacity()
-        pc.optimizer_step()
+        pc.optimizer_step()      # train.py:178-186; a no-op right after densify_and_prune, as in the reference (grad None)
     e_end = torch.cuda.Event(enable_timing=True)
     e_end.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     gpu_ms = e_start.elapsed_time(e_end)
-    print(json.dumps({"tool": "train_bench", "gaussians_start": a.gaussians, "gaussians_end": pc.P, "image": [W, H],
-                      "iterations": a.iterations, "views_per_iteration": V, "wall_s": round(wall, 3), "gpu_ms": round(gpu_ms, 1),
-                      "iterations_per_s": round(a.iterations / wall, 2), "mpix_per_s": round(a.iterations * V * H * W / wall / 1e6, 1),
-                      "densifications": len(dens_ms), "densify_ms_mean": round(sum(dens_ms) / len(dens_ms), 2) if dens_ms else None,
-                      "P_trace": P_trace[:12], "loss_last": float(out["losses"].mean()),
-                      "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}))
+    return {"tool": "train_bench", "gaussians_start": a.gaussians, "gaussians_end": pc.P, "image": [W, H],
+            "iterations": a.iterations, "views_per_iteration": V, "wall_s": round(wall, 3), "gpu_ms": round(gpu_ms, 1),
+            "iterations_per_s": round(a.iterations / (gpu_ms / 1e3), 2), "mpix_per_s": round(a.iterations * V * H * W / (gpu_ms / 1e3) / 1e6, 1),
+            "densifications": len(dens_ms), "densify_ms_mean": round(sum(dens_ms) / len(dens_ms), 2) if dens_ms else None,
+            "densify_ms_max": round(max(dens_ms), 2) if dens_ms else None,
+            "P_trace": P_trace[:12], "instances_per_view_max": int(D_max), "loss_last": float(out["losses"].mean()),
+            "optimizer_steps": pc.step_count, "gpu_launches": dgr.launch_count(),
+            "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}
+
+
+def bench_line(b) -> None:
+    """`python bench.py --workload train6m`: BASELINE.json configs[3] (6 M gaussians, 1600x1060, 1 k iterations with densify /
+    prune / opacity reset / fused Adam / L1 + D-SSIM), one line in bench.py's shape.  Not the headline metric (that is the
+    rasterizer's Mpix/s): metric here is training iterations per second, one view per iteration as in train.py."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    a = parse([])
+    if b.gaussians != 1_000_000:
+        a.gaussians = b.gaussians
+    if (b.width, b.height) != (1920, 1080):
+        a.width, a.height = b.width, b.height
+    a.iterations = b.iterations
+    r = run(a)
+    line = {"metric": "training iterations/s @6M gaussians 1600x1060 (BASELINE.json configs[3])", "value": r["iterations_per_s"],
+            "unit": "it/s", "n_gpus": 1, "steps": a.iterations, "warmup": 0, "ms_per_step": r["gpu_ms"] / a.iterations,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{a.gaussians} gaussians, {a.width}x{a.height}, SH 3, {a.iterations} iterations, densify every "
+                                   f"{a.densify_interval} after {a.densify_from}, L1 + D-SSIM, fused Adam on the flat store"},
+            "gpu_launches": r["gpu_launches"], "train": r}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    print(json.dumps(run(parse())))
 
 
 if __name__ == "__main__":
