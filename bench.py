@@ -614,7 +614,24 @@ def main():
         torch.cuda.synchronize()
         gc.enable()
         sv_ms = e0.elapsed_time(e1) / n_sv
+        # where the time goes (separate, untimed pass): this library's kernels per view; the rest of ms_per_view is torch's own
+        # kernels (zeros, clamp, |x - y|.mean() and its backward, nonzero) and launch gaps behind the two host synchronisations
+        # of the drop-in contract (the instance-count read-back and render()'s visibility_filter = (radii > 0).nonzero())
+        dgr.set_option("time_kernels", 2)
+        dgr.kernel_time("", reset=True)
+        for i in range(V):
+            one_view(i)
+        torch.cuda.synchronize()
+        sv_kernels = {}
+        for name in ("preprocess_fwd", "sort_hist", "sort_scatter", "scan_reduce", "scan_partials", "scan_apply", "emit", "tile_ranges",
+                     "tile_order", "render_fwd", "render_bwd", "preprocess_bwd"):
+            t, n = dgr.kernel_time(name)
+            sv_kernels[name] = round(t / V, 4)
+        sv_kernels["sum"] = round(sum(sv_kernels.values()), 4)
+        dgr.kernel_time("", reset=True)
+        dgr.set_option("time_kernels", 0)
         single_view = {"value": H * W / 1e6 / (sv_ms / 1e3), "unit": UNIT, "ms_per_view": sv_ms, "views_timed": n_sv,
+                       "library_kernel_ms_per_view": sv_kernels,
                        "api": "gaussian_renderer.render() -> GaussianRasterizer.forward + loss.backward(), one camera per iteration, "
                               "per rank (not aggregated over ranks)"}
 

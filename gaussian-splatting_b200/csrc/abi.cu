@@ -38,7 +38,6 @@ void timer_end(void *token, cudaStream_t stream) {
 }
 
 static int opt_cull = 1;
-static int opt_fused_ranges = 0;  // 1: tile ranges and the tile sort's histograms from counters filled by emit (A/B; binning.cu)
 static int opt_tile_order = 0;    // 1: blend CTAs take the tiles by descending list length (render.cu tile_order_kernel; A/B)
 
 void set_error(const char *fmt, ...) {
@@ -167,11 +166,9 @@ int32_t gsb_set_option(const char *name, int32_t value) {
     if (!name) return 1;
     if (!strcmp(name, "cull")) { opt_cull = value; return 0; }
     if (!strcmp(name, "time_kernels")) { g_time_kernels = value; return 0; }
-    if (!strcmp(name, "sort_variant")) { g_sort_variant = value; return 0; }
     if (!strcmp(name, "sort_small")) { g_sort_force_small = value; return 0; }
-    if (!strcmp(name, "fused_ranges")) { opt_fused_ranges = value; return 0; }
-    if (!strcmp(name, "sort_big_ipt")) { if (value != 8 && value != 16) return 1; g_sort_big_ipt = value; return 0; }
     if (!strcmp(name, "tile_order")) { opt_tile_order = value; return 0; }
+    if (!strcmp(name, "pre_tma")) { g_pre_tma = value; return 0; }
     return 1;
 }
 
@@ -255,7 +252,7 @@ int32_t gsb_forward(const GsbSettings *s, const GsbInputs *in, float *out_color,
     BinArgs ba;
     ba.P = P; ba.num_tiles = num_tiles; ba.gx = cam.gx; ba.order = idx; ba.tiles = tiles; ba.rect = rect; ba.splat = splat;
     ba.offsets = offsets; ba.partials = partials; ba.total = total;
-    ba.sv_gauss = 0; ba.sv_splat = 0; ba.sv_partials = 0; ba.sv_inst = 0; ba.tile_count = nullptr;
+    ba.sv_gauss = 0; ba.sv_splat = 0; ba.sv_partials = 0; ba.sv_inst = 0;
     st->splat = splat; st->final_T = iv.final_T; st->n_contrib = iv.n_contrib;
 
     // binning + blend for an instance capacity `cap`; the true count is read by the kernels from *n_dev when given
@@ -272,29 +269,17 @@ int32_t gsb_forward(const GsbSettings *s, const GsbInputs *in, float *out_color,
             const size_t Dn = (size_t)cap;
             Carver c1(nullptr);
             c1.take<uint32_t>(Dn); c1.take<uint32_t>(Dn); c1.take<uint32_t>(Dn); c1.take<char>(sort_scratch_bytes(cap));
-            c1.take<uint32_t>((size_t)num_tiles + 1);
             void *scr1 = do_alloc(alloc, alloc_ctx, GSB_BUF_SCRATCH1, c1.bytes());
             if (!scr1) return GSB_ERR_ALLOC;
             Carver c1r(scr1);
             uint32_t *inst_tile = c1r.take<uint32_t>(Dn), *inst_tile_alt = c1r.take<uint32_t>(Dn), *inst_gauss_alt = c1r.take<uint32_t>(Dn);
             char *sortscr1 = c1r.take<char>(sort_scratch_bytes(cap));
-            uint32_t *tile_count = c1r.take<uint32_t>((size_t)num_tiles + 1);
-            const bool fused = opt_fused_ranges && g_sort_variant == 1;
-            BinArgs be = ba;
-            be.tile_count = fused ? tile_count : nullptr;
-            if (fused) GSB_CUDA(cudaMemsetAsync(tile_count, 0, ((size_t)num_tiles + 1) * sizeof(uint32_t), stream));
-            r = launch_emit(be, 1, inst_tile, bv.point_list, cap, debug, stream);
+            r = launch_emit(ba, 1, inst_tile, bv.point_list, cap, debug, stream);
             if (r) return r;
-            if (fused) {
-                r = launch_ranges_from_counts(tile_count, 1, num_tiles, tile_bits, bv.ranges, sortscr1, debug, stream);
-                if (r) return r;
-            }
-            r = sort_pairs(inst_tile, bv.point_list, inst_tile_alt, inst_gauss_alt, cap, n_dev, 0, tile_bits, sortscr1, debug, stream, 1, 0, fused);
+            r = sort_pairs(inst_tile, bv.point_list, inst_tile_alt, inst_gauss_alt, cap, n_dev, 0, tile_bits, sortscr1, debug, stream, 1, 0);
             if (r) return r;
-            if (!fused) {
-                r = launch_tile_ranges(inst_tile, cap, n_dev, num_tiles, bv.ranges, 1, 0, debug, stream);
-                if (r) return r;
-            }
+            r = launch_tile_ranges(inst_tile, cap, n_dev, num_tiles, bv.ranges, 1, 0, debug, stream);
+            if (r) return r;
         } else {
             r = launch_tile_ranges(nullptr, 0, nullptr, num_tiles, bv.ranges, 1, 0, debug, stream);
             if (r) return r;
@@ -490,7 +475,7 @@ static int forward_batch_impl(int32_t V, const GsbSettings *s, const GsbInputs *
     BinArgs ba;
     ba.P = P; ba.num_tiles = num_tiles; ba.gx = c0.gx; ba.order = idx; ba.tiles = tiles; ba.rect = rect; ba.splat = splat;
     ba.offsets = offsets; ba.partials = partials; ba.total = total;
-    ba.sv_gauss = Pn; ba.sv_splat = sv_splat; ba.sv_partials = np; ba.sv_inst = 0; ba.tile_count = nullptr;
+    ba.sv_gauss = Pn; ba.sv_splat = sv_splat; ba.sv_partials = np; ba.sv_inst = 0;
     rc = launch_tile_scan(ba, V, debug, stream);
     if (rc) return rc;
     unsigned long long *h = nullptr;
@@ -526,31 +511,20 @@ static int forward_batch_impl(int32_t V, const GsbSettings *s, const GsbInputs *
         if (cap > 0) {
             Carver c1(nullptr);
             c1.take<uint32_t>(V * capn); c1.take<uint32_t>(V * capn); c1.take<uint32_t>(V * capn); c1.take<char>(sort_scratch_bytes(cap, V));
-            c1.take<uint32_t>((size_t)V * (num_tiles + 1));
             void *scr1 = do_alloc(alloc, alloc_ctx, GSB_BUF_SCRATCH1, c1.bytes());
             if (!scr1) return GSB_ERR_ALLOC;
             Carver c1r(scr1);
             uint32_t *inst_tile = c1r.take<uint32_t>(V * capn), *inst_tile_alt = c1r.take<uint32_t>(V * capn);
             uint32_t *inst_gauss_alt = c1r.take<uint32_t>(V * capn);
             char *sortscr1 = c1r.take<char>(sort_scratch_bytes(cap, V));
-            uint32_t *tile_count = c1r.take<uint32_t>((size_t)V * (num_tiles + 1));
-            const bool fused = opt_fused_ranges != 0;          // the view-batch sort is always the onesweep path
             BinArgs bb = ba;
             bb.sv_inst = capn;
-            bb.tile_count = fused ? tile_count : nullptr;
-            if (fused) GSB_CUDA(cudaMemsetAsync(tile_count, 0, (size_t)V * (num_tiles + 1) * sizeof(uint32_t), stream));
             r = launch_emit(bb, V, inst_tile, point_list, cap, debug, stream);
             if (r) return r;
-            if (fused) {
-                r = launch_ranges_from_counts(tile_count, V, num_tiles, tile_bits, ranges, sortscr1, debug, stream);
-                if (r) return r;
-            }
-            r = sort_pairs(inst_tile, point_list, inst_tile_alt, inst_gauss_alt, cap, total, 0, tile_bits, sortscr1, debug, stream, V, capn, fused);
+            r = sort_pairs(inst_tile, point_list, inst_tile_alt, inst_gauss_alt, cap, total, 0, tile_bits, sortscr1, debug, stream, V, capn);
             if (r) return r;
-            if (!fused) {
-                r = launch_tile_ranges(inst_tile, cap, total, num_tiles, ranges, V, capn, debug, stream);
-                if (r) return r;
-            }
+            r = launch_tile_ranges(inst_tile, cap, total, num_tiles, ranges, V, capn, debug, stream);
+            if (r) return r;
         } else {
             r = launch_tile_ranges(nullptr, 0, nullptr, num_tiles, ranges, V, 0, debug, stream);
             if (r) return r;

@@ -127,7 +127,6 @@ emit_kernel(BinArgs a, uint32_t *__restrict__ inst_tile, uint32_t *__restrict__ 
     a.order += blockIdx.y * a.sv_gauss; a.tiles += blockIdx.y * a.sv_gauss; a.rect += blockIdx.y * a.sv_gauss;
     a.offsets += blockIdx.y * a.sv_gauss; a.splat += blockIdx.y * a.sv_splat;
     inst_tile += blockIdx.y * a.sv_inst; inst_gauss += blockIdx.y * a.sv_inst;
-    uint32_t *const tile_count = a.tile_count ? a.tile_count + (size_t)blockIdx.y * (a.num_tiles + 1) : nullptr;
     const int r = blockIdx.x * 256 + threadIdx.x;
     if (r >= a.P) return;
     const uint32_t g = a.order[r];
@@ -149,7 +148,6 @@ emit_kernel(BinArgs a, uint32_t *__restrict__ inst_tile, uint32_t *__restrict__ 
             for (int tx = cg.rx0; tx < cg.rx1 && k < n; ++tx, ++k) {
                 inst_tile[start + k] = (uint32_t)(ty * a.gx + tx);
                 inst_gauss[start + k] = g;
-                if (tile_count) atomicAdd(tile_count + (ty * a.gx + tx), 1u);
             }
     } else {
         int ty0, ty1;
@@ -160,7 +158,6 @@ emit_kernel(BinArgs a, uint32_t *__restrict__ inst_tile, uint32_t *__restrict__ 
             for (int tx = tx0; tx < tx1 && k < n; ++tx, ++k) {
                 inst_tile[start + k] = (uint32_t)(ty * a.gx + tx);
                 inst_gauss[start + k] = g;
-                if (tile_count) atomicAdd(tile_count + (ty * a.gx + tx), 1u);
             }
         }
     }
@@ -168,58 +165,11 @@ emit_kernel(BinArgs a, uint32_t *__restrict__ inst_tile, uint32_t *__restrict__ 
     for (; k < n; ++k) {
         inst_tile[start + k] = (uint32_t)a.num_tiles;
         inst_gauss[start + k] = g;
-        if (tile_count) atomicAdd(tile_count + a.num_tiles, 1u);
     }
 }
 
 int launch_emit(const BinArgs &a, int V, uint32_t *inst_tile, uint32_t *inst_gauss, int64_t cap, bool debug, cudaStream_t stream) {
     GSB_LAUNCH("emit", debug, stream, emit_kernel, dim3((int)ceil_div(a.P, 256), V), 256, 0, a, inst_tile, inst_gauss, (uint32_t)cap);
-    return GSB_OK;
-}
-
-// Option fused_ranges.  One block per view: exclusive scan of the per-tile instance counters -> ranges[t] = [start, start + count)
-// (an empty tile gets an empty range at its position instead of (0, 0); the blend kernels only loop while start < end), and the
-// digit histograms of the tile sort's passes (a tile's count goes to the bin of each of its digits; the sentinel id num_tiles,
-// which emit never produces when its count and its enumeration agree, has a counter of its own and sorts behind every tile).
-__global__ void __launch_bounds__(SCAN_THREADS)
-ranges_from_counts_kernel(const uint32_t *__restrict__ tile_count, const int num_tiles, const int tile_bits, uint2 *__restrict__ ranges,
-                          uint32_t *__restrict__ ghist) {
-    __shared__ uint32_t hist[GSB_SORT_MAX_PASSES][GSB_SORT_RADIX];
-    __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
-    const int v = blockIdx.x;
-    tile_count += (size_t)v * (num_tiles + 1);
-    ranges += (size_t)v * num_tiles;
-    ghist += (size_t)v * (GSB_SORT_MAX_PASSES * GSB_SORT_RADIX);
-#pragma unroll
-    for (int p = 0; p < GSB_SORT_MAX_PASSES; ++p) hist[p][threadIdx.x] = 0u;
-    __syncthreads();
-    uint32_t carry = 0;
-    for (int base = 0; base <= num_tiles; base += SCAN_THREADS) {
-        const int t = base + threadIdx.x;
-        const uint32_t c = t <= num_tiles ? tile_count[t] : 0u;
-        uint32_t total;
-        const uint32_t start = carry + block_exclusive_scan_256(c, warp_sums, total);
-        if (t < num_tiles) ranges[t] = make_uint2(start, start + c);
-        if (c) {
-#pragma unroll
-            for (int p = 0; p < GSB_SORT_MAX_PASSES; ++p) {
-                const int bits = tile_bits - 8 * p;
-                if (bits > 0) atomicAdd(&hist[p][((uint32_t)t >> (8 * p)) & ((1u << (bits < 8 ? bits : 8)) - 1u)], c);
-            }
-        }
-        carry += total;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int p = 0; p < GSB_SORT_MAX_PASSES; ++p) ghist[p * GSB_SORT_RADIX + threadIdx.x] = hist[p][threadIdx.x];
-}
-
-int launch_ranges_from_counts(const uint32_t *tile_count, int V, int num_tiles, int tile_bits, uint2 *ranges, void *sort_scratch,
-                              bool debug, cudaStream_t stream) {
-    static_assert(SCAN_THREADS == GSB_SORT_RADIX, "one thread per histogram bin");
-    if (V > GSB_SORT_MAX_VIEWS || tile_bits > 8 * GSB_SORT_MAX_PASSES) { set_error("ranges_from_counts: bad geometry"); return GSB_ERR_ARGUMENT; }
-    GSB_LAUNCH("ranges_from_counts", debug, stream, ranges_from_counts_kernel, V, SCAN_THREADS, 0, tile_count, num_tiles, tile_bits, ranges,
-               static_cast<uint32_t *>(sort_scratch));
     return GSB_OK;
 }
 

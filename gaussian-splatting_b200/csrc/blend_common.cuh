@@ -26,11 +26,12 @@ __device__ __forceinline__ float rcp_approx(const float x) {
 }
 #endif
 
-// staged record: q0 = {x, y, A', B'}, q1 = {C', opacity, r, g} with A' = -0.5 log2e A, B' = -log2e B, C' = -0.5 log2e C
+// staged record: q0 = {x, y, A', C'}, q1 = {B', opacity, r, g} with A' = -0.5 log2e A, B' = -log2e B, C' = -0.5 log2e C.
+// (x, y) and (A', C') are 64-bit register pairs after the 128-bit shared-memory load, i.e. ready-made f32x2 operands:
+// (dx, dy) = (x, y) - pixel is ONE packed add and (A' dx dx, C' dy dy) two packed multiplies.
 __device__ __forceinline__ void stage_scale(float4 &q0, float4 &q1) {
-    q0.z = __fmul_rn(q0.z, -0.5f * LOG2E);
-    q0.w = __fmul_rn(q0.w, -LOG2E);
-    q1.x = __fmul_rn(q1.x, -0.5f * LOG2E);
+    const float a = __fmul_rn(q0.z, -0.5f * LOG2E), b = __fmul_rn(q0.w, -LOG2E), c = __fmul_rn(q1.x, -0.5f * LOG2E);
+    q0.z = a; q0.w = c; q1.x = b;
 }
 
 // log2-domain exponent at offset (dx, dy); pinned operation order: forward and backward must agree bit for bit

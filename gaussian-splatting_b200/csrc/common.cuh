@@ -53,6 +53,55 @@ __device__ __forceinline__ float div_apx(const float a, const float b) { float y
 __device__ __forceinline__ float rcp_apx(const float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #endif
 
+// ---- TMA bulk copies (cp.async.bulk: SASS UBLKCP / UBLKRED) and the mbarrier they complete on ------------------------------
+// 1-D bulk copies need no tensor map: 16-byte aligned source / destination, size a multiple of 16.  Used by the per-gaussian
+// kernels to move SH rows (192 B each) between global and shared memory without a single LDG / STG / index instruction.
+#ifdef GSB_HOST_EMUL     // tests/host_emul: synchronous copies; the barrier degenerates to nothing (each thread waits for its own row)
+inline void mbar_init(unsigned long long *, int) {}
+inline void mbar_expect_tx(unsigned long long *, uint32_t) {}
+inline void mbar_wait(unsigned long long *, uint32_t) {}
+inline void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *) { memcpy(smem_dst, gsrc, bytes); }
+inline void bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes) { memcpy(gdst, smem_src, bytes); }
+inline void bulk_s2g_add_f32(float *gdst, const float *smem_src, uint32_t bytes) { for (uint32_t k = 0; k < bytes / 4; ++k) gdst[k] += smem_src[k]; }
+inline void bulk_store_fence() {}
+inline void bulk_store_commit_and_wait() {}
+#else
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, const int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, const uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, const uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LAB_DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "LAB_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, const uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, const uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_add_f32(float *gdst, const float *smem_src, const uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (before a bulk store reads them)
+__device__ __forceinline__ void bulk_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// the issuing thread's bulk stores have finished READING shared memory (required before the CTA exits or reuses it)
+__device__ __forceinline__ void bulk_store_commit_and_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+#endif
+
 // ---- host-side plumbing -------------------------------------------------------------------
 void set_error(const char *fmt, ...);
 extern int64_t g_launch_count;
@@ -120,13 +169,9 @@ size_t sort_scratch_bytes(int64_t n, int V = 1);
 // n_dev is an array of V counts.
 int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n,
                const unsigned long long *n_dev, int begin_bit, int end_bit, void *scratch, bool debug,
-               cudaStream_t stream, int V = 1, size_t sv = 0, bool hist_ready = false);
-// The onesweep path keeps its digit histograms at the start of `scratch`: [GSB_SORT_MAX_VIEWS][GSB_SORT_MAX_PASSES][256] uint32,
-// pass p = bits [begin_bit + 8p, ...).  hist_ready = true: the caller has filled them (launch_ranges_from_counts) and the
-// sort's own histogram pass over the keys is skipped.
+               cudaStream_t stream, int V = 1, size_t sv = 0);
 constexpr int GSB_SORT_MAX_VIEWS = 16, GSB_SORT_MAX_PASSES = 4, GSB_SORT_RADIX = 256;
-extern int g_sort_variant;
 extern int g_sort_force_small;
-extern int g_sort_big_ipt;
+extern int g_pre_tma;
 
 }  // namespace gsb

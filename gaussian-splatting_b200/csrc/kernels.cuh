@@ -54,7 +54,6 @@ struct BinArgs {
     uint32_t *offsets;        // [P] exclusive scan of tiles in depth order
     uint32_t *partials;       // scan scratch
     unsigned long long *total;  // device scalar: D
-    uint32_t *tile_count;     // option fused_ranges: [V][num_tiles + 1] instance counters filled by emit (NULL = off)
 };
 
 // Blend launches cover V views (blockIdx.y): every per-view array is base + view * stride (strides in elements; 0 and V = 1
@@ -97,10 +96,6 @@ int launch_tile_scan(const BinArgs &a, int V, bool debug, cudaStream_t stream);
 // async forward: counts[GSB_MAX_VIEWS] = max(counts[GSB_MAX_VIEWS], counts[0..V))  (running maximum the host polls later)
 int launch_count_max(unsigned long long *counts, int V, bool debug, cudaStream_t stream);
 int launch_emit(const BinArgs &a, int V, uint32_t *inst_tile, uint32_t *inst_gauss, int64_t cap, bool debug, cudaStream_t stream);
-// option fused_ranges: tile ranges AND the tile sort's digit histograms from the per-tile counters emit filled
-// (replaces tile_ranges' pass over the D sorted keys and the sort's histogram pass over the D unsorted ones)
-int launch_ranges_from_counts(const uint32_t *tile_count, int V, int num_tiles, int tile_bits, uint2 *ranges, void *sort_scratch,
-                              bool debug, cudaStream_t stream);
 int launch_tile_ranges(const uint32_t *sorted_tiles, int64_t D, const unsigned long long *n_dev, int num_tiles,
                        uint2 *ranges, int V, size_t sv_inst, bool debug, cudaStream_t stream);
 

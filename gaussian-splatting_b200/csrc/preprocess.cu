@@ -18,15 +18,153 @@ constexpr int PRE_THREADS = 128;
 // access would touch 32 different 128-byte lines per warp instruction, so the block's rows are moved between
 // global and shared memory with fully coalesced accesses and each thread works on its own row in shared memory
 // (row stride padded to an odd word count: conflict-free).
-__device__ __forceinline__ int sh_row_stride(const int n) { return n | 1; }
+__host__ __device__ __forceinline__ int sh_row_stride(const int n) { return n | 1; }
 
-// global -> shared: first `ncols` floats of each of the block's rows (row length n); four loads in flight per thread
+// Second layout (VEC, option pre_tma): rows 16-byte aligned at a stride of an ODD number of 16-byte units.  A row is then one TMA
+// bulk copy (cp.async.bulk, 192 B at SH degree 3) in either direction -- no load / store / index instruction at all -- and its
+// owner reads and writes it as float4: the 8 rows of a quarter warp fall into 8 different 16-byte bank groups (conflict-free).
+__host__ __device__ __forceinline__ int sh_row_stride_vec(const int n) { return 4 * (((n + 3) >> 2) | 1); }
+template <bool VEC>
+__device__ __forceinline__ int sh_stride(const int n) { return VEC ? sh_row_stride_vec(n) : sh_row_stride(n); }
+
+// element e of a row <-> coefficient k = e / 3, channel c = e % 3; every index below is a compile-time constant after unrolling
+#define GSB_SH_QUADS(m, nfloats, q, ...)                                                       \
+    _Pragma("unroll") for (int m = 0; m < 12; ++m) {                                           \
+        if (4 * m < (nfloats)) {                                                               \
+            float4 _v = (q)[m];                                                                \
+            float vv[4] = {_v.x, _v.y, _v.z, _v.w};                                            \
+            __VA_ARGS__                                                                        \
+        }                                                                                      \
+    }
+
+// rgb += sum_{k < nb} bas[k] * row[3k + c]
+template <bool VEC>
+__device__ __forceinline__ void sh_eval(const float *row, const float (&bas)[16], const int nb, float &r, float &g, float &b) {
+    if (VEC) {
+        const float4 *q = reinterpret_cast<const float4 *>(row);
+        float acc[3] = {r, g, b};
+        GSB_SH_QUADS(m, 3 * nb, q,
+                     _Pragma("unroll") for (int i = 0; i < 4; ++i) {
+                         const int e = 4 * m + i, k = e / 3, c = e % 3;
+                         if (k < nb) acc[c] += bas[k] * vv[i];
+                     })
+        r = acc[0]; g = acc[1]; b = acc[2];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {   // compile-time bound: bas[] stays in registers
+            if (k < nb) { r += bas[k] * row[3 * k]; g += bas[k] * row[3 * k + 1]; b += bas[k] * row[3 * k + 2]; }
+        }
+    }
+}
+
+// dd{x,y,z} += sum_{1 <= k < nb} b{x,y,z}[k] * (row[3k] d0 + row[3k+1] d1 + row[3k+2] d2)
+template <bool VEC>
+__device__ __forceinline__ void sh_dir_grad(const float *row, const float (&d)[3], const float (&bx)[16], const float (&by)[16],
+                                            const float (&bz)[16], const int nb, float &ddx, float &ddy, float &ddz) {
+    if (VEC) {
+        const float4 *q = reinterpret_cast<const float4 *>(row);
+        float sk[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) sk[k] = 0.f;
+        GSB_SH_QUADS(m, 3 * nb, q,
+                     _Pragma("unroll") for (int i = 0; i < 4; ++i) {
+                         const int e = 4 * m + i, k = e / 3, c = e % 3;
+                         if (k >= 1 && k < nb) sk[k] = c == 0 ? vv[i] * d[0] : sk[k] + vv[i] * d[c];
+                     })
+#pragma unroll
+        for (int k = 1; k < 16; ++k)
+            if (k < nb) { ddx += bx[k] * sk[k]; ddy += by[k] * sk[k]; ddz += bz[k] * sk[k]; }
+    } else {
+#pragma unroll
+        for (int k = 1; k < 16; ++k) {   // compile-time bound: bx/by/bz stay in registers
+            if (k < nb) {
+                const float s = row[3 * k] * d[0] + row[3 * k + 1] * d[1] + row[3 * k + 2] * d[2];
+                ddx += bx[k] * s; ddy += by[k] * s; ddz += bz[k] * s;
+            }
+        }
+    }
+}
+
+// gradient row: row[3k + c] (+)= bas[k] d[c] for k < nb; with ADD = false the rest of the row (k >= nb, up to M) is zeroed
+template <bool VEC, bool ADD>
+__device__ __forceinline__ void sh_grad_row(float *row, const float (&bas)[16], const float (&d)[3], const int nb, const int M) {
+    if (VEC) {
+        float4 *q = reinterpret_cast<float4 *>(row);
+        GSB_SH_QUADS(m, ADD ? 3 * nb : 3 * M, q,
+                     _Pragma("unroll") for (int i = 0; i < 4; ++i) {
+                         const int e = 4 * m + i, k = e / 3, c = e % 3;
+                         const float t = k < nb ? bas[k] * d[c] : 0.f;
+                         vv[i] = ADD ? vv[i] + t : t;
+                     }
+                     q[m] = make_float4(vv[0], vv[1], vv[2], vv[3]);)
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (ADD) {
+                if (k < nb) { row[3 * k] += bas[k] * d[0]; row[3 * k + 1] += bas[k] * d[1]; row[3 * k + 2] += bas[k] * d[2]; }
+            } else if (k < M) {
+                const float bk = k < nb ? bas[k] : 0.f;
+                row[3 * k] = bk * d[0]; row[3 * k + 1] = bk * d[1]; row[3 * k + 2] = bk * d[2];
+            }
+        }
+        if (!ADD)
+            for (int k = 16; k < M; ++k) { row[3 * k] = 0.f; row[3 * k + 1] = 0.f; row[3 * k + 2] = 0.f; }
+    }
+}
+
+// TMA staging of the block's SH rows: one bulk copy per row, issued by the row's owner, completing on one mbarrier
+__device__ __forceinline__ void tma_rows_in(const float *__restrict__ g, float *s, unsigned long long *bar, const int row0,
+                                            const int nrows, const int n) {
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) mbar_expect_tx(bar, (uint32_t)(nrows * n) * 4u);
+    if ((int)threadIdx.x < nrows)
+        bulk_g2s(s + threadIdx.x * sh_row_stride_vec(n), g + (size_t)(row0 + threadIdx.x) * n, (uint32_t)n * 4u, bar);
+    mbar_wait(bar, 0u);
+}
+
+// the owner's (gradient) row back to global memory: bulk store, or bulk reduce-add (ACC)
+template <bool ACC>
+__device__ __forceinline__ void tma_row_out(float *__restrict__ g, const float *row, const int i, const int n, const bool live) {
+    bulk_store_fence();
+    if (live) {
+        if (ACC) bulk_s2g_add_f32(g + (size_t)i * n, row, (uint32_t)n * 4u);
+        else bulk_s2g(g + (size_t)i * n, row, (uint32_t)n * 4u);
+    }
+    bulk_store_commit_and_wait();
+}
+
+// global -> shared: first `ncols` floats of each of the block's rows (row length n).  When both n and ncols
+// are multiples of four (SH degree 1 and 3 rows: 12 and 48 floats) the block's rows are fetched as 128-bit loads (a quarter of the load instructions and of the index
+// arithmetic; the row stride in shared memory stays odd, so the four words are stored one by one); otherwise word by word.
 __device__ __forceinline__ void stage_rows_in(const float *__restrict__ g, float *s, const int row0, const int nrows,
                                               const int n, const int ncols) {
     const int stride = sh_row_stride(n);
+    const float *gb = g + (size_t)row0 * n;
+    if (((n | ncols) & 3) == 0 && ((reinterpret_cast<size_t>(gb) & 15) == 0)) {
+        const int q = ncols >> 2, total = nrows * q;        // float4 per row, float4 in the block
+        const float inv = 1.0f / (float)q;
+        for (int base = 0; base < total; base += 4 * PRE_THREADS) {
+            float4 v[4];
+            int si[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * PRE_THREADS + threadIdx.x;
+                si[u] = -1;
+                if (idx < total) {
+                    const int r = (int)(((float)idx + 0.5f) * inv), c = idx - r * q;
+                    si[u] = r * stride + 4 * c;
+                    v[u] = __ldg(reinterpret_cast<const float4 *>(gb + (size_t)r * n) + c);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (si[u] >= 0) { s[si[u]] = v[u].x; s[si[u] + 1] = v[u].y; s[si[u] + 2] = v[u].z; s[si[u] + 3] = v[u].w; }
+        }
+        return;
+    }
     const int total = nrows * ncols;
     const float inv = 1.0f / (float)ncols;
-    const float *gb = g + (size_t)row0 * n;
     for (int base = 0; base < total; base += 4 * PRE_THREADS) {
         float v[4];
         int si[4];
@@ -46,14 +184,40 @@ __device__ __forceinline__ void stage_rows_in(const float *__restrict__ g, float
     }
 }
 
-// shared -> global: full rows (contiguous in global memory); ACC adds into the destination
+// shared -> global: full rows (contiguous in global memory); ACC adds into the destination.  128-bit stores (and loads, for
+// ACC) when the row length is a multiple of four floats.
 template <bool ACC>
 __device__ __forceinline__ void stage_rows_out(float *__restrict__ g, const float *s, const int row0, const int nrows,
                                                const int n) {
     const int stride = sh_row_stride(n);
+    float *gb = g + (size_t)row0 * n;
+    if ((n & 3) == 0 && ((reinterpret_cast<size_t>(gb) & 15) == 0)) {
+        const int q = n >> 2, total = nrows * q;
+        const float inv = 1.0f / (float)q;
+        float4 *gb4 = reinterpret_cast<float4 *>(gb);
+        for (int base = 0; base < total; base += 4 * PRE_THREADS) {
+            float4 v[4];
+            int gi[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * PRE_THREADS + threadIdx.x;
+                gi[u] = -1;
+                if (idx < total) {
+                    const int r = (int)(((float)idx + 0.5f) * inv), c = idx - r * q;
+                    const float *sp = s + r * stride + 4 * c;
+                    gi[u] = idx;
+                    v[u] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                    if (ACC) { const float4 o = gb4[idx]; v[u].x += o.x; v[u].y += o.y; v[u].z += o.z; v[u].w += o.w; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (gi[u] >= 0) gb4[gi[u]] = v[u];
+        }
+        return;
+    }
     const int total = nrows * n;
     const float inv = 1.0f / (float)n;
-    float *gb = g + (size_t)row0 * n;
     for (int base = 0; base < total; base += 4 * PRE_THREADS) {
         float v[4];
         int gi[4];
@@ -75,6 +239,7 @@ __device__ __forceinline__ void stage_rows_out(float *__restrict__ g, const floa
 }
 
 // one gaussian, one view: everything of K1 after the SH row has been staged
+template <bool VEC>
 __device__ __forceinline__ void preprocess_fwd_body(const CamParams &cam, const PreFwdArgs &a, const int i, const float *sh_row) {
     // defaults for a culled gaussian
     uint32_t key = 0xffffffffu, ntiles = 0;
@@ -131,11 +296,7 @@ __device__ __forceinline__ void preprocess_fwd_body(const CamParams &cam, const 
                     float bas[16];
                     sh_basis(cam.sh_degree, dx * inv, dy * inv, dz * inv, bas);
                     const int nb = (cam.sh_degree + 1) * (cam.sh_degree + 1);
-                    const float *sh = sh_row;
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {   // compile-time bound: bas[] stays in registers
-                        if (k < nb) { r += bas[k] * sh[3 * k]; g += bas[k] * sh[3 * k + 1]; b += bas[k] * sh[3 * k + 2]; }
-                    }
+                    sh_eval<VEC>(sh_row, bas, nb, r, g, b);
                     r += 0.5f; g += 0.5f; b += 0.5f;
                     if (r < 0.f) { bits |= 1u; r = 0.f; }
                     if (g < 0.f) { bits |= 2u; g = 0.f; }
@@ -173,32 +334,44 @@ __device__ __forceinline__ void preprocess_fwd_body(const CamParams &cam, const 
     a.radii[i] = radius_out;
 }
 
+template <bool TMA>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_fwd_kernel(const CamArgs ca, const PreFwdArgs a) {
     __shared__ CamParams cam;
-    GSB_DYNAMIC_SMEM(float, sh_rows);
+    __shared__ unsigned long long bar;
+    GSB_DYNAMIC_SMEM(float4, sh_rows4);
+    float *sh_rows = reinterpret_cast<float *>(sh_rows4);
     load_cam(ca, cam);
     const int row0 = blockIdx.x * PRE_THREADS;
     const int nrows = min(PRE_THREADS, a.P - row0);
     const int shn = 3 * ca.sh_coeffs;
-    if (a.shs) stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * (ca.sh_degree + 1) * (ca.sh_degree + 1));
+    if (a.shs) {
+        if (TMA) tma_rows_in(a.shs, sh_rows, &bar, row0, nrows, shn);
+        else stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * (ca.sh_degree + 1) * (ca.sh_degree + 1));
+    }
     __syncthreads();
     const int i = row0 + threadIdx.x;
     if (i >= a.P) return;
-    preprocess_fwd_body(cam, a, i, sh_rows + threadIdx.x * sh_row_stride(shn));
+    preprocess_fwd_body<TMA>(cam, a, i, sh_rows + threadIdx.x * sh_stride<TMA>(shn));
 }
 
 // View-batch K1: the gaussians' parameters (236 B each at SH degree 3, 192 B of it the SH row) are read ONCE and
 // projected through every camera of the batch; per-view outputs are [V][...] arrays with uniform strides.
+template <bool TMA>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_fwd_batch_kernel(const CamArgsBatch cb, const PreFwdArgs a, const PreFwdBatchStrides st) {
     __shared__ CamParams cams[GSB_MAX_VIEWS];
-    GSB_DYNAMIC_SMEM(float, sh_rows);
+    __shared__ unsigned long long bar;
+    GSB_DYNAMIC_SMEM(float4, sh_rows4);
+    float *sh_rows = reinterpret_cast<float *>(sh_rows4);
     for (int v = 0; v < cb.V; ++v) load_cam(cb.cam[v], cams[v]);
     const int row0 = blockIdx.x * PRE_THREADS;
     const int nrows = min(PRE_THREADS, a.P - row0);
     const int shn = 3 * cb.cam[0].sh_coeffs;
-    if (a.shs) stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * (cb.cam[0].sh_degree + 1) * (cb.cam[0].sh_degree + 1));
+    if (a.shs) {
+        if (TMA) tma_rows_in(a.shs, sh_rows, &bar, row0, nrows, shn);
+        else stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * (cb.cam[0].sh_degree + 1) * (cb.cam[0].sh_degree + 1));
+    }
     __syncthreads();
     const int i = row0 + threadIdx.x;
     if (i >= a.P) return;
@@ -206,7 +379,7 @@ preprocess_fwd_batch_kernel(const CamArgsBatch cb, const PreFwdArgs a, const Pre
         PreFwdArgs av = a;
         av.splat += (size_t)v * st.splat; av.depth_key += (size_t)v * st.per_gauss; av.depth_idx += (size_t)v * st.per_gauss;
         av.tiles += (size_t)v * st.per_gauss; av.rect += (size_t)v * st.per_gauss; av.radii += (size_t)v * st.radii;
-        preprocess_fwd_body(cams[v], av, i, sh_rows + threadIdx.x * sh_row_stride(shn));
+        preprocess_fwd_body<TMA>(cams[v], av, i, sh_rows + threadIdx.x * sh_stride<TMA>(shn));
     }
 }
 
@@ -248,6 +421,7 @@ struct ViewGrad {
 // K8 for one gaussian and one view: chain rule from the blend kernel's accumulators (mean2D / conic or raw moments, opacity,
 // rgb, inverse depth) to the rasterizer inputs.  Every field of `o` is written.
 // Returns false when the gaussian received no gradient in this view (all fields of `o` are zero then).
+template <bool VEC>
 __device__ __forceinline__ bool preprocess_bwd_view(const CamParams &cam, const PreBwdArgs &a, const int i, const float *sh_row,
                                                     const uint32_t bits, ViewGrad &o) {
     float (&gm)[3] = o.gm; float (&g_m2)[2] = o.g_m2; float &g_op = o.g_op; float (&g_rgb)[3] = o.g_rgb;
@@ -297,15 +471,8 @@ __device__ __forceinline__ bool preprocess_bwd_view(const CamParams &cam, const 
             d_rgb_sh[0] = (bits & 1u) ? 0.f : d_rgb[0];
             d_rgb_sh[1] = (bits & 2u) ? 0.f : d_rgb[1];
             d_rgb_sh[2] = (bits & 4u) ? 0.f : d_rgb[2];
-            const float *sh = sh_row;
             float ddx = 0.f, ddy = 0.f, ddz = 0.f;
-#pragma unroll
-            for (int k = 1; k < 16; ++k) {   // compile-time bound: bx/by/bz stay in registers
-                if (k < nb) {
-                    const float s = sh[3 * k] * d_rgb_sh[0] + sh[3 * k + 1] * d_rgb_sh[1] + sh[3 * k + 2] * d_rgb_sh[2];
-                    ddx += bx[k] * s; ddy += by[k] * s; ddz += bz[k] * s;
-                }
-            }
+            sh_dir_grad<VEC>(sh_row, d_rgb_sh, bx, by, bz, nb, ddx, ddy, ddz);
             const float dot = ux * ddx + uy * ddy + uz * ddz;
             gm[0] += (ddx - ux * dot) * inv; gm[1] += (ddy - uy * dot) * inv; gm[2] += (ddz - uz * dot) * inv;
         } else {
@@ -452,39 +619,39 @@ __device__ __forceinline__ void write_gauss_grads(const PreBwdArgs &a, const int
 }
 
 // K8, one view.
-template <bool ACC>
+template <bool ACC, bool TMA>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_bwd_kernel(const CamArgs ca, const PreBwdArgs a) {
     __shared__ CamParams cam;
-    GSB_DYNAMIC_SMEM(float, sh_rows);
+    __shared__ unsigned long long bar;
+    GSB_DYNAMIC_SMEM(float4, sh_rows4);
+    float *sh_rows = reinterpret_cast<float *>(sh_rows4);
     load_cam(ca, cam);
     const int row0 = a.p_begin + blockIdx.x * PRE_THREADS;      // gaussians [p_begin, p_end) of this launch
     const int nrows = min(PRE_THREADS, a.p_end - row0);
     const int shn = 3 * ca.sh_coeffs;
     const int nb = (ca.sh_degree + 1) * (ca.sh_degree + 1);
-    if (a.shs) stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * nb);
+    if (a.shs) {
+        if (TMA) tma_rows_in(a.shs, sh_rows, &bar, row0, nrows, shn);
+        else stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * nb);
+    }
     __syncthreads();
     const int i = row0 + threadIdx.x;
     const bool live = i < a.p_end;
     const int M = cam.sh_coeffs;
-    float *sh_row = sh_rows + threadIdx.x * sh_row_stride(shn);
+    float *sh_row = sh_rows + threadIdx.x * sh_stride<TMA>(shn);
     ViewGrad g;
-    if (live) preprocess_bwd_view(cam, a, i, sh_row, __float_as_uint(a.splat[(size_t)i * SPLAT_F4 + 2].w), g);
+    if (live) preprocess_bwd_view<TMA>(cam, a, i, sh_row, __float_as_uint(a.splat[(size_t)i * SPLAT_F4 + 2].w), g);
 
-    // SH gradient rows go out through shared memory (coalesced); each thread rewrites only its own row
+    // SH gradient rows go out through shared memory (coalesced / one bulk store); each thread rewrites only its own row
     if (a.g.dL_dshs && a.shs) {
-        if (live) {
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                if (k < M) {
-                    const float bk = k < nb ? g.bas[k] : 0.f;
-                    sh_row[3 * k] = bk * g.d_rgb_sh[0]; sh_row[3 * k + 1] = bk * g.d_rgb_sh[1]; sh_row[3 * k + 2] = bk * g.d_rgb_sh[2];
-                }
-            }
-            for (int k = 16; k < M; ++k) { sh_row[3 * k] = 0.f; sh_row[3 * k + 1] = 0.f; sh_row[3 * k + 2] = 0.f; }
+        if (live) sh_grad_row<TMA, false>(sh_row, g.bas, g.d_rgb_sh, nb, M);
+        if (TMA) {
+            tma_row_out<ACC>(a.g.dL_dshs, sh_row, i, shn, live);
+        } else {
+            __syncthreads();
+            stage_rows_out<ACC>(a.g.dL_dshs, sh_rows, row0, nrows, shn);
         }
-        __syncthreads();
-        stage_rows_out<ACC>(a.g.dL_dshs, sh_rows, row0, nrows, shn);
     }
     if (!live) return;
     if (a.g.dL_dmeans2D) {
@@ -497,30 +664,41 @@ preprocess_bwd_kernel(const CamArgs ca, const PreBwdArgs a) {
 // View-batch K8: parameters read once, the V views' accumulators chained one after the other, the per-gaussian
 // gradient summed over views in registers (SH: in a second shared-memory row) and written ONCE.
 // Per-view arrays (dacc, splat, means2D gradient) are [V][...] with uniform strides.
-template <bool ACC>
+template <bool ACC, bool TMA>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_bwd_batch_kernel(const CamArgsBatch cb, const PreBwdArgs a, const PreBwdBatchStrides st) {
     __shared__ CamParams cams[GSB_MAX_VIEWS];
-    GSB_DYNAMIC_SMEM(float, sh_rows);
+    __shared__ unsigned long long bar;
+    GSB_DYNAMIC_SMEM(float4, sh_rows4);
+    float *sh_rows = reinterpret_cast<float *>(sh_rows4);
     for (int v = 0; v < cb.V; ++v) load_cam(cb.cam[v], cams[v]);
     const int row0 = a.p_begin + blockIdx.x * PRE_THREADS;      // gaussians [p_begin, p_end) of this launch
     const int nrows = min(PRE_THREADS, a.p_end - row0);
     const int shn = 3 * cb.cam[0].sh_coeffs;
     const int nb = (cb.cam[0].sh_degree + 1) * (cb.cam[0].sh_degree + 1);
-    float *grad_rows = sh_rows + PRE_THREADS * sh_row_stride(shn);
-    if (a.shs) stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * nb);
+    float *grad_rows = sh_rows + PRE_THREADS * sh_stride<TMA>(shn);
+    if (a.shs) {
+        if (TMA) tma_rows_in(a.shs, sh_rows, &bar, row0, nrows, shn);
+        else stage_rows_in(a.shs, sh_rows, row0, nrows, shn, 3 * nb);
+    }
     __syncthreads();
     const int i = row0 + threadIdx.x;
     const bool live = i < a.p_end;
     const int M = cb.cam[0].sh_coeffs;
-    const float *sh_row = sh_rows + threadIdx.x * sh_row_stride(shn);
-    float *gr = grad_rows + threadIdx.x * sh_row_stride(shn);
+    const float *sh_row = sh_rows + threadIdx.x * sh_stride<TMA>(shn);
+    float *gr = grad_rows + threadIdx.x * sh_stride<TMA>(shn);
     float gm[3] = {0.f, 0.f, 0.f}, g_op = 0.f, g_rgb[3] = {0.f, 0.f, 0.f}, g_sc[3] = {0.f, 0.f, 0.f};
     float g_rot[4] = {0.f, 0.f, 0.f, 0.f}, dS[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const bool want_sh = a.g.dL_dshs && a.shs;
     if (live) {
-        if (want_sh)
-            for (int k = 0; k < 3 * M; ++k) gr[k] = 0.f;
+        if (want_sh) {
+            if (TMA) {
+                float4 *gq = reinterpret_cast<float4 *>(gr);
+                for (int k = 0; 4 * k < 3 * M; ++k) gq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (int k = 0; k < 3 * M; ++k) gr[k] = 0.f;
+            }
+        }
 #ifdef GSB_PRE_UNROLL
         constexpr int kViewUnroll = GSB_PRE_UNROLL;
 #else
@@ -539,7 +717,7 @@ preprocess_bwd_batch_kernel(const CamArgsBatch cb, const PreBwdArgs a, const Pre
                 continue;
             }
             ViewGrad g;
-            if (!preprocess_bwd_view(cams[v], av, i, sh_row, bits, g)) {
+            if (!preprocess_bwd_view<TMA>(cams[v], av, i, sh_row, bits, g)) {
                 if (a.g.dL_dmeans2D) {
                     float *m2 = a.g.dL_dmeans2D + (size_t)v * st.means2D + 3 * (size_t)i;
                     m2[0] = 0.f; m2[1] = 0.f; m2[2] = 0.f;
@@ -553,15 +731,7 @@ preprocess_bwd_batch_kernel(const CamArgsBatch cb, const PreBwdArgs a, const Pre
 #pragma unroll
             for (int c = 0; c < 6; ++c) dS[c] += g.dS[c];
             g_op += g.g_op;
-            if (want_sh) {
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    if (k < nb) {
-                        gr[3 * k] += g.bas[k] * g.d_rgb_sh[0]; gr[3 * k + 1] += g.bas[k] * g.d_rgb_sh[1];
-                        gr[3 * k + 2] += g.bas[k] * g.d_rgb_sh[2];
-                    }
-                }
-            }
+            if (want_sh) sh_grad_row<TMA, true>(gr, g.bas, g.d_rgb_sh, nb, M);
             if (a.g.dL_dmeans2D) {
                 float *m2 = a.g.dL_dmeans2D + (size_t)v * st.means2D + 3 * (size_t)i;
                 m2[0] = g.g_m2[0]; m2[1] = g.g_m2[1]; m2[2] = 0.f;
@@ -569,8 +739,12 @@ preprocess_bwd_batch_kernel(const CamArgsBatch cb, const PreBwdArgs a, const Pre
         }
     }
     if (want_sh) {
-        __syncthreads();
-        stage_rows_out<ACC>(a.g.dL_dshs, grad_rows, row0, nrows, shn);
+        if (TMA) {
+            tma_row_out<ACC>(a.g.dL_dshs, gr, i, shn, live);
+        } else {
+            __syncthreads();
+            stage_rows_out<ACC>(a.g.dL_dshs, grad_rows, row0, nrows, shn);
+        }
     }
     if (!live) return;
     write_gauss_grads<ACC>(a, i, gm, g_op, g_rgb, g_sc, g_rot, dS);
@@ -584,47 +758,74 @@ mark_visible_kernel(const int P, const float *__restrict__ means, const float *_
     present[i] = tz > NEAR_CULL ? 1 : 0;
 }
 
+// Option pre_tma: SH rows move between global and shared memory as TMA bulk copies (one per row) and are accessed as float4.
+// Needs 16-byte rows (n = 3 M a multiple of 4: SH degree 1 and 3 tensors) and 16-byte aligned tensors.
+int g_pre_tma = 0;
+static bool use_tma_rows(const float *shs, const float *dshs, int sh_coeffs) {
+    return g_pre_tma && shs && ((3 * sh_coeffs) & 3) == 0 && (reinterpret_cast<size_t>(shs) & 15) == 0 &&
+           (reinterpret_cast<size_t>(dshs) & 15) == 0;
+}
+static size_t sh_smem_bytes(bool tma, int sh_coeffs, int rows_per_thread) {
+    const int n = 3 * sh_coeffs;
+    return (size_t)rows_per_thread * PRE_THREADS * (tma ? sh_row_stride_vec(n) : sh_row_stride(n)) * sizeof(float);
+}
+#define GSB_PRE_LAUNCH(kernel, grid, smem, ...)                                                                             \
+    do {                                                                                                                    \
+        if ((smem) > 40 * 1024) GSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
+        GSB_LAUNCH(name, debug, stream, kernel, grid, PRE_THREADS, smem, __VA_ARGS__);                                      \
+    } while (0)
+
 int launch_preprocess_fwd(const CamArgs &ca, const PreFwdArgs &a, bool debug, cudaStream_t stream) {
     if (a.P <= 0) return GSB_OK;
-    const size_t smem = a.shs ? (size_t)PRE_THREADS * ((3 * ca.sh_coeffs) | 1) * sizeof(float) : 0;
-    if (smem > 48 * 1024) GSB_CUDA(cudaFuncSetAttribute(preprocess_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GSB_LAUNCH("preprocess_fwd", debug, stream, preprocess_fwd_kernel, (int)ceil_div(a.P, PRE_THREADS), PRE_THREADS, smem, ca, a);
+    const char *name = "preprocess_fwd";
+    const bool tma = use_tma_rows(a.shs, nullptr, ca.sh_coeffs);
+    const size_t smem = a.shs ? sh_smem_bytes(tma, ca.sh_coeffs, 1) : 0;
+    const int grid = (int)ceil_div(a.P, PRE_THREADS);
+    if (tma) GSB_PRE_LAUNCH(preprocess_fwd_kernel<true>, grid, smem, ca, a);
+    else GSB_PRE_LAUNCH(preprocess_fwd_kernel<false>, grid, smem, ca, a);
     return GSB_OK;
 }
 
 int launch_preprocess_bwd(const CamArgs &ca, const PreBwdArgs &a, bool accumulate, bool debug, cudaStream_t stream) {
     if (a.P <= 0 || a.p_end <= a.p_begin) return GSB_OK;
+    const char *name = "preprocess_bwd";
     const int grid = (int)ceil_div(a.p_end - a.p_begin, PRE_THREADS);
-    const size_t smem = a.shs ? (size_t)PRE_THREADS * ((3 * ca.sh_coeffs) | 1) * sizeof(float) : 0;
+    const bool tma = use_tma_rows(a.shs, a.g.dL_dshs, ca.sh_coeffs);
+    const size_t smem = a.shs ? sh_smem_bytes(tma, ca.sh_coeffs, 1) : 0;
     if (accumulate) {
-        if (smem > 48 * 1024) GSB_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GSB_LAUNCH("preprocess_bwd", debug, stream, preprocess_bwd_kernel<true>, grid, PRE_THREADS, smem, ca, a);
+        if (tma) GSB_PRE_LAUNCH((preprocess_bwd_kernel<true, true>), grid, smem, ca, a);
+        else GSB_PRE_LAUNCH((preprocess_bwd_kernel<true, false>), grid, smem, ca, a);
     } else {
-        if (smem > 48 * 1024) GSB_CUDA(cudaFuncSetAttribute(preprocess_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GSB_LAUNCH("preprocess_bwd", debug, stream, preprocess_bwd_kernel<false>, grid, PRE_THREADS, smem, ca, a);
+        if (tma) GSB_PRE_LAUNCH((preprocess_bwd_kernel<false, true>), grid, smem, ca, a);
+        else GSB_PRE_LAUNCH((preprocess_bwd_kernel<false, false>), grid, smem, ca, a);
     }
     return GSB_OK;
 }
 
 int launch_preprocess_fwd_batch(const CamArgsBatch &cb, const PreFwdArgs &a, const PreFwdBatchStrides &st, bool debug, cudaStream_t stream) {
     if (a.P <= 0) return GSB_OK;
-    const size_t smem = a.shs ? (size_t)PRE_THREADS * ((3 * cb.cam[0].sh_coeffs) | 1) * sizeof(float) : 0;
-    if (smem > 40 * 1024) GSB_CUDA(cudaFuncSetAttribute(preprocess_fwd_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GSB_LAUNCH("preprocess_fwd", debug, stream, preprocess_fwd_batch_kernel, (int)ceil_div(a.P, PRE_THREADS), PRE_THREADS, smem, cb, a, st);
+    const char *name = "preprocess_fwd";
+    const bool tma = use_tma_rows(a.shs, nullptr, cb.cam[0].sh_coeffs);
+    const size_t smem = a.shs ? sh_smem_bytes(tma, cb.cam[0].sh_coeffs, 1) : 0;
+    const int grid = (int)ceil_div(a.P, PRE_THREADS);
+    if (tma) GSB_PRE_LAUNCH(preprocess_fwd_batch_kernel<true>, grid, smem, cb, a, st);
+    else GSB_PRE_LAUNCH(preprocess_fwd_batch_kernel<false>, grid, smem, cb, a, st);
     return GSB_OK;
 }
 
 int launch_preprocess_bwd_batch(const CamArgsBatch &cb, const PreBwdArgs &a, const PreBwdBatchStrides &st, bool accumulate, bool debug,
                                 cudaStream_t stream) {
     if (a.P <= 0 || a.p_end <= a.p_begin) return GSB_OK;
+    const char *name = "preprocess_bwd";
     const int grid = (int)ceil_div(a.p_end - a.p_begin, PRE_THREADS);
-    const size_t smem = a.shs ? 2 * (size_t)PRE_THREADS * ((3 * cb.cam[0].sh_coeffs) | 1) * sizeof(float) : 0;
+    const bool tma = use_tma_rows(a.shs, a.g.dL_dshs, cb.cam[0].sh_coeffs);
+    const size_t smem = a.shs ? sh_smem_bytes(tma, cb.cam[0].sh_coeffs, 2) : 0;
     if (accumulate) {
-        if (smem > 40 * 1024) GSB_CUDA(cudaFuncSetAttribute(preprocess_bwd_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GSB_LAUNCH("preprocess_bwd", debug, stream, preprocess_bwd_batch_kernel<true>, grid, PRE_THREADS, smem, cb, a, st);
+        if (tma) GSB_PRE_LAUNCH((preprocess_bwd_batch_kernel<true, true>), grid, smem, cb, a, st);
+        else GSB_PRE_LAUNCH((preprocess_bwd_batch_kernel<true, false>), grid, smem, cb, a, st);
     } else {
-        if (smem > 40 * 1024) GSB_CUDA(cudaFuncSetAttribute(preprocess_bwd_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GSB_LAUNCH("preprocess_bwd", debug, stream, preprocess_bwd_batch_kernel<false>, grid, PRE_THREADS, smem, cb, a, st);
+        if (tma) GSB_PRE_LAUNCH((preprocess_bwd_batch_kernel<false, true>), grid, smem, cb, a, st);
+        else GSB_PRE_LAUNCH((preprocess_bwd_batch_kernel<false, false>), grid, smem, cb, a, st);
     }
     return GSB_OK;
 }

@@ -9,8 +9,10 @@
 //   2. instances by tile id, STABLE (D pairs, ceil(log2(tiles)/8) = 2 passes)
 // because instances are emitted in depth order and a stable sort keeps that order per tile.
 //
-// Per pass: digit histogram per block -> per-digit row scan -> stable scatter.
-// Traffic per pass: 2 key reads + 1 value read + 1 key write + 1 value write = 20 B / pair.
+// One upfront kernel builds the digit histograms of every pass; each pass is then ONE kernel ("onesweep", below):
+// keys and values are read once and written once per pass (16 B / pair).  The round-1 three-kernel-per-pass version
+// (histogram / row scan / scatter) and the 8-keys-per-thread block size (measured 4 % slower per pass on the B200,
+// gpurun_out/r2a_bench_ipt8.json) are gone from the build; git has them.
 #include "common.cuh"
 
 namespace gsb {
@@ -24,149 +26,16 @@ constexpr int SORT_IPT_BIG = 16;
 constexpr int SORT_IPT_SMALL = 4;
 constexpr int64_t SORT_SMALL_LIMIT = 148 * 4 * 1024;   // below ~0.6 M keys: 1024-key blocks to fill the SMs
 int g_sort_force_small = 0;   // option "sort_small": 1 = 4 keys per thread for every size, -1 = never (A/B, tests)
-int g_sort_big_ipt = SORT_IPT_BIG;   // option "sort_big_ipt": 8 or 16 keys per thread for large inputs (A/B: 8 halves the block's
-                                     // shared memory and registers -> more resident CTAs to hide the ranking / look-back latency)
 static inline int sort_ipt(int64_t n) {
-    if (g_sort_force_small < 0) return g_sort_big_ipt;
-    return (g_sort_force_small || n < SORT_SMALL_LIMIT) ? SORT_IPT_SMALL : g_sort_big_ipt;
+    if (g_sort_force_small < 0) return SORT_IPT_BIG;
+    return (g_sort_force_small || n < SORT_SMALL_LIMIT) ? SORT_IPT_SMALL : SORT_IPT_BIG;
 }
 // runs CALL with the compile-time constant I = keys per thread
 #define SORT_WITH_IPT(ipt, CALL)                                       \
     switch (ipt) {                                                     \
         case SORT_IPT_SMALL: { constexpr int I = SORT_IPT_SMALL; CALL; } break; \
-        case 8: { constexpr int I = 8; CALL; } break;                  \
         default: { constexpr int I = SORT_IPT_BIG; CALL; } break;      \
     }
-
-template <int SORT_IPT>
-__global__ void __launch_bounds__(SORT_THREADS)
-sort_hist_kernel(const uint32_t *__restrict__ keys, uint32_t *__restrict__ table, int64_t n,
-                 const unsigned long long *__restrict__ n_dev, int nblocks, int shift, uint32_t mask) {
-    constexpr int SORT_KPB = SORT_THREADS * SORT_IPT;
-    __shared__ uint32_t hist[RADIX];
-    if (n_dev) n = min((int64_t)*n_dev, n);
-    const int tid = threadIdx.x;
-    hist[tid] = 0;
-    __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * SORT_KPB;
-#pragma unroll 4
-    for (int i = 0; i < SORT_IPT; ++i) {
-        int64_t idx = base + (int64_t)i * SORT_THREADS + tid;
-        if (idx < n) atomicAdd(&hist[(keys[idx] >> shift) & mask], 1u);
-    }
-    __syncthreads();
-    table[(int64_t)tid * nblocks + blockIdx.x] = hist[tid];
-}
-
-// one block per digit: in-row exclusive scan over the blocks, row total -> totals[digit]
-__global__ void __launch_bounds__(256)
-sort_rowscan_kernel(uint32_t *__restrict__ table, uint32_t *__restrict__ totals, int nblocks) {
-    __shared__ uint32_t warp_sums[8];
-    __shared__ uint32_t carry_s;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    uint32_t *row = table + (int64_t)blockIdx.x * nblocks;
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    for (int base = 0; base < nblocks; base += 256) {
-        int i = base + tid;
-        uint32_t v = i < nblocks ? row[i] : 0u;
-        uint32_t incl = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) warp_sums[w] = incl;
-        __syncthreads();
-        uint32_t wprefix = 0, total = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            uint32_t s = warp_sums[k];
-            if (k < w) wprefix += s;
-            total += s;
-        }
-        const uint32_t carry = carry_s;
-        if (i < nblocks) row[i] = carry + wprefix + incl - v;
-        __syncthreads();
-        if (tid == 0) carry_s = carry + total;
-        __syncthreads();
-    }
-    if (tid == 0) totals[blockIdx.x] = carry_s;
-}
-
-template <int SORT_IPT>
-__global__ void __launch_bounds__(SORT_THREADS)
-sort_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
-                    const uint32_t *__restrict__ table, const uint32_t *__restrict__ totals, int64_t n,
-                    const unsigned long long *__restrict__ n_dev, int nblocks, int shift, uint32_t mask) {
-    constexpr int SORT_KPB = SORT_THREADS * SORT_IPT;
-    __shared__ uint32_t warp_cnt[SORT_THREADS / 32][RADIX];
-    if (n_dev) n = min((int64_t)*n_dev, n);
-    __shared__ uint32_t warp_sums[8];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-#pragma unroll
-    for (int k = 0; k < SORT_THREADS / 32; ++k) warp_cnt[k][tid] = 0;
-
-    // exclusive scan of the 256 digit totals -> global base of digit `tid`
-    const uint32_t tot = totals[tid];
-    uint32_t incl = tot;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) warp_sums[w] = incl;
-    __syncthreads();
-    uint32_t digit_base = incl - tot;
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-        if (k < w) digit_base += warp_sums[k];
-
-    // stable ranks: block order = (warp, round, lane)
-    const int64_t seg = (int64_t)blockIdx.x * SORT_KPB + (int64_t)w * (32 * SORT_IPT);
-    uint32_t key[SORT_IPT];
-    uint32_t rank[SORT_IPT];
-    const uint32_t lt_mask = (1u << lane) - 1u;
-#pragma unroll
-    for (int r = 0; r < SORT_IPT; ++r) {
-        const int64_t idx = seg + r * 32 + lane;
-        const bool valid = idx < n;
-        key[r] = valid ? keys_in[idx] : 0xffffffffu;
-        const uint32_t d = valid ? ((key[r] >> shift) & mask) : (uint32_t)RADIX;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (lane == leader && valid) {
-            base = warp_cnt[w][d];
-            warp_cnt[w][d] = base + __popc(peers);
-        }
-        base = __shfl_sync(0xffffffffu, base, leader);
-        rank[r] = base + __popc(peers & lt_mask);
-        __syncwarp();
-    }
-    __syncthreads();
-    {
-        uint32_t run = digit_base + table[(int64_t)tid * nblocks + blockIdx.x];
-#pragma unroll
-        for (int k = 0; k < SORT_THREADS / 32; ++k) {
-            uint32_t c = warp_cnt[k][tid];
-            warp_cnt[k][tid] = run;
-            run += c;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < SORT_IPT; ++r) {
-        const int64_t idx = seg + r * 32 + lane;
-        if (idx < n) {
-            const uint32_t d = (key[r] >> shift) & mask;
-            const uint32_t pos = warp_cnt[w][d] + rank[r];
-            keys_out[pos] = key[r];
-            vals_out[pos] = vals_in[idx];
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Single-pass-per-digit variant ("onesweep"): one upfront kernel builds the global digit histograms of
@@ -397,8 +266,6 @@ onesweep_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
     }
 }
 
-int g_sort_variant = 1;  // 0: histogram / row scan / scatter per pass, 1: onesweep
-
 static size_t onesweep_scratch_bytes(int64_t n, int V) {
     const int64_t nblocks = ceil_div(n > 0 ? n : 1, SORT_THREADS * sort_ipt(n));
     return align_up((size_t)GSB_SORT_MAX_VIEWS * OS_MAX_PASSES * RADIX * 4 + 256 + (size_t)V * OS_MAX_PASSES * nblocks * RADIX * 4, 256);
@@ -406,7 +273,7 @@ static size_t onesweep_scratch_bytes(int64_t n, int V) {
 
 static int onesweep_sort(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n,
                          const unsigned long long *n_dev, int begin_bit, int end_bit, void *scratch, bool debug,
-                         cudaStream_t stream, int V, size_t sv, bool hist_ready) {
+                         cudaStream_t stream, int V, size_t sv) {
     OnesweepPasses ps;
     ps.npass = 0;
     for (int bit = begin_bit; bit < end_bit; bit += RADIX_BITS) {
@@ -424,14 +291,9 @@ static int onesweep_sort(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uin
     uint32_t *status = ticket + 64;
     const size_t sv_status = (size_t)ps.npass * nblocks * RADIX;
     const size_t zero_bytes = (size_t)GSB_SORT_MAX_VIEWS * OS_MAX_PASSES * RADIX * 4 + 256 + (size_t)V * sv_status * 4;
-    if (hist_ready) {      // the histograms are already there: clear only the tickets and the look-back status words
-        const size_t hist_bytes = (size_t)GSB_SORT_MAX_VIEWS * OS_MAX_PASSES * RADIX * 4;
-        GSB_CUDA(cudaMemsetAsync(static_cast<char *>(scratch) + hist_bytes, 0, zero_bytes - hist_bytes, stream));
-    } else {
-        GSB_CUDA(cudaMemsetAsync(scratch, 0, zero_bytes, stream));
-        const int hist_blocks = (int)(ceil_div(n, 256 * 16) < 148 * 8 ? ceil_div(n, 256 * 16) : 148 * 8);
-        GSB_LAUNCH("sort_hist", debug, stream, onesweep_hist_kernel, dim3(hist_blocks, V), 256, 0, keys, ghist, n, n_dev, ps, sv);
-    }
+    GSB_CUDA(cudaMemsetAsync(scratch, 0, zero_bytes, stream));
+    const int hist_blocks = (int)(ceil_div(n, 256 * 16) < 148 * 8 ? ceil_div(n, 256 * 16) : 148 * 8);
+    GSB_LAUNCH("sort_hist", debug, stream, onesweep_hist_kernel, dim3(hist_blocks, V), 256, 0, keys, ghist, n, n_dev, ps, sv);
     uint32_t *kin = keys, *vin = vals, *kout = keys_alt, *vout = vals_alt;
     for (int p = 0; p < ps.npass; ++p) {
         uint32_t *st = status + (size_t)p * nblocks * RADIX;
@@ -448,50 +310,18 @@ static int onesweep_sort(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uin
     return GSB_OK;
 }
 
-size_t sort_scratch_bytes(int64_t n, int V) {
-    int64_t nblocks = ceil_div(n > 0 ? n : 1, SORT_THREADS * sort_ipt(n));
-    const size_t classic = align_up((size_t)RADIX * nblocks * sizeof(uint32_t), 256) + align_up(RADIX * sizeof(uint32_t), 256);
-    const size_t os = onesweep_scratch_bytes(n, V);
-    return classic > os ? classic : os;
-}
+size_t sort_scratch_bytes(int64_t n, int V) { return onesweep_scratch_bytes(n, V); }
 
 int sort_pairs(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uint32_t *vals_alt, int64_t n,
                const unsigned long long *n_dev, int begin_bit, int end_bit, void *scratch, bool debug,
-               cudaStream_t stream, int V, size_t sv, bool hist_ready) {
+               cudaStream_t stream, int V, size_t sv) {
     if (n <= 0 || end_bit <= begin_bit) return GSB_OK;
     if (n >= (int64_t)1 << 30) {
         set_error("sort_pairs: n=%lld does not fit 30-bit positions", (long long)n);
         return GSB_ERR_OVERFLOW;
     }
     if (V > GSB_SORT_MAX_VIEWS) { set_error("sort_pairs: more than %d views", GSB_SORT_MAX_VIEWS); return GSB_ERR_ARGUMENT; }
-    if ((g_sort_variant == 1 || V > 1) && (end_bit - begin_bit) <= OS_MAX_PASSES * RADIX_BITS)
-        return onesweep_sort(keys, vals, keys_alt, vals_alt, n, n_dev, begin_bit, end_bit, scratch, debug, stream, V, sv, hist_ready);
-    if (hist_ready) { set_error("sort_pairs: precomputed histograms need the onesweep path"); return GSB_ERR_ARGUMENT; }
-    if (V > 1) { set_error("sort_pairs: the view-batch sort needs the onesweep path"); return GSB_ERR_ARGUMENT; }
-    const int ipt = sort_ipt(n);
-    const int nblocks = (int)ceil_div(n, SORT_THREADS * ipt);
-    uint32_t *table = static_cast<uint32_t *>(scratch);
-    uint32_t *totals = reinterpret_cast<uint32_t *>(static_cast<char *>(scratch) +
-                                                    align_up((size_t)RADIX * nblocks * sizeof(uint32_t), 256));
-    uint32_t *kin = keys, *vin = vals, *kout = keys_alt, *vout = vals_alt;
-    int passes = 0;
-    for (int bit = begin_bit; bit < end_bit; bit += RADIX_BITS) {
-        const int bits = (end_bit - bit) < RADIX_BITS ? (end_bit - bit) : RADIX_BITS;
-        const uint32_t mask = (1u << bits) - 1u;
-        SORT_WITH_IPT(ipt, GSB_LAUNCH("sort_hist", debug, stream, sort_hist_kernel<I>, nblocks, SORT_THREADS, 0, kin, table, n, n_dev,
-                                 nblocks, bit, mask));
-        GSB_LAUNCH("sort_rowscan", debug, stream, sort_rowscan_kernel, RADIX, 256, 0, table, totals, nblocks);
-        SORT_WITH_IPT(ipt, GSB_LAUNCH("sort_scatter", debug, stream, sort_scatter_kernel<I>, nblocks, SORT_THREADS, 0, kin, vin, kout, vout,
-                                 table, totals, n, n_dev, nblocks, bit, mask));
-        uint32_t *t = kin; kin = kout; kout = t;
-        t = vin; vin = vout; vout = t;
-        ++passes;
-    }
-    if (passes & 1) {  // result sits in the alt buffers
-        GSB_CUDA(cudaMemcpyAsync(keys, keys_alt, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
-        GSB_CUDA(cudaMemcpyAsync(vals, vals_alt, (size_t)n * 4, cudaMemcpyDeviceToDevice, stream));
-    }
-    return GSB_OK;
+    return onesweep_sort(keys, vals, keys_alt, vals_alt, n, n_dev, begin_bit, end_bit, scratch, debug, stream, V, sv);
 }
 
 }  // namespace gsb

@@ -286,8 +286,7 @@ void gsb_reset_launch_count(void);
 /* CUDA-event time of the launches of kernel `name` ("" = all) recorded on their launching stream since
  * the last reset, while option "time_kernels" was 1 (blend kernels) or 2 (all).  Synchronises on the events. */
 int32_t gsb_kernel_time(const char *name, double *total_ms, int64_t *launches, int32_t reset);
-/* tuning knobs (integers): "cull", "fused_ranges", "sort_big_ipt", "sort_variant", "sort_small", "tile_order",
- * "time_kernels"; returns 0 if known */
+/* tuning knobs (integers): "cull", "sort_small", "tile_order", "pre_tma", "time_kernels"; returns 0 if known */
 int32_t gsb_set_option(const char *name, int32_t value);
 
 #ifdef __cplusplus

@@ -192,19 +192,6 @@ def test_needle_gaussians_are_as_exact_as_float32_allows(on_host):
     U.assert_grads_close(got["grads"], ref["grads"], tol=1e-2)
 
 
-def test_fused_ranges_option(on_host):
-    """Option fused_ranges (default off; an A/B candidate): tile ranges and the tile sort's digit histograms come from per-tile
-    counters that emit fills, instead of a pass over the D sorted keys and a histogram pass over the D unsorted ones.  Single
-    view against the oracle here (some tiles empty at the image border); the -m gpu suite repeats it on the view-batch path."""
-    dgr = on_host
-    scene = TO.make_scene(180, seed=62, log_scale_mean=-2.1, log_scale_std=0.6)
-    dgr.set_option("fused_ranges", 1)
-    try:
-        _check(scene, TO.make_camera(80, 48, sh_degree=2, bg=(0.2, 0.1, 0.3)), "sh")
-    finally:
-        dgr.set_option("fused_ranges", 0)
-
-
 def _batch_step(scene, cams, gts, bg, **kw):
     import bench
     from gaussian_renderer import GradientBucket, render_views_backward
@@ -271,3 +258,27 @@ def test_chunked_gradient_kernel_and_tile_order(on_host):
     ref = U.run_oracle(U.make_args(small, "sh"), cam, *_weights(cam))
     U.assert_image_close(single["color"], ref["color"], "tile_order single view")
     U.assert_grads_close(single["grads"], ref["grads"])
+
+
+@pytest.mark.parametrize("deg", [1, 3])
+def test_tma_row_path_source(on_host, deg):
+    """Option pre_tma: SH rows staged with one bulk copy each and accessed as float4 (csrc/preprocess.cu, VEC layout): single
+    view against the oracle, and the view-batch step in accumulate mode (bulk reduce-add of the gradient rows) against the
+    default path.  (On the host build the bulk copies are synchronous memcpys: this checks layout and indexing, the -m gpu
+    suite the asynchronous mechanics.)"""
+    dgr = on_host
+    sh_coeffs = (deg + 1) ** 2
+    scene = TO.make_scene(260, seed=40 + deg, sh_coeffs=sh_coeffs, log_scale_mean=-2.4)
+    dgr.set_option("pre_tma", 1)
+    try:
+        _check(scene, TO.make_camera(64, 48, sh_degree=deg, bg=(0.1, 0.3, 0.6)), "sh")
+        if deg == 3:
+            sc, cams, gts, bg = _batch_inputs()
+            l1, g1, im1, _ = _batch_step(sc, cams, gts, bg)
+    finally:
+        dgr.set_option("pre_tma", 0)
+    if deg == 3:
+        l0, g0, im0, _ = _batch_step(sc, cams, gts, bg)
+        for a, b in zip(im0, im1):
+            assert np.array_equal(a, b)
+        assert np.array_equal(l0, l1) and np.abs(g0 - g1).max() <= 1e-5 * np.abs(g0).max()

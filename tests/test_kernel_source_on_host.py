@@ -31,7 +31,7 @@ def emul(host_lib):
     lib.emul_scan_partials.argtypes = [ctypes.c_size_t]
     lib.emul_sort_scratch_bytes.restype = ctypes.c_size_t
     lib.emul_sort_scratch_bytes.argtypes = [i64, i32]
-    lib.emul_sort_pairs.argtypes = [vp, vp, vp, vp, i64, vp, i32, i32, vp, i32, ctypes.c_size_t, i32, i32, i32]
+    lib.emul_sort_pairs.argtypes = [vp, vp, vp, vp, i64, vp, i32, i32, vp, i32, ctypes.c_size_t, i32]
     return lib
 
 
@@ -120,18 +120,16 @@ def test_knn_source_matches_bruteforce(on_host, kind):
         assert distCUDA2(torch.from_numpy(pts[:1])).tolist() == [0.0] and distCUDA2(torch.zeros(0, 3)).numel() == 0
 
 
-@pytest.mark.parametrize("n,bits,V,variant,small,big_ipt", [
-    (1, 32, 1, 1, 0, 16), (1000, 32, 1, 1, 0, 16), (5000, 13, 1, 1, 0, 16),   # onesweep, 1024-key blocks, multi-block look-back
-    (5000, 13, 3, 1, 0, 16),                                                  # view batch: three independent sorts, ragged counts
-    (40000, 13, 1, 1, 0, 16),                                                 # 40 blocks: the eight-deep look-back window wraps
-    (5000, 10, 1, 0, 0, 16),                                                  # classic histogram / row-scan / scatter path
-    (40000, 13, 2, 1, -1, 16),                                                # 16 keys per thread (large-input instantiation)
-    (50000, 8, 1, 1, -1, 8),                                                  # option sort_big_ipt = 8
-    (50000, 8, 1, 0, -1, 16),                                                 # classic path, 16 keys per thread
+@pytest.mark.parametrize("n,bits,V,small", [
+    (1, 32, 1, 0), (1000, 32, 1, 0), (5000, 13, 1, 0),     # 1024-key blocks, multi-block look-back
+    (5000, 13, 3, 0),                                      # view batch: three independent sorts, ragged counts
+    (40000, 13, 1, 0),                                     # 40 blocks: the eight-deep look-back window wraps
+    (40000, 13, 2, -1),                                    # 16 keys per thread (large-input instantiation)
+    (50000, 8, 1, -1),
 ])
-def test_radix_sort_source_is_stable(emul, n, bits, V, variant, small, big_ipt):
-    """The hot path's sort (csrc/radix_sort.cu, both variants and all block sizes) on the host: stable order on the sorted
-    bits, values carried, untouched tails when the per-view count is below the launch size."""
+def test_radix_sort_source_is_stable(emul, n, bits, V, small):
+    """The hot path's sort (csrc/radix_sort.cu, both block sizes) on the host: stable order on the sorted bits, values
+    carried, untouched tails when the per-view count is below the launch size."""
     r = np.random.default_rng(n + bits)
     sv = n + 37                                                       # stride between the views' arrays
     keys = r.integers(0, 2 ** 32, V * sv, dtype=np.uint64).astype(np.uint32)
@@ -143,7 +141,7 @@ def test_radix_sort_source_is_stable(emul, n, bits, V, variant, small, big_ipt):
     ka, va = np.zeros_like(k), np.zeros_like(v_)
     scratch = np.zeros(emul.emul_sort_scratch_bytes(n, V), dtype=np.uint8)
     rc = emul.emul_sort_pairs(k.ctypes.data, v_.ctypes.data, ka.ctypes.data, va.ctypes.data, n, counts.ctypes.data if V > 1 else None,
-                              0, bits, scratch.ctypes.data, V, sv, variant, small, big_ipt)
+                              0, bits, scratch.ctypes.data, V, sv, small)
     assert rc == 0
     mask = np.uint32((1 << bits) - 1) if bits < 32 else np.uint32(0xFFFFFFFF)
     for view in range(V):
