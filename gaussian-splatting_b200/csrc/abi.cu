@@ -38,7 +38,9 @@ void timer_end(void *token, cudaStream_t stream) {
 }
 
 static int opt_cull = 1;
-static int opt_tile_order = 0;    // 1: blend CTAs take the tiles by descending list length (render.cu tile_order_kernel; A/B)
+static int opt_tile_order = 1;    // blend CTAs take the tiles by descending list length (render.cu tile_order_kernel): measured on the
+                                  // bench workload, blend kernels of a single view -9 % / -6 % (backward / forward: the tail of
+                                  // a lone 8160-CTA launch), of the 8-view launch -1.4 % (gpurun_out/r2b_bench_*.json); 0 = off
 
 void set_error(const char *fmt, ...) {
     va_list ap;

@@ -760,7 +760,7 @@ mark_visible_kernel(const int P, const float *__restrict__ means, const float *_
 
 // Option pre_tma: SH rows move between global and shared memory as TMA bulk copies (one per row) and are accessed as float4.
 // Needs 16-byte rows (n = 3 M a multiple of 4: SH degree 1 and 3 tensors) and 16-byte aligned tensors.
-int g_pre_tma = 0;
+int g_pre_tma = 1;   // measured: preprocess_bwd 0.165 -> 0.134 ms, preprocess_fwd 0.087 -> 0.076 ms per single view; 0 = off (A/B)
 static bool use_tma_rows(const float *shs, const float *dshs, int sh_coeffs) {
     return g_pre_tma && shs && ((3 * sh_coeffs) & 3) == 0 && (reinterpret_cast<size_t>(shs) & 15) == 0 &&
            (reinterpret_cast<size_t>(dshs) & 15) == 0;

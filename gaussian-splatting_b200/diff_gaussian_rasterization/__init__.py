@@ -355,6 +355,12 @@ def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
 
 
 def _check(rc: int, arena: Optional[_Arena] = None):
+    if arena is not None:
+        # The ctypes callback holds a bound method of the arena, the arena holds the callback: a reference cycle that would keep
+        # every buffer of the call (hundreds of MB of state per step) alive until the cyclic garbage collector runs -- forcing
+        # the caching allocator to cudaMalloc fresh segments meanwhile (a device-wide synchronisation, tens of ms).  The library
+        # never calls back after the entry point has returned, so the cycle is cut here and everything frees by refcount.
+        arena.cb = None
     if rc != 0:
         msg = _C.gsb_last_error().decode(errors="replace")
         if arena is not None and arena.error is not None:

@@ -282,3 +282,25 @@ def test_tma_row_path_source(on_host, deg):
         for a, b in zip(im0, im1):
             assert np.array_equal(a, b)
         assert np.array_equal(l0, l1) and np.abs(g0 - g1).max() <= 1e-5 * np.abs(g0).max()
+
+
+def test_state_buffers_are_freed_by_refcount_not_by_the_garbage_collector(on_host):
+    """The allocator callback handed to the C ABI must not keep a call's buffers in a reference cycle: with the cyclic GC off
+    (bench.py's timed region; any latency-sensitive loop) every step would otherwise pin ~1 GB of forward state until the next
+    collection, and the caching allocator would have to cudaMalloc its way around it."""
+    import gc
+    import weakref
+    dgr = on_host
+    scene = TO.make_scene(120, seed=3, log_scale_mean=-2.2)
+    cam = U.settings_to(TO.make_camera(48, 32, sh_degree=3), "cpu")
+    a = U.make_args(scene, "sh")
+    gc.collect()
+    gc.disable()
+    try:
+        _, _, _, pack = dgr._forward_impl(a["means3D"], a["shs"], None, a["opacities"].reshape(-1), a["scales"], a["rotations"], None, cam)
+        refs = [weakref.ref(pack[k]) for k in ("geom", "binning", "image")]
+        assert all(r() is not None for r in refs)
+        del pack
+        assert all(r() is None for r in refs), "forward state survived its last reference: a cycle keeps it alive"
+    finally:
+        gc.enable()
