@@ -489,6 +489,7 @@ def main():
                                         on_grad_chunk=on_chunk if chunked else None)
             total = out["losses"].sum()
             if chunked:
+                pending.extend(bucket.all_reduce_rest())     # the narrow parameters: one collective behind the last chunk
                 GradientBucket.wait_all(pending)
             else:
                 bucket.all_reduce()

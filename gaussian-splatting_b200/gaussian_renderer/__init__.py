@@ -347,34 +347,44 @@ class GradientBucket:
             raise ValueError("GradientBucket needs at least one parameter")
         dev, total = self.params[0].device, sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        # Layout: the widest parameter (the SH coefficients: 48 of the 59 floats per gaussian) LAST, everything else in front of
+        # it as one contiguous region -- the chunk-wise reduction then needs one collective per chunk of SH rows plus ONE for the
+        # rest, instead of one per (chunk, parameter): twenty latency-bound launches cost what the overlap saves.
+        width = lambda p: p.numel() // max(1, p.shape[0])
+        self.big = max(self.params, key=width)
         off = 0
-        for p in self.params:
+        for p in [q for q in self.params if q is not self.big] + [self.big]:
             if p.dtype != torch.float32 or p.device != dev:
                 raise ValueError("GradientBucket: float32 parameters on one device only")
+            if p is self.big:
+                self.rest = self.flat[:off]
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
 
     def zero_(self):
         self.flat.zero_()
 
-    def all_reduce_rows(self, p_begin: int, p_end: int, group=None):
-        """Asynchronous all-reduce of gaussians [p_begin, p_end) of every parameter's gradient (each a contiguous row
-        range), issued as ONE coalesced NCCL launch.  Ordered after the work enqueued so far on the current stream and
-        running on the process group's own stream, i.e. concurrently with whatever the caller enqueues next.  Returns a
-        list of handles for ``wait_all``; empty for world size 1."""
+    @staticmethod
+    def _distributed(group) -> bool:
         import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+    def all_reduce_rows(self, p_begin: int, p_end: int, group=None):
+        """Asynchronous all-reduce of gaussians [p_begin, p_end) of the WIDEST parameter's gradient (a contiguous row range).
+        Ordered after the work enqueued so far on the current stream, running on the process group's own stream, i.e.
+        concurrently with whatever the caller enqueues next.  Returns a list of handles for ``wait_all`` (empty for world
+        size 1).  The other parameters go out with ``all_reduce_rest`` once every chunk has been enqueued."""
+        import torch.distributed as dist
+        if not self._distributed(group) or p_end <= p_begin:
             return []
-        segs = [p.grad[p_begin:p_end] for p in self.params if p_end > p_begin]
-        if not segs:
+        return [dist.all_reduce(self.big.grad[p_begin:p_end], op=dist.ReduceOp.SUM, group=group, async_op=True)]
+
+    def all_reduce_rest(self, group=None):
+        """Asynchronous all-reduce of every parameter but the widest one: one collective over their contiguous region."""
+        import torch.distributed as dist
+        if not self._distributed(group) or self.rest.numel() == 0:
             return []
-        manager = getattr(dist, "_coalescing_manager", None)
-        if manager is None:      # older torch: one launch per segment
-            return [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True) for t in segs]
-        with manager(group=group, async_ops=True) as cm:
-            for t in segs:
-                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        return [cm]
+        return [dist.all_reduce(self.rest, op=dist.ReduceOp.SUM, group=group, async_op=True)]
 
     @staticmethod
     def wait_all(handles) -> None:

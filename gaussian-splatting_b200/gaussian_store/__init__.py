@@ -32,8 +32,8 @@ __all__ = ["GaussianModel", "expon_lr", "store_offsets"]
 
 
 class _StoreBucket:
-    """GaussianModel.grad as the data-parallel bucket: one all-reduce for everything, or row ranges of the five groups
-    (xyz | features | opacity | scaling | rotation) as one coalesced launch (overlapped with the chunked gradient kernel)."""
+    """GaussianModel.grad as the data-parallel bucket: one all-reduce for everything, or -- overlapped with the chunked
+    gradient kernel -- row ranges of the features group (most of the bytes) followed by one launch for the other groups."""
 
     def __init__(self, model):
         self.m = model
@@ -41,19 +41,28 @@ class _StoreBucket:
     def zero_(self):
         self.m.grad.zero_()
 
-    def _segments(self, p0, p1):
-        m = self.m
-        o, P, M = store_offsets(m.P, m.sh_coeffs), m.P, m.sh_coeffs
-        widths = (("xyz", 3), ("features", 3 * M), ("opacity", 1), ("scaling", 3), ("rotation", 4))
-        return [m.grad[o[n] + w * p0:o[n] + w * p1] for n, w in widths if p1 > p0]
+    @staticmethod
+    def _distributed(group) -> bool:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
 
     def all_reduce_rows(self, p_begin: int, p_end: int, group=None):
+        """Rows [p_begin, p_end) of the features group (3 M of the 11 + 3 M floats per gaussian), asynchronously."""
         import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if not self._distributed(group) or p_end <= p_begin:
             return []
-        segs = self._segments(p_begin, p_end)
-        if not segs:
+        m = self.m
+        a, w = store_offsets(m.P, m.sh_coeffs)["features"], 3 * m.sh_coeffs
+        return [dist.all_reduce(m.grad[a + w * p_begin:a + w * p_end], op=dist.ReduceOp.SUM, group=group, async_op=True)]
+
+    def all_reduce_rest(self, group=None):
+        """The other four groups: xyz, and opacity | scaling | rotation (contiguous), as one coalesced launch."""
+        import torch.distributed as dist
+        if not self._distributed(group):
             return []
+        m = self.m
+        o = store_offsets(m.P, m.sh_coeffs)
+        segs = [m.grad[:o["features"]], m.grad[o["opacity"]:]]
         manager = getattr(dist, "_coalescing_manager", None)
         if manager is None:
             return [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True) for t in segs]

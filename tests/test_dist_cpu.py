@@ -141,10 +141,15 @@ def _train_worker(rank, world, port, q, lib):
             gts = [torch.rand(3, H, W, generator=torch.Generator().manual_seed(100 + i)) for i in range(NV)]
             mine = shard_views(list(range(NV)), rank, world)
             m.update_learning_rate(1)
+            # the reduction protocol of bench.py: rows of the features group as each chunk of the gradient kernel is enqueued,
+            # one launch for the narrow groups behind the last chunk (world 1: both are no-ops)
+            bucket, pending = m.gradient_bucket(), []
             render_views_backward([cams[i] for i in mine], m, bench.Pipe(), torch.zeros(3),
-                                  lambda img, d, k: dgr.l1_loss_and_grad(img, gts[mine[k]]), loss_returns_grad=True, overwrite=True)
-            if world > 1:
-                dist.all_reduce(m.grad)                      # the one collective of the step
+                                  lambda img, d, k: dgr.l1_loss_and_grad(img, gts[mine[k]]), loss_returns_grad=True, overwrite=True,
+                                  grad_chunks=2, on_grad_chunk=lambda c, p0, p1: pending.extend(bucket.all_reduce_rows(p0, p1)))
+            pending.extend(bucket.all_reduce_rest())
+            bucket.wait_all(pending)
+            assert (len(pending) >= 2) == (world > 1)
             grad = m.grad.clone()
             m.optimizer_step()
             q.put((rank, world, grad.numpy(), m.store.numpy().copy()))
@@ -155,7 +160,7 @@ def _train_worker(rank, world, port, q, lib):
 
 def test_data_parallel_training_step_with_kernel_sources_gloo_world2(host_lib):
     """View-parallel step end to end on the CPU: each rank renders its views with the kernels' source (tests/host_emul),
-    ONE gloo all-reduce of the store's gradient buffer, fused Adam on every rank.  The reduced gradient equals the
+    the chunk-wise gloo all-reduce of the store's gradient buffer, fused Adam on every rank.  The reduced gradient equals the
     single-process gradient over all views, and both ranks end with bit-identical parameters."""
     import numpy as np
     ctx = mp.get_context("spawn")
