@@ -71,9 +71,15 @@ def parse():
     ap.add_argument("--no-batch", action="store_true", help="views API view by view instead of gsb_forward_batch")
     ap.add_argument("--sync", action="store_true",
                     help="A/B: the synchronous view-batch call (one instance-count read-back per step) instead of the sync-free one")
-    ap.add_argument("--grad-chunks", type=int, default=-1,
-                    help="gaussian-range chunks of the gradient-writing kernel, each all-reduced while the next computes "
-                         "(default: 4 when world size > 1, else 1)")
+    ap.add_argument("--grad-chunks", type=int, default=1,
+                    help="gaussian-range chunks of the gradient-writing kernel, each chunk's SH rows all-reduced while the next "
+                         "computes.  Default 1 = one all-reduce after the last kernel: on 8 B200s the chunked variant measured "
+                         "SLOWER (9.75 vs 9.47 ms/step, profiles/r2_scaling.md) -- the concurrent NCCL kernels cost the compute "
+                         "kernel more than the overlap hides")
+    ap.add_argument("--reduce", default="allreduce", choices=["allreduce", "peer"],
+                    help="allreduce: one NCCL all-reduce of the gradient bucket after the last kernel.  peer: the FUSED reduce-"
+                         "scatter -- the gradient kernel adds every row into its owner rank's peer-mapped buffer over NVLink while "
+                         "it computes (gsb_backward_batch_peer), then a barrier and an in-place all-gather of the owned rows")
     ap.add_argument("--no-pin", action="store_true", help="do not pin the process to its GPU's NUMA-local cores")
     ap.add_argument("--no-single-view", action="store_true", help="skip the drop-in single-view leg (render() + autograd)")
     ap.add_argument("--workload", default="raster", choices=["raster", "train6m"],
@@ -411,7 +417,7 @@ def main():
             dgr.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     if world != a.gpus and rank == 0:
         print(f"# note: --gpus {a.gpus} but WORLD_SIZE {world}; using {world}", file=sys.stderr)
-    grad_chunks = a.grad_chunks if a.grad_chunks > 0 else (4 if world > 1 else 1)
+    grad_chunks = max(1, a.grad_chunks)
 
     torch.manual_seed(0)
     scene = make_scene(a.gaussians, seed=0, log_scale_mean=LOG_SCALE_MEAN)
@@ -432,6 +438,11 @@ def main():
     else:
         pc = BenchGaussians(scene, a.sh_degree, dev)
         bucket = GradientBucket(pc.parameters())
+    peer_bucket = None
+    if a.reduce == "peer" and world > 1 and not a.optimizer and a.api == "views" and not a.no_batch:
+        from gaussian_renderer.peer import PeerGradientBucket
+        peer_bucket = PeerGradientBucket({"means3D": pc._xyz, "shs": pc._shs, "opacities": pc._opacity, "scales": pc._scaling,
+                                          "rotations": pc._rotation})
     pipe = Pipe()
     bg = torch.zeros(3, device=dev)
     V, H, W = a.views_per_rank, a.height, a.width
@@ -482,13 +493,18 @@ def main():
 
             def on_chunk(_c, p0, p1):      # rows [p0, p1) of every gradient are final: reduce them while the next chunk computes
                 pending.extend(bucket.all_reduce_rows(p0, p1))
-            chunked = world > 1 and grad_chunks > 1 and not a.no_batch
+            chunked = world > 1 and grad_chunks > 1 and not a.no_batch and peer_bucket is None
+            if peer_bucket is not None:
+                peer_bucket.begin_step()
             out = render_views_backward(HostCams() if host_inputs else cams, pc, pipe, bg, loss_fn, loss_returns_grad=True,
                                         batched=not a.no_batch, overwrite=True,   # first chunk writes the bucket: no zeroing pass
                                         capacity=capacity, grad_chunks=grad_chunks if chunked else 1,
-                                        on_grad_chunk=on_chunk if chunked else None)
+                                        on_grad_chunk=on_chunk if chunked else None,
+                                        peers=peer_bucket.table() if peer_bucket is not None else None)
             total = out["losses"].sum()
-            if chunked:
+            if peer_bucket is not None:
+                peer_bucket.finish()        # barrier + in-place all-gather of the owned rows: every rank holds the summed gradient
+            elif chunked:
                 pending.extend(bucket.all_reduce_rest())     # the narrow parameters: one collective behind the last chunk
                 GradientBucket.wait_all(pending)
             else:
@@ -673,6 +689,9 @@ def main():
 
     if world > 1:
         dist.barrier()
+    if peer_bucket is not None:
+        torch.cuda.synchronize()
+        peer_bucket.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -734,6 +753,7 @@ def main():
 
     cfg = workload_config(a, world)
     cfg.update({"sync_free": capacity is not None, "grad_chunks": grad_chunks if world > 1 else 1,
+                "reduction": "fused reduce-scatter over peer memory + all-gather" if peer_bucket is not None else "one NCCL all-reduce",
                 "pinned_cores": None if not pinned_cores else f"{pinned_cores[0]}-{pinned_cores[-1]} ({len(pinned_cores)})",
                 "instance_capacity": None if capacity is None else capacity.capacity})
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),

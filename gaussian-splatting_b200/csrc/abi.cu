@@ -385,6 +385,7 @@ int32_t gsb_backward(const GsbSettings *s, const GsbInputs *in, const GsbState *
     pa.P = P; pa.means = in->means3D; pa.shs = in->shs; pa.opac = in->opacities; pa.scales = in->scales; pa.rots = in->rotations;
     pa.cov_pre = in->cov3D_precomp; pa.splat = splat; pa.dacc = dacc; pa.g = *grads;
     pa.p_begin = 0; pa.p_end = P;
+    pa.peer.world = 0;
     return launch_preprocess_bwd(cam, pa, accumulate != 0, debug, stream);
 }
 
@@ -601,7 +602,7 @@ int32_t gsb_forward_batch_async(int32_t V, const GsbSettings *s, const GsbInputs
 static int backward_batch_impl(int32_t V, const GsbSettings *s, const GsbInputs *in, const GsbState *states, const float *out_color,
                                const float *out_invdepth, const float *dL_dcolor, const float *dL_dinvdepth, const GsbGrads *grads,
                                int32_t accumulate, int32_t n_chunks, gsb_chunk_fn on_chunk, void *chunk_ctx, gsb_alloc_fn alloc,
-                               void *alloc_ctx, cudaStream_t stream) {
+                               void *alloc_ctx, cudaStream_t stream, const GsbPeerTable *peers = nullptr) {
     CamArgsBatch cb;
     int rc = check_batch(V, s, in, cb);
     if (rc) return rc;
@@ -647,6 +648,18 @@ static int backward_batch_impl(int32_t V, const GsbSettings *s, const GsbInputs 
     PreBwdArgs pa;
     pa.P = P; pa.means = in->means3D; pa.shs = in->shs; pa.opac = in->opacities; pa.scales = in->scales; pa.rots = in->rotations;
     pa.cov_pre = nullptr; pa.splat = static_cast<const float4 *>(states[0].splat); pa.dacc = dacc; pa.g = *grads;
+    pa.peer.world = 0;
+    if (peers) {
+        if (peers->world < 1 || peers->world > GSB_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world ||
+            (int64_t)peers->rows_per_rank * peers->world < P) {
+            set_error("gsb_backward_batch_peer: bad peer table (world %d, rank %d, rows_per_rank %d, P %d)", peers->world, peers->rank,
+                      peers->rows_per_rank, P);
+            return GSB_ERR_ARGUMENT;
+        }
+        pa.peer.world = peers->world; pa.peer.rows_per_rank = peers->rows_per_rank;
+        for (int r = 0; r < GSB_MAX_PEERS; ++r)
+            pa.peer.delta[r] = r < peers->world ? (long long)((const char *)peers->base[r] - (const char *)peers->base[peers->rank]) : 0;
+    }
     PreBwdBatchStrides ps;
     ps.splat = sv_splat; ps.dacc = sv_dacc; ps.means2D = (size_t)P * 3;
     // gaussian-range chunks: chunk c's gradients are final when its launch completes, so the caller can start reducing
@@ -673,6 +686,17 @@ int32_t gsb_backward_batch(int32_t V, const GsbSettings *s, const GsbInputs *in,
                                alloc, alloc_ctx, static_cast<cudaStream_t>(cuda_stream));
 }
 
+int32_t gsb_backward_batch_peer(int32_t V, const GsbSettings *s, const GsbInputs *in, const GsbState *states, const float *out_color,
+                                const float *out_invdepth, const float *dL_dcolor, const float *dL_dinvdepth, const GsbGrads *grads,
+                                const GsbPeerTable *peers, gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream) {
+    if (!s || !in || !states || !out_color || !out_invdepth || !dL_dcolor || !grads || !alloc || in->P <= 0 || !peers) {
+        set_error("gsb_backward_batch_peer: NULL argument or empty input");
+        return GSB_ERR_ARGUMENT;
+    }
+    return backward_batch_impl(V, s, in, states, out_color, out_invdepth, dL_dcolor, dL_dinvdepth, grads, 1, 1, nullptr, nullptr, alloc,
+                               alloc_ctx, static_cast<cudaStream_t>(cuda_stream), peers);
+}
+
 int32_t gsb_backward_batch_chunked(int32_t V, const GsbSettings *s, const GsbInputs *in, const GsbState *states, const float *out_color,
                                    const float *out_invdepth, const float *dL_dcolor, const float *dL_dinvdepth, const GsbGrads *grads,
                                    int32_t accumulate, int32_t n_chunks, gsb_chunk_fn on_chunk, void *chunk_ctx, gsb_alloc_fn alloc,
@@ -684,6 +708,59 @@ int32_t gsb_backward_batch_chunked(int32_t V, const GsbSettings *s, const GsbInp
     return backward_batch_impl(V, s, in, states, out_color, out_invdepth, dL_dcolor, dL_dinvdepth, grads, accumulate, n_chunks, on_chunk,
                                chunk_ctx, alloc, alloc_ctx, static_cast<cudaStream_t>(cuda_stream));
 }
+
+// ---- peer memory (one process per GPU of a node): allocation + CUDA IPC, for the fused reduce-scatter ----
+#ifdef GSB_HOST_EMUL   // tests/host_emul: one process, plain pointers; the IPC entry points do not exist there
+int32_t gsb_enable_peer_access(int32_t) { return GSB_OK; }
+int32_t gsb_peer_alloc(size_t bytes, void **ptr, uint8_t *) { *ptr = calloc(1, bytes ? bytes : 1); return *ptr ? GSB_OK : GSB_ERR_ALLOC; }
+int32_t gsb_peer_open(const uint8_t *, void **) { set_error("gsb_peer_open: no IPC on the host build"); return GSB_ERR_CUDA; }
+int32_t gsb_peer_close(void *) { return GSB_OK; }
+int32_t gsb_peer_free(void *ptr) { free(ptr); return GSB_OK; }
+#else
+int32_t gsb_enable_peer_access(int32_t peer_device) {
+    int dev = -1;
+    GSB_CUDA(cudaGetDevice(&dev));
+    if (peer_device == dev) return GSB_OK;
+    int can = 0;
+    GSB_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    if (!can) { set_error("device %d cannot access device %d as a peer", dev, peer_device); return GSB_ERR_CUDA; }
+    const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); return GSB_OK; }
+    if (e != cudaSuccess) { set_error("cudaDeviceEnablePeerAccess(%d) failed: %s", peer_device, cudaGetErrorString(e)); return GSB_ERR_CUDA; }
+    return GSB_OK;
+}
+
+int32_t gsb_peer_alloc(size_t bytes, void **ptr, uint8_t *handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!ptr || !handle64 || bytes == 0) { set_error("gsb_peer_alloc: bad argument"); return GSB_ERR_ARGUMENT; }
+    GSB_CUDA(cudaMalloc(ptr, bytes));
+    GSB_CUDA(cudaMemset(*ptr, 0, bytes));
+    cudaIpcMemHandle_t h;
+    GSB_CUDA(cudaIpcGetMemHandle(&h, *ptr));
+    memcpy(handle64, &h, 64);
+    return GSB_OK;
+}
+
+int32_t gsb_peer_open(const uint8_t *handle64, void **ptr) {
+    if (!ptr || !handle64) { set_error("gsb_peer_open: bad argument"); return GSB_ERR_ARGUMENT; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    // opened on the CURRENT device (the one whose kernels will dereference it): the lazy flag sets up peer access to the
+    // exporting device's memory for exactly this mapping
+    GSB_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GSB_OK;
+}
+
+int32_t gsb_peer_close(void *ptr) {
+    if (ptr) GSB_CUDA(cudaIpcCloseMemHandle(ptr));
+    return GSB_OK;
+}
+
+int32_t gsb_peer_free(void *ptr) {
+    if (ptr) GSB_CUDA(cudaFree(ptr));
+    return GSB_OK;
+}
+#endif
 
 int32_t gsb_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
                          uint8_t *present, void *cuda_stream) {

@@ -11,6 +11,7 @@ constexpr int DACC_STRIDE = 12;
 
 // ---- view-batch variants: per-view arrays are laid out [V][...] with uniform strides (in elements) ----
 constexpr int GSB_MAX_VIEWS = 16;
+constexpr int GSB_MAX_PEERS = 16;
 struct CamArgsBatch {
     int V;
     CamArgs cam[GSB_MAX_VIEWS];
@@ -30,6 +31,15 @@ struct PreFwdArgs {
     int cull;             // 1: exact tile culling, 0: reference rectangle (debug / A-B)
 };
 
+// Fused reduce-scatter (gsb_backward_batch_peer): gaussians [r * rows_per_rank, (r + 1) * rows_per_rank) are OWNED by rank r;
+// every rank adds its gradient rows straight into the owner's buffer.  delta[r] = byte offset that turns an address inside THIS
+// rank's gradient buffer into the same location of rank r's buffer as mapped into this process (0 for r == rank).
+struct PeerTable {
+    int world;              // 0 = no peers (plain local output)
+    int rows_per_rank;      // multiple of the per-gaussian kernels' block size
+    long long delta[GSB_MAX_PEERS];
+};
+
 struct PreBwdArgs {
     int P;
     const float *means, *shs, *opac, *scales, *rots, *cov_pre;
@@ -37,6 +47,7 @@ struct PreBwdArgs {
     const float *dacc;    // [P*DACC_STRIDE]
     int p_begin, p_end;   // gaussian range of this launch (chunked backward: the caller reduces finished chunks meanwhile)
     GsbGrads g;
+    PeerTable peer;       // world > 0: outputs are ADDED into the owners' buffers (view-batch kernel, TMA rows only)
 };
 
 struct BinArgs {

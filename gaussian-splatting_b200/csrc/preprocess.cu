@@ -618,6 +618,20 @@ __device__ __forceinline__ void write_gauss_grads(const PreBwdArgs &a, const int
     }
 }
 
+// ---- fused reduce-scatter: the block's gradients leave as bulk reduce-adds into the OWNER rank's memory ----------------------
+__device__ __forceinline__ long long peer_delta(const PeerTable &t, const int row0) {
+    const int owner = row0 / t.rows_per_rank;          // uniform per block: rows_per_rank is a multiple of PRE_THREADS
+    long long d = t.delta[0];
+#pragma unroll
+    for (int k = 1; k < GSB_MAX_PEERS; ++k)
+        if (k == owner) d = t.delta[k];
+    return d;
+}
+template <typename T>
+__device__ __forceinline__ T *shift_ptr(T *p, const long long bytes) {
+    return reinterpret_cast<T *>(reinterpret_cast<char *>(p) + bytes);
+}
+
 // K8, one view.
 template <bool ACC, bool TMA>
 __global__ void __launch_bounds__(PRE_THREADS)
@@ -738,6 +752,30 @@ preprocess_bwd_batch_kernel(const CamArgsBatch cb, const PreBwdArgs a, const Pre
             }
         }
     }
+    if (TMA && a.peer.world > 0) {
+        // Fused reduce-scatter.  SH gradient rows: one bulk reduce-add per row into the owner's buffer.  Narrow gradients (11
+        // floats per gaussian): staged as four dense [128, w] panels in the (now dead) parameter rows, one bulk reduce-add each --
+        // four NVLink-sized transactions per block instead of 11 scalar atomics per gaussian.  Threads past the end add zeros
+        // into the padding rows of the owner's buffer (the buffers hold world * rows_per_rank rows).
+        const long long dlt = peer_delta(a.peer, row0);
+        if (want_sh) tma_row_out<true>(shift_ptr(a.g.dL_dshs, dlt), gr, i, shn, live);
+        __syncthreads();                                   // every thread is done reading its parameter row
+        float *pan = sh_rows;                              // [128,3] xyz | [128] opacity | [128,3] scales | [128,4] rotations
+        const int t = threadIdx.x;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { pan[3 * t + c] = live ? gm[c] : 0.f; pan[4 * PRE_THREADS + 3 * t + c] = live ? g_sc[c] : 0.f; }
+        pan[3 * PRE_THREADS + t] = live ? g_op : 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) pan[7 * PRE_THREADS + 4 * t + c] = live ? g_rot[c] : 0.f;
+        bulk_store_fence();
+        __syncthreads();
+        if (t == 0 && a.g.dL_dmeans3D) bulk_s2g_add_f32(shift_ptr(a.g.dL_dmeans3D, dlt) + 3 * (size_t)row0, pan, 3 * PRE_THREADS * 4);
+        if (t == 1 && a.g.dL_dopacities) bulk_s2g_add_f32(shift_ptr(a.g.dL_dopacities, dlt) + (size_t)row0, pan + 3 * PRE_THREADS, PRE_THREADS * 4);
+        if (t == 2 && a.g.dL_dscales) bulk_s2g_add_f32(shift_ptr(a.g.dL_dscales, dlt) + 3 * (size_t)row0, pan + 4 * PRE_THREADS, 3 * PRE_THREADS * 4);
+        if (t == 3 && a.g.dL_drotations) bulk_s2g_add_f32(shift_ptr(a.g.dL_drotations, dlt) + 4 * (size_t)row0, pan + 7 * PRE_THREADS, 4 * PRE_THREADS * 4);
+        if (t < 4) bulk_store_commit_and_wait();
+        return;
+    }
     if (want_sh) {
         if (TMA) {
             tma_row_out<ACC>(a.g.dL_dshs, gr, i, shn, live);
@@ -819,6 +857,16 @@ int launch_preprocess_bwd_batch(const CamArgsBatch &cb, const PreBwdArgs &a, con
     const char *name = "preprocess_bwd";
     const int grid = (int)ceil_div(a.p_end - a.p_begin, PRE_THREADS);
     const bool tma = use_tma_rows(a.shs, a.g.dL_dshs, cb.cam[0].sh_coeffs);
+    if (a.peer.world > 0) {
+        if (!tma || 3 * cb.cam[0].sh_coeffs < 11) {
+            set_error("peer gradients need the TMA row path (option pre_tma, SH rows of 16-byte multiples, at least 4 coefficients)");
+            return GSB_ERR_ARGUMENT;
+        }
+        if (a.peer.world > GSB_MAX_PEERS || a.peer.rows_per_rank <= 0 || a.peer.rows_per_rank % PRE_THREADS) {
+            set_error("peer gradients: rows_per_rank must be a positive multiple of %d, world <= %d", PRE_THREADS, GSB_MAX_PEERS);
+            return GSB_ERR_ARGUMENT;
+        }
+    }
     const size_t smem = a.shs ? sh_smem_bytes(tma, cb.cam[0].sh_coeffs, 2) : 0;
     if (accumulate) {
         if (tma) GSB_PRE_LAUNCH((preprocess_bwd_batch_kernel<true, true>), grid, smem, cb, a, st);

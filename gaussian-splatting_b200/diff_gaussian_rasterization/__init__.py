@@ -53,6 +53,10 @@ class _Grads(Structure):
                 ("dL_dcov3D", c_void_p)]
 
 
+class _PeerTable(Structure):          # GsbPeerTable
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("rows_per_rank", c_int32), ("reserved", c_int32), ("base", c_void_p * 16)]
+
+
 _ALLOC_FN = CFUNCTYPE(c_void_p, c_void_p, c_int32, c_size_t)
 _CHUNK_FN = CFUNCTYPE(None, c_void_p, c_int32, c_int32, c_int32)     # gsb_chunk_fn(ctx, chunk, p_begin, p_end)
 ABI_VERSION = 6
@@ -99,6 +103,19 @@ def _load(path: Optional[str] = None):
     lib.gsb_backward_batch_chunked.argtypes = [c_int32, POINTER(_Settings), POINTER(_Inputs), POINTER(_State), c_void_p, c_void_p,
                                                c_void_p, c_void_p, POINTER(_Grads), c_int32, c_int32, _CHUNK_FN, c_void_p,
                                                _ALLOC_FN, c_void_p, c_void_p]
+    lib.gsb_backward_batch_peer.restype = c_int32
+    lib.gsb_backward_batch_peer.argtypes = [c_int32, POINTER(_Settings), POINTER(_Inputs), POINTER(_State), c_void_p, c_void_p,
+                                            c_void_p, c_void_p, POINTER(_Grads), POINTER(_PeerTable), _ALLOC_FN, c_void_p, c_void_p]
+    lib.gsb_enable_peer_access.restype = c_int32
+    lib.gsb_enable_peer_access.argtypes = [c_int32]
+    lib.gsb_peer_alloc.restype = c_int32
+    lib.gsb_peer_alloc.argtypes = [c_size_t, POINTER(c_void_p), c_void_p]
+    lib.gsb_peer_open.restype = c_int32
+    lib.gsb_peer_open.argtypes = [c_void_p, POINTER(c_void_p)]
+    lib.gsb_peer_close.restype = c_int32
+    lib.gsb_peer_close.argtypes = [c_void_p]
+    lib.gsb_peer_free.restype = c_int32
+    lib.gsb_peer_free.argtypes = [c_void_p]
     lib.gsb_mark_visible.restype = c_int32
     lib.gsb_mark_visible.argtypes = [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.gsb_sort_pairs.restype = c_int32
@@ -134,6 +151,38 @@ def _load(path: Optional[str] = None):
 
 
 _C = _load()
+
+
+def enable_peer_access(device, peer_device_index: int) -> None:
+    """Kernels on `device` may dereference pointers into GPU `peer_device_index` afterwards (gsb_enable_peer_access)."""
+    with _device_ctx(device):
+        _check(_C.gsb_enable_peer_access(int(peer_device_index)))
+
+
+def peer_alloc(device, nbytes: int):
+    """(device pointer, 64-byte IPC handle) of a fresh zero-filled allocation on `device` (gsb_peer_alloc)."""
+    ptr, handle = c_void_p(), ctypes.create_string_buffer(64)
+    with _device_ctx(device):
+        _check(_C.gsb_peer_alloc(int(nbytes), byref(ptr), handle))
+    return int(ptr.value), bytes(handle.raw)
+
+
+def peer_open(device, handle: bytes) -> int:
+    """Maps another process's gsb_peer_alloc allocation for kernels running on `device`; returns the local address."""
+    ptr, buf = c_void_p(), ctypes.create_string_buffer(handle, 64)
+    with _device_ctx(device):
+        _check(_C.gsb_peer_open(buf, byref(ptr)))
+    return int(ptr.value)
+
+
+def peer_close(device, ptr: int) -> None:
+    with _device_ctx(device):
+        _check(_C.gsb_peer_close(c_void_p(ptr)))
+
+
+def peer_free(device, ptr: int) -> None:
+    with _device_ctx(device):
+        _check(_C.gsb_peer_free(c_void_p(ptr)))
 
 
 def launch_count() -> int:
@@ -526,11 +575,13 @@ def capacity_for(count: int) -> int:
 
 
 def _backward_batch_impl(pack, settings_list, means3D, sh, opacities, scales, rotations, out_color, out_invdepth,
-                         grad_color, grad_invdepth, grads: dict, accumulate: bool, n_chunks: int = 1, on_chunk=None):
+                         grad_color, grad_invdepth, grads: dict, accumulate: bool, n_chunks: int = 1, on_chunk=None, peers=None):
     """View-batch backward (gsb_backward_batch).  grads: tensors holding / receiving the gradient SUMMED over the views
     (means2D, if present, is [V,P,3] and per view).  ``n_chunks`` > 1: gsb_backward_batch_chunked -- the last kernel runs in
     gaussian-range chunks and ``on_chunk(chunk, p_begin, p_end)`` is called after each chunk has been enqueued (rows
-    [p_begin, p_end) of every gradient are final in stream order from there on)."""
+    [p_begin, p_end) of every gradient are final in stream order from there on).  ``peers`` = (world, rank, rows_per_rank,
+    [base pointers]): gsb_backward_batch_peer -- the gradients are ADDED into the owner ranks' buffers (fused reduce-scatter;
+    gaussian_renderer.peer.PeerGradientBucket drives the protocol around it)."""
     dev = means3D.device
     V, P = pack["V"], int(means3D.shape[0])
     with _device_ctx(dev):
@@ -543,7 +594,15 @@ def _backward_batch_impl(pack, settings_list, means3D, sh, opacities, scales, ro
         g.dL_dscales, g.dL_drotations = _ptr(grads.get("scales")), _ptr(grads.get("rotations"))
         stream = _current_stream(dev)
         arena = _Arena(dev, stream)
-        if n_chunks > 1 or on_chunk is not None:
+        if peers is not None:
+            world, rank, rows_per_rank, bases = peers
+            pt = _PeerTable()
+            pt.world, pt.rank, pt.rows_per_rank, pt.reserved = int(world), int(rank), int(rows_per_rank), 0
+            pt.base = (c_void_p * 16)(*([int(b) for b in bases] + [None] * (16 - len(bases))))
+            rc = _C.gsb_backward_batch_peer(V, cs, byref(ci), pack["states"], out_color.data_ptr(), out_invdepth.data_ptr(),
+                                            grad_color.data_ptr(), _ptr(grad_invdepth), byref(g), byref(pt), arena.cb, None, stream)
+            _check(rc, arena)
+        elif n_chunks > 1 or on_chunk is not None:
             err = []
 
             def _cb(_ctx, chunk, p0, p1):

@@ -184,7 +184,7 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
                           scaling_modifier: float = 1.0, densify_stats: Optional[dict] = None,
                           keep_images: bool = False, loss_returns_grad: bool = False, batched: bool = True,
                           overwrite: bool = False, capacity: Optional[AsyncCapacity] = None, grad_chunks: int = 1,
-                          on_grad_chunk=None) -> dict:
+                          on_grad_chunk=None, peers=None) -> dict:
     """Fused view-batch training step: forward + loss + backward for every camera, with the per-gaussian
     gradients of ALL views summed in place.
 
@@ -272,7 +272,8 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
             last_chunk = c0 + _dgr.MAX_BATCH_VIEWS >= len(cams_all)     # gradients are final only after the last view chunk
             _dgr._backward_batch_impl(pack, rss, c["means3D"], c["shs"], c["opacities"], c["scales"], c["rotations"], color,
                                       invdepth, g_color, g_depth, vg, accumulate=not (overwrite and c0 == 0),
-                                      n_chunks=grad_chunks if last_chunk else 1, on_chunk=on_grad_chunk if last_chunk else None)
+                                      n_chunks=grad_chunks if last_chunk else 1, on_chunk=on_grad_chunk if last_chunk else None,
+                                      peers=peers)
             torch.maximum(radii_max, radii.max(dim=0).values, out=radii_max)
             if densify_stats is not None:
                 vis = radii > 0                                               # [V,P]

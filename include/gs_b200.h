@@ -183,6 +183,37 @@ int32_t gsb_backward_batch_chunked(int32_t V, const GsbSettings *settings, const
                                    int32_t n_chunks, gsb_chunk_fn on_chunk, void *chunk_ctx, gsb_alloc_fn alloc,
                                    void *alloc_ctx, void *cuda_stream);
 
+/* FUSED REDUCE-SCATTER of the data-parallel gradients (one process per GPU of a node).  gsb_backward_batch whose last kernel does
+ * not write this rank's gradient buffer but ADDS every row into the buffer of the rank that OWNS the row -- over NVLink, as TMA
+ * bulk reduce-adds (one per 192-byte SH row, four per 128-gaussian block for the narrow tensors) issued while the kernel computes.
+ * Rank r owns gaussians [r * rows_per_rank, (r + 1) * rows_per_rank); rows_per_rank is a multiple of 128 and
+ * world * rows_per_rank >= P; every gradient tensor has world * rows_per_rank rows (the padding rows receive zeros).
+ * `grads` points into THIS rank's buffer; base[r] is rank r's buffer as mapped into this process (gsb_peer_open), base[rank] the
+ * local one, all with the same internal layout.  Protocol (caller): owners zero their rows; barrier; this call on every rank;
+ * barrier; the owned rows now hold the sum over ranks -- all-gather them (or step the owned slice and all-gather parameters).
+ * dL_dmeans2D (per-view, not reduced) is written locally as usual.  Needs option pre_tma (default) and SH tensors. */
+typedef struct GsbPeerTable {
+    int32_t world, rank;
+    int32_t rows_per_rank;
+    int32_t reserved;
+    void *base[16];
+} GsbPeerTable;
+int32_t gsb_backward_batch_peer(int32_t V, const GsbSettings *settings, const GsbInputs *in, const GsbState *states,
+                                const float *out_color, const float *out_invdepth, const float *dL_dcolor,
+                                const float *dL_dinvdepth, const GsbGrads *grads, const GsbPeerTable *peers,
+                                gsb_alloc_fn alloc, void *alloc_ctx, void *cuda_stream);
+
+/* Lets kernels launched on the CURRENT device dereference pointers into `peer_device`'s memory (cudaDeviceEnablePeerAccess;
+ * already-enabled is not an error).  Needed once per peer before gsb_backward_batch_peer is given peer-mapped buffers. */
+int32_t gsb_enable_peer_access(int32_t peer_device);
+/* Peer-visible device memory for the ranks of one node (one process per GPU).  gsb_peer_alloc: cudaMalloc (zero-filled) on the
+ * current device + its 64-byte CUDA-IPC handle, which the caller ships to the other processes by any means; gsb_peer_open: maps
+ * another process's allocation into this one, on the current device (the device whose kernels will use it); _close / _free undo. */
+int32_t gsb_peer_alloc(size_t bytes, void **ptr, uint8_t *handle64);
+int32_t gsb_peer_open(const uint8_t *handle64, void **ptr);
+int32_t gsb_peer_close(void *ptr);
+int32_t gsb_peer_free(void *ptr);
+
 /* Frustum test only (GaussianRasterizer.markVisible): present[i] = 1 if view-space z > 0.2 */
 int32_t gsb_mark_visible(int32_t P, const float *means3D, const float *viewmatrix,
                          const float *projmatrix, uint8_t *present, void *cuda_stream);

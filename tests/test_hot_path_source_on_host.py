@@ -304,3 +304,42 @@ def test_state_buffers_are_freed_by_refcount_not_by_the_garbage_collector(on_hos
         assert all(r() is None for r in refs), "forward state survived its last reference: a cycle keeps it alive"
     finally:
         gc.enable()
+
+
+def test_fused_reduce_scatter_source(on_host):
+    """gsb_backward_batch_peer (csrc/preprocess.cu, peer output path): two "ranks" played one after the other in this process,
+    each adding the gradients of ITS views into the buffer of the rank that owns the row (rank 0: gaussians [0, 256), rank 1:
+    [256, 512) of a 300-gaussian cloud -- the padding rows receive zeros).  The owned rows, put side by side, equal the gradient
+    of all views computed the ordinary way.  (On the host build the bulk reduce-adds are plain loops: layout, ownership and
+    panel indexing are what is checked here; NVLink and the IPC mappings by the -m gpu two-GPU test.)"""
+    import bench
+    from gaussian_renderer import GradientBucket, render_views_backward
+    scene, cams, gts, bg = _batch_inputs(n=300, views=4)
+    P, rows, world = 300, 256, 2
+    width = {"means3D": 3, "opacities": 1, "scales": 3, "rotations": 4, "shs": 48}
+    offset, off = {}, 0
+    for k, w in width.items():
+        offset[k] = off
+        off += rows * world * w
+    bufs = [torch.zeros(off), torch.zeros(off)]
+    loss = lambda mine: (lambda img, d, i: (img - gts[mine[i]]).abs().mean() + 0.1 * d.mean())
+    for r in range(world):
+        mine = [v for v in range(4) if v % world == r]
+        pc = bench.BenchGaussians(scene, 3, "cpu")
+        named = {"means3D": pc._xyz, "shs": pc._shs, "opacities": pc._opacity, "scales": pc._scaling, "rotations": pc._rotation}
+        for k, p in named.items():
+            p.grad = bufs[r][offset[k]:offset[k] + rows * world * width[k]].view(rows * world, width[k])[:P].view_as(p)
+        render_views_backward([cams[v] for v in mine], pc, bench.Pipe(), bg, loss(mine),
+                              peers=(world, r, rows, [b.data_ptr() for b in bufs]))
+    # reference: all four views, ordinary path
+    pc = bench.BenchGaussians(scene, 3, "cpu")
+    bucket = GradientBucket(pc.parameters())
+    render_views_backward(cams, pc, bench.Pipe(), bg, loss(list(range(4))))
+    ref = {"means3D": pc._xyz.grad, "shs": pc._shs.grad, "opacities": pc._opacity.grad, "scales": pc._scaling.grad, "rotations": pc._rotation.grad}
+    for k, w in width.items():
+        full = [b[offset[k]:offset[k] + rows * world * w].view(rows * world, w) for b in bufs]
+        got = torch.cat((full[0][:rows], full[1][rows:P]))                       # owned rows side by side
+        want = ref[k].reshape(P, w)
+        assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max()) + 1e-12, k
+        assert float(full[0][rows:].abs().max()) == 0.0 and float(full[1][:rows].abs().max()) == 0.0      # nobody touched foreign rows
+        assert float(full[1][P:].abs().max()) == 0.0                                                         # padding rows: zeros

@@ -203,10 +203,33 @@ def _two_gpu_worker(rank, world, port, paths, out_path):
         one = local(rank)
         one.all_reduce()
         err_single_collective = float((one.flat - total).abs().max() / total.abs().max())
+        # fused reduce-scatter: the gradient kernel adds every row into its owner's buffer over NVLink (peer-mapped memory),
+        # then a barrier and an in-place all-gather; three steps so that both halves of the double buffer are used twice
+        from gaussian_renderer.peer import PeerGradientBucket
+        pc = bench.BenchGaussians(scene, 3, dev)
+        named = {"means3D": pc._xyz, "shs": pc._shs, "opacities": pc._opacity, "scales": pc._scaling, "rotations": pc._rotation}
+        pb = PeerGradientBucket(named)
+        errs_peer = []
+        for _step in range(4):
+            pb.begin_step()
+            render_views_backward(cams_of(rank), pc, bench.Pipe(), bg, lambda img, d, i: (img - gts[i]).abs().mean(), capacity=cap,
+                                  peers=pb.table())
+            pb.finish()
+            flat = torch.cat([pc._xyz.grad.reshape(-1), pc._shs.grad.reshape(-1), pc._opacity.grad.reshape(-1),
+                              pc._scaling.grad.reshape(-1), pc._rotation.grad.reshape(-1)])
+            # `total` was laid out by GradientBucket: narrow parameters first, SH last -- compare tensor by tensor instead
+            ref_pc = bench.BenchGaussians(scene, 3, dev)
+            ref_b = GradientBucket(ref_pc.parameters())
+            ref_b.flat.copy_(total)
+            ref_flat = torch.cat([ref_pc._xyz.grad.reshape(-1), ref_pc._shs.grad.reshape(-1), ref_pc._opacity.grad.reshape(-1),
+                                  ref_pc._scaling.grad.reshape(-1), ref_pc._rotation.grad.reshape(-1)])
+            errs_peer.append(float((flat - ref_flat).abs().max() / ref_flat.abs().max()))
+        torch.cuda.synchronize()
+        pb.close()
         if rank == 0:
             with open(out_path, "w") as f:
-                f.write(f"{err} {err_single_collective} {len(pending)}")
-        assert err <= 1e-4 and err_single_collective <= 1e-4
+                f.write(f"{err} {err_single_collective} {len(pending)} {max(errs_peer)}")
+        assert err <= 1e-4 and err_single_collective <= 1e-4 and max(errs_peer) <= 1e-4, (err, err_single_collective, errs_peer)
     finally:
         dist.destroy_process_group()
 
@@ -215,15 +238,17 @@ def _two_gpu_worker(rank, world, port, paths, out_path):
 def test_two_gpu_chunked_all_reduce_equals_single_process_sum(tmp_path):
     """On real hardware: two ranks, three views each, the sync-free step with the gradient kernel in four chunks, each chunk's
     SH rows all-reduced while the next computes, one collective for the narrow parameters at the end -- the reduced bucket equals the sum of both ranks'
-    buckets computed in one process, and equals the single all-reduce of the whole bucket."""
+    buckets computed in one process, and equals the single all-reduce of the whole bucket.  Then the FUSED reduce-scatter
+    (gsb_backward_batch_peer: TMA bulk reduce-adds into the owner's peer-mapped buffer, barrier, in-place all-gather) gives the
+    same sums on both halves of its double buffer."""
     import torch.multiprocessing as mp
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     paths = [root, os.path.join(root, "gaussian-splatting_b200"), os.path.join(root, "tests")]
     out = str(tmp_path / "two_gpu.txt")
     mp.spawn(_two_gpu_worker, args=(2, 29500 + os.getpid() % 2000, paths, out), nprocs=2, join=True)
-    err, err1, n = open(out).read().split()
-    print("two-GPU chunked reduction: rel err", err, "single collective", err1, "handles", n)
-    assert float(err) <= 1e-4 and int(n) == 5
+    err, err1, n, err_peer = open(out).read().split()
+    print("two-GPU chunked reduction: rel err", err, "single collective", err1, "handles", n, "| fused reduce-scatter over peer memory:", err_peer)
+    assert float(err) <= 1e-4 and int(n) == 5 and float(err_peer) <= 1e-4
 
 
 def test_training_state_at_a_million_gaussians_through_two_densifications():
