@@ -443,8 +443,8 @@ def test_fused_photometric_loss_and_fused_ssim(shape, golden):
     assert (ga.cpu() - ga_ref).abs().max().item() <= 1e-4 * ga_ref.abs().max().item()
 
 
-@pytest.mark.parametrize("opts", [{"sort_small": -1}, {"sort_small": 1}, {"pre_tma": 1}, {"tile_order": 1}],
-                         ids=["sort_16_keys_per_thread", "sort_4_keys_per_thread", "pre_tma", "tile_order"])
+@pytest.mark.parametrize("opts", [{"sort_small": -1}, {"sort_small": 1}, {"pre_tma": 0}, {"tile_order": 0}],
+                         ids=["sort_16_keys_per_thread", "sort_4_keys_per_thread", "pre_tma_off", "tile_order_off"])
 def test_ab_options_keep_results(opts):
     """The tuning knobs change neither the image nor, beyond the order of float atomics, the gradients; single-view and
     view-batch path."""
@@ -468,7 +468,7 @@ def test_ab_options_keep_results(opts):
         return out["losses"].cpu().numpy(), bucket.flat.cpu().numpy()
 
     base, (bl, bg_) = U.run_cuda(args, cam, wc, wd), batch()
-    defaults = {"sort_small": 0, "pre_tma": 0, "tile_order": 0}
+    defaults = {"sort_small": 0, "pre_tma": 1, "tile_order": 1}
     try:
         for k, v in opts.items():
             dgr.set_option(k, v)

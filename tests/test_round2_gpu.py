@@ -63,7 +63,7 @@ def test_chunked_gradient_kernel_and_tile_order():
     scene, cams, gts, bg = _batch_inputs(30000, 4, 320, 200, dev, seed=52)
     l0, g0, im0 = _batch_step(scene, cams, gts, bg, dev, overwrite=True)
     seen = []
-    dgr.set_option("tile_order", 1)
+    dgr.set_option("tile_order", 0)          # default is on (heavy tiles first): the A/B is "off"
     try:
         l1, g1, im1 = _batch_step(scene, cams, gts, bg, dev, overwrite=True, grad_chunks=4,
                                   on_grad_chunk=lambda c, a, b: seen.append((c, a, b)))
@@ -73,7 +73,7 @@ def test_chunked_gradient_kernel_and_tile_order():
         wc = torch.randn(3, 120, 200, generator=gen).numpy()
         single = U.run_cuda(U.make_args(sc1, "sh"), cam, wc, None)
     finally:
-        dgr.set_option("tile_order", 0)
+        dgr.set_option("tile_order", 1)
     assert [c for c, _, _ in seen] == [0, 1, 2, 3] and seen[0][1] == 0 and seen[-1][2] == 30000
     assert all(seen[i][2] == seen[i + 1][1] for i in range(3))
     for a, b in zip(im0, im1):

@@ -11,7 +11,7 @@ GS_OPTS=pre_tma=1 $B > $O/r2b_bench_pre_tma.json 2> $O/r2b_bench_pre_tma.err
 GS_OPTS=tile_order=1 $B > $O/r2b_bench_tile_order.json 2> $O/r2b_bench_tile_order.err
 GS_OPTS=pre_tma=1,tile_order=1 $B > $O/r2b_bench_both.json 2> $O/r2b_bench_both.err
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_round2_gpu.py -q -k "sync_free or chunked" > $O/r2b_memcheck.log 2>&1; echo "memcheck rc=$?" >> $O/r2b_memcheck.log
-GS_OPTS=pre_tma=1 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_parity_gpu.py -q -k "pre_tma" > $O/r2b_memcheck_tma.log 2>&1; echo "memcheck rc=$?" >> $O/r2b_memcheck_tma.log
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_parity_gpu.py -q -k "tile_order_off or sort_4" > $O/r2b_memcheck_tma.log 2>&1; echo "memcheck rc=$?" >> $O/r2b_memcheck_tma.log
 # launch list of two batched steps (cold-cache, serialised: shares only)
 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 80 --csv --log-file $O/r2b_launches.csv python tools/profile_one.py 3 > $O/r2b_ncu_a.log 2>&1
 # full captures: blend kernels + both preprocess kernels of the batched step
