@@ -381,29 +381,60 @@ class GaussianModel:
         return self
 
     # ---- checkpoint (capture :63-76 / restore :78-99) -----------------------------------------------------------------
-    def capture(self):
-        return dict(active_sh_degree=self.active_sh_degree, max_sh_degree=self.max_sh_degree, P=self.P, store=self.store.clone(),
-                    exp_avg=self.exp_avg.clone(), exp_avg_sq=self.exp_avg_sq.clone(), max_radii2D=self.max_radii2D.clone(),
-                    xyz_gradient_accum=None if self.xyz_gradient_accum is None else self.xyz_gradient_accum.clone(),
-                    denom=None if self.denom is None else self.denom.clone(), step_count=self.step_count, lr=dict(self.lr),
-                    group_steps=dict(self.group_steps), densify_seed=self.densify_seed, densify_calls=self._densify_calls,
-                    xyz_sched=self._xyz_sched, percent_dense=self.percent_dense, spatial_lr_scale=self.spatial_lr_scale)
+    def _group_views(self, buf):
+        """A flat buffer of the store's layout as the reference's six tensors."""
+        P, M, o = self.P, self.sh_coeffs, store_offsets(self.P, self.sh_coeffs)
+        feat = buf[o["features"]:o["opacity"]].view(P, M, 3)
+        return {"xyz": buf[:3 * P].view(P, 3), "f_dc": feat[:, :1], "f_rest": feat[:, 1:], "opacity": buf[o["opacity"]:o["scaling"]].view(P, 1),
+                "scaling": buf[o["scaling"]:o["rotation"]].view(P, 3), "rotation": buf[o["rotation"]:].view(P, 4)}
 
-    def restore(self, state: dict):
-        if int(state["max_sh_degree"]) != self.max_sh_degree:
+    def capture(self):
+        """The reference's checkpoint tuple (gaussian_model.py:63-76), optimizer state in ``torch.optim.Adam.state_dict()``
+        form (six single-parameter groups in the reference's order, per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq``), so
+        that ``torch.save((gaussians.capture(), iteration), path)`` of train.py:212 writes a file the reference can load."""
+        raw, m, v = self._group_views(self.store), self._group_views(self.exp_avg), self._group_views(self.exp_avg_sq)
+        c = lambda t: t.detach().clone().contiguous()
+        state = {k: {"step": torch.tensor(float(self.group_steps[n])), "exp_avg": c(m[n]), "exp_avg_sq": c(v[n])}
+                 for k, n in enumerate(GROUPS) if self.group_steps[n] > 0}
+        groups = [{"lr": self.lr.get(n, 0.0), "name": n, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                   "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None, "params": [k]}
+                  for k, n in enumerate(GROUPS)]
+        return (self.active_sh_degree, c(raw["xyz"]), c(raw["f_dc"]), c(raw["f_rest"]), c(raw["scaling"]), c(raw["rotation"]),
+                c(raw["opacity"]), self.max_radii2D.clone(), None if self.xyz_gradient_accum is None else self.xyz_gradient_accum.clone(),
+                None if self.denom is None else self.denom.clone(), {"state": state, "param_groups": groups}, self.spatial_lr_scale)
+
+    def restore(self, model_args, training_args=None):
+        """``restore(model_args, training_args)`` of the reference (gaussian_model.py:78-99): ``model_args`` is the tuple written by
+        the reference's or this class's ``capture()`` -- the per-group Adam state (moments and step counts) goes into the flat
+        moments.  The per-image exposure parameters of the reference are not part of this model."""
+        if not isinstance(model_args, (tuple, list)) or len(model_args) != 12:
+            raise ValueError("restore: expected the 12-tuple of GaussianModel.capture()")
+        (active, xyz, f_dc, f_rest, scaling, rotation, opacity, max_radii2D, grad_accum, denom, opt_dict, spatial) = model_args
+        if int(f_rest.shape[1]) + 1 != self.sh_coeffs:
             raise ValueError("checkpoint was written with another SH degree")
-        self.active_sh_degree = int(state["active_sh_degree"])
-        self._allocate(int(state["P"]), state["store"].device)
-        self.store.copy_(state["store"])
-        self.exp_avg.copy_(state["exp_avg"])
-        self.exp_avg_sq.copy_(state["exp_avg_sq"])
-        self.max_radii2D = state["max_radii2D"].clone()
-        self.xyz_gradient_accum = None if state["xyz_gradient_accum"] is None else state["xyz_gradient_accum"].clone()
-        self.denom = None if state["denom"] is None else state["denom"].clone()
-        self.step_count, self.lr, self._xyz_sched = int(state["step_count"]), dict(state["lr"]), state["xyz_sched"]
-        self.group_steps = dict(state.get("group_steps") or {n: self.step_count for n in GROUPS})
-        self.densify_seed, self._densify_calls = int(state.get("densify_seed", 0)), int(state.get("densify_calls", 0))
+        dev = xyz.device
+        t = lambda x: x.detach().to(dev, torch.float32)
+        self.create_from_tensors(t(xyz), t(f_dc), t(f_rest), t(scaling), t(rotation), t(opacity), float(spatial))
+        self.active_sh_degree = int(active)
+        if training_args is not None:
+            self.training_setup(training_args)
+        self.max_radii2D = max_radii2D.detach().to(dev).clone()
+        self.xyz_gradient_accum = None if grad_accum is None else grad_accum.detach().to(dev).clone()
+        self.denom = None if denom is None else denom.detach().to(dev).clone()
+        m, v = self._group_views(self.exp_avg), self._group_views(self.exp_avg_sq)
+        names = [g.get("name") for g in opt_dict.get("param_groups", [])]
+        for k, n in enumerate(GROUPS):
+            idx = opt_dict["param_groups"][names.index(n)]["params"][0] if n in names else k
+            st = opt_dict.get("state", {}).get(idx)
+            if st is None:
+                m[n].zero_(); v[n].zero_(); self.group_steps[n] = 0
+                continue
+            m[n].copy_(st["exp_avg"].to(dev).view_as(m[n]))
+            v[n].copy_(st["exp_avg_sq"].to(dev).view_as(v[n]))
+            self.group_steps[n] = int(float(st["step"]))
+        self.step_count = max(self.group_steps.values())
         self._skip_next = set()
-        self.percent_dense, self.spatial_lr_scale = float(state["percent_dense"]), float(state["spatial_lr_scale"])
-        self._reactivate()
+        for g in opt_dict.get("param_groups", []):
+            if g.get("name") in self.lr:
+                self.lr[g["name"]] = float(g["lr"])
         return self

@@ -150,3 +150,47 @@ def test_radix_sort_source_is_stable(emul, n, bits, V, small):
         order = np.argsort(keys[seg] & mask, kind="stable")
         assert np.array_equal(k[seg], keys[seg][order]), view
         assert np.array_equal(v_[seg], vals[seg][order]), view
+
+
+def test_checkpoint_contract_of_the_reference(on_host):
+    """capture() / restore(model_args, training_args) speak the reference's checkpoint format (gaussian_model.py:63-99): the tuple
+    written by this class reloads into it bit for bit (including per-group step counts), and a tuple whose optimizer part is a REAL
+    torch.optim.Adam.state_dict() -- what the reference's own capture() writes -- loads into the flat moments."""
+    from oracle.model_oracle import ModelOracle
+    g = torch.Generator().manual_seed(9)
+    P = 70
+    raw = {"xyz": torch.randn(P, 3, generator=g), "f_dc": torch.randn(P, 1, 3, generator=g), "f_rest": torch.randn(P, 15, 3, generator=g) * 0.1,
+           "opacity": torch.randn(P, 1, generator=g), "scaling": torch.randn(P, 3, generator=g) - 3, "rotation": torch.randn(P, 4, generator=g)}
+    opt = dict(position_lr_init=0.00016, position_lr_final=0.0000016, position_lr_delay_mult=0.01, position_lr_max_steps=30000,
+               feature_lr=0.0025, opacity_lr=0.025, scaling_lr=0.005, rotation_lr=0.001, percent_dense=0.01)
+    args = SimpleNamespace(**opt)
+    m = GaussianModel(3).create_from_tensors(raw["xyz"], raw["f_dc"], raw["f_rest"], raw["scaling"], raw["rotation"], raw["opacity"], 2.0)
+    m.training_setup(args)
+    for it in (1, 2, 3):
+        m.update_learning_rate(it)
+        m.grad.copy_(torch.randn(m.grad.shape, generator=g) * 1e-3)
+        m.gradients_ready()
+        if it == 3:
+            m.reset_opacity()                      # opacity misses this step: its step count lags
+        m.optimizer_step()
+    ck = m.capture()
+    assert len(ck) == 12 and set(ck[10]) == {"state", "param_groups"} and [gr["name"] for gr in ck[10]["param_groups"]] == list(GROUPS)
+    m2 = GaussianModel(3).restore(ck, args)
+    assert m2.group_steps == m.group_steps == {"xyz": 3, "f_dc": 3, "f_rest": 3, "opacity": 2, "scaling": 3, "rotation": 3}
+    assert torch.equal(m2.store, m.store) and torch.equal(m2.exp_avg, m.exp_avg) and torch.equal(m2.exp_avg_sq, m.exp_avg_sq)
+    assert torch.equal(m2.act, m.act) and m2.active_sh_degree == m.active_sh_degree and m2.spatial_lr_scale == 2.0
+    # a checkpoint as the reference writes it: parameters + a real Adam state_dict
+    ref = ModelOracle(raw["xyz"], raw["f_dc"], raw["f_rest"], raw["opacity"], raw["scaling"], raw["rotation"], opt, 2.0)
+    for it in (1, 2):
+        ref.step(it, {"xyz": torch.randn(P, 3, generator=g) * 1e-3, "features": torch.randn(P, 16, 3, generator=g) * 1e-3,
+                      "opacity": torch.randn(P, 1, generator=g) * 1e-3, "scaling": torch.randn(P, 3, generator=g) * 1e-3,
+                      "rotation": torch.randn(P, 4, generator=g) * 1e-3})
+    p = {n: ref.p[n].detach() for n in GROUPS}
+    tup = (2, p["xyz"], p["f_dc"], p["f_rest"], p["scaling"], p["rotation"], p["opacity"], torch.zeros(P), torch.zeros(P, 1), torch.zeros(P, 1),
+           ref.adam.state_dict(), 2.0)
+    m3 = GaussianModel(3).restore(tup, args)
+    mom = ref.moments()
+    views_m, views_v = m3._group_views(m3.exp_avg), m3._group_views(m3.exp_avg_sq)
+    for n in GROUPS:
+        assert torch.equal(views_m[n], mom[n]["m"]) and torch.equal(views_v[n], mom[n]["v"]) and m3.group_steps[n] == 2
+    assert m3.active_sh_degree == 2 and torch.equal(m3._xyz, p["xyz"])
