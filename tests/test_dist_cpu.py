@@ -136,7 +136,7 @@ def _train_worker(rank, world, port, q, lib):
             m.training_setup(SimpleNamespace(position_lr_init=0.00016, position_lr_final=0.0000016, position_lr_delay_mult=0.01,
                                              position_lr_max_steps=30000, feature_lr=0.0025, opacity_lr=0.025, scaling_lr=0.005,
                                              rotation_lr=0.001, percent_dense=0.01))
-            W, H, NV = 48, 32, 4
+            W, H, NV = 48, 32, 2
             cams = [bench.BenchCamera(W, H, math.radians(60.0), *bench.view_pose(i, 3.0), "cpu") for i in range(NV)]
             gts = [torch.rand(3, H, W, generator=torch.Generator().manual_seed(100 + i)) for i in range(NV)]
             mine = shard_views(list(range(NV)), rank, world)

@@ -61,7 +61,7 @@ def test_large_and_anisotropic_gaussians(on_host):
 
 def test_many_gaussians_per_tile(on_host):
     """More than one 128-record staging round in most tiles."""
-    scene = TO.make_scene(700, seed=36, log_scale_mean=-2.0)
+    scene = TO.make_scene(480, seed=36, log_scale_mean=-2.0)
     scene["opacities"] = scene["opacities"] * 0.15                      # keep transmittance alive deep into the lists
     _check(scene, TO.make_camera(48, 32, sh_degree=1), "sh")
 
@@ -245,13 +245,14 @@ def test_sync_free_chunked_view_batch_step(on_host):
     assert not small.check() and small.capacity >= seen and small.observed_max() == 0
 
 
-@pytest.mark.parametrize("deg", [1, 3])
-def test_scalar_row_path_source(on_host, deg):
-    """Option pre_tma switched OFF: the SH rows staged with 128-bit / scalar loads at an odd word stride instead of one TMA bulk
-    copy per row and float4 access (the default, which every other test of this file exercises).  Single view against the oracle."""
+@pytest.mark.parametrize("deg,tma", [(1, 1), (3, 0)])
+def test_sh_row_layouts_source(on_host, deg, tma):
+    """The two shared-memory layouts of the SH rows (csrc/preprocess.cu): TMA bulk copies + float4 access with a 12-float row
+    (SH degree 1 tensors: three 16-byte units per row; every other test of this file runs the 48-float rows), and option
+    pre_tma switched OFF (128-bit / scalar staging at an odd word stride).  Single view against the oracle."""
     dgr = on_host
     scene = TO.make_scene(260, seed=40 + deg, sh_coeffs=(deg + 1) ** 2, log_scale_mean=-2.4)
-    dgr.set_option("pre_tma", 0)
+    dgr.set_option("pre_tma", tma)
     try:
         _check(scene, TO.make_camera(48, 32, sh_degree=deg, bg=(0.1, 0.3, 0.6)), "sh")
     finally:
@@ -288,7 +289,7 @@ def test_fused_reduce_scatter_source(on_host):
     panel indexing are what is checked here; NVLink and the IPC mappings by the -m gpu two-GPU test.)"""
     import bench
     from gaussian_renderer import GradientBucket, render_views_backward
-    scene, cams, gts, bg = _batch_inputs(n=300, views=4)
+    scene, cams, gts, bg = _batch_inputs(n=300, views=2)
     P, rows, world = 300, 256, 2
     width = {"means3D": 3, "opacities": 1, "scales": 3, "rotations": 4, "shs": 48}
     offset, off = {}, 0
@@ -298,7 +299,7 @@ def test_fused_reduce_scatter_source(on_host):
     bufs = [torch.zeros(off), torch.zeros(off)]
     loss = lambda mine: (lambda img, d, i: (img - gts[mine[i]]).abs().mean() + 0.1 * d.mean())
     for r in range(world):
-        mine = [v for v in range(4) if v % world == r]
+        mine = [v for v in range(2) if v % world == r]
         pc = bench.BenchGaussians(scene, 3, "cpu")
         named = {"means3D": pc._xyz, "shs": pc._shs, "opacities": pc._opacity, "scales": pc._scaling, "rotations": pc._rotation}
         for k, p in named.items():
@@ -308,7 +309,7 @@ def test_fused_reduce_scatter_source(on_host):
     # reference: all four views, ordinary path
     pc = bench.BenchGaussians(scene, 3, "cpu")
     bucket = GradientBucket(pc.parameters())
-    render_views_backward(cams, pc, bench.Pipe(), bg, loss(list(range(4))))
+    render_views_backward(cams, pc, bench.Pipe(), bg, loss(list(range(2))))
     ref = {"means3D": pc._xyz.grad, "shs": pc._shs.grad, "opacities": pc._opacity.grad, "scales": pc._scaling.grad, "rotations": pc._rotation.grad}
     for k, w in width.items():
         full = [b[offset[k]:offset[k] + rows * world * w].view(rows * world, w) for b in bufs]

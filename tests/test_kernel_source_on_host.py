@@ -53,8 +53,9 @@ def test_scan_source_multi_tile(emul):
     assert emul.emul_exclusive_scan(x.ctypes.data, out.ctypes.data, n, partials.ctypes.data, total.ctypes.data) == 0
     ref = np.concatenate(([0], np.cumsum(x, dtype=np.uint64)[:-1])).astype(np.uint32)
     assert np.array_equal(out, ref) and int(total[0]) == int(x.sum())
-    assert emul.emul_exclusive_scan(x.ctypes.data, x.ctypes.data, n, partials.ctypes.data, total.ctypes.data) == 0     # in place
-    assert np.array_equal(x, ref)
+    small = x[:5000].copy()                                          # in place, on a prefix (one more full pass would double the test)
+    assert emul.emul_exclusive_scan(small.ctypes.data, small.ctypes.data, 5000, partials.ctypes.data, total.ctypes.data) == 0
+    assert np.array_equal(small, ref[:5000])
 
 
 def test_kernel_sources_replay_reference_fixture(on_host):
