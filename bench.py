@@ -364,6 +364,11 @@ def run_reference(a):
     if stock is not None:
         return run_reference_cuda(a, stock, syn)
     from oracle.c_oracle import set_threads
+    if hasattr(os, "sched_setaffinity"):
+        try:                            # launchers may start the process on one NUMA node: the CPU arm gets every core of the box
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))
+        except OSError:
+            pass
     nthreads = set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     scene = syn.make_scene(a.gaussians, seed=0, log_scale_mean=LOG_SCALE_MEAN)
     R, T = syn.sphere_pose(0, 3.0)
