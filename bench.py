@@ -487,8 +487,11 @@ def main():
             bucket.zero_()
         pending = []
         if a.api == "views":
-            def loss_fn(img, _invdepth, i):
-                fused = dgr.l1_loss_and_grad if a.loss == "l1" else (lambda x, y: dgr.photometric_loss_and_grad(x, y, 0.2)[:2])
+            def loss_fn(img, _invdepth, i, grad_out=None):      # the gradient goes straight into the batch's buffer (no copy)
+                if a.loss == "l1":
+                    fused = lambda x, y: dgr.l1_loss_and_grad(x, y, grad_out=grad_out)
+                else:
+                    fused = lambda x, y: dgr.photometric_loss_and_grad(x, y, 0.2, grad_out=grad_out)[:2]
                 if host_inputs:
                     torch.cuda.current_stream(dev).wait_event(copied[i % NS])
                     res = fused(img, stage[i % NS])      # fused loss (train.py:120-126) + gradient

@@ -222,13 +222,17 @@ def state_views(pack: dict, height: int, width: int):
     return dict(final_T=final_T, n_contrib=n_contrib, point_list=point_list, ranges=ranges)
 
 
-def l1_loss_and_grad(image: torch.Tensor, target: torch.Tensor, loss_accum: Optional[torch.Tensor] = None):
+def l1_loss_and_grad(image: torch.Tensor, target: torch.Tensor, loss_accum: Optional[torch.Tensor] = None,
+                     grad_out: Optional[torch.Tensor] = None):
     """mean |clamp(image,0,1) - target| and its gradient w.r.t. `image`, in one kernel.  Returns (loss, grad);
-    `loss` is `loss_accum` (a 1-element float32 tensor that is ADDED to) or a fresh scalar tensor."""
+    `loss` is `loss_accum` (a 1-element float32 tensor that is ADDED to) or a fresh scalar tensor; the gradient is written
+    into `grad_out` when given (contiguous float32 of the image's shape: e.g. the slot render_views_backward offers)."""
     _require_cuda(image)
     img, gt = _f32c(image), _f32c(target)
     n = img.numel()
-    grad = torch.empty_like(img)
+    if grad_out is not None and (grad_out.dtype != torch.float32 or not grad_out.is_contiguous() or grad_out.shape != img.shape):
+        grad_out = None
+    grad = grad_out if grad_out is not None else torch.empty_like(img)
     if loss_accum is None:
         loss_accum = torch.zeros(1, dtype=torch.float32, device=img.device)
     with _device_ctx(img.device):
@@ -238,7 +242,8 @@ def l1_loss_and_grad(image: torch.Tensor, target: torch.Tensor, loss_accum: Opti
     return loss_accum, grad
 
 
-def photometric_loss_and_grad(image: torch.Tensor, target: torch.Tensor, lambda_dssim: float = 0.2, clamp_input: bool = True):
+def photometric_loss_and_grad(image: torch.Tensor, target: torch.Tensor, lambda_dssim: float = 0.2, clamp_input: bool = True,
+                              grad_out: Optional[torch.Tensor] = None):
     """The reference training step's loss (train.py:120-126) fused with its gradient:
     ``(1 - lambda) * mean|x - y| + lambda * (1 - SSIM(x, y))`` with ``x = clamp(image, 0, 1)`` (render()'s clamp and its
     gradient mask; ``clamp_input=False``: x = image); image / target [C,H,W].
@@ -246,7 +251,9 @@ def photometric_loss_and_grad(image: torch.Tensor, target: torch.Tensor, lambda_
     _require_cuda(image)
     img, gt = _f32c(image), _f32c(target)
     C, H, W = (int(v) for v in img.shape[-3:])
-    grad = torch.empty_like(img)
+    if grad_out is not None and (grad_out.dtype != torch.float32 or not grad_out.is_contiguous() or grad_out.shape != img.shape):
+        grad_out = None
+    grad = grad_out if grad_out is not None else torch.empty_like(img)
     # accumulators [loss - lambda, sum |x - y|, sum SSIM]: created on the device (a host-side tensor would be a pageable copy,
     # i.e. a host synchronisation in every training step)
     acc = torch.zeros(3, dtype=torch.float32, device=img.device)

@@ -197,7 +197,8 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
 
     ``loss_fn(image[3,H,W] (clamped to [0,1] like render() does), invdepth[1,H,W], view_index) -> scalar``, or,
     with ``loss_returns_grad=True``, ``loss_fn(raw_image, invdepth, view_index) -> (loss, dL/d raw_image[, dL/d invdepth])``
-    for a loss that brings its own gradient (e.g. ``diff_gaussian_rasterization.l1_loss_and_grad``); no autograd then.
+    for a loss that brings its own gradient (e.g. ``diff_gaussian_rasterization.l1_loss_and_grad``); no autograd then.  If such
+    a loss_fn has a ``grad_out`` parameter it is handed the slot of the batch's gradient buffer to write into (no copy).
     Returns {"losses": [V] tensor, "radii_max": [P] int32, "num_rendered": per-view instance counts, "images": list (if keep_images)}.
 
     ``overwrite=True``: the gradient buffers are WRITTEN by the first chunk of views instead of added to, so the
@@ -208,6 +209,13 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
     depth sorts / scans / tile sorts of the views run as single batched launches, the summed gradient is written
     once, and there is ONE host read-back per chunk.  ``batched=False`` runs view by view (one read-back each).
     """
+    takes_grad_out = False
+    if loss_returns_grad:
+        try:
+            import inspect
+            takes_grad_out = "grad_out" in inspect.signature(loss_fn).parameters
+        except (TypeError, ValueError):
+            takes_grad_out = False
     xyz, opacity = pc.get_xyz, pc.get_opacity
     scales, rotations, shs = pc.get_scaling, pc.get_rotation, pc.get_features
     inputs = dict(means3D=xyz, shs=shs, opacities=opacity, scales=scales, rotations=rotations)
@@ -246,7 +254,7 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
             for k in range(len(chunk)):
                 vi = c0 + k
                 if loss_returns_grad:
-                    res = loss_fn(color[k], invdepth[k], vi)
+                    res = loss_fn(color[k], invdepth[k], vi, grad_out=g_color[k]) if takes_grad_out else loss_fn(color[k], invdepth[k], vi)
                     loss, g_img = res[0], res[1]
                     g_dep = res[2] if len(res) > 2 else None
                 else:
@@ -257,7 +265,7 @@ def render_views_backward(viewpoint_cameras: Sequence, pc, pipe, bg_color: torch
                     g_img, g_dep = torch.autograd.grad(loss, (img, dep), allow_unused=True)
                 if g_img is None:
                     g_color[k].zero_()
-                else:
+                elif g_img.data_ptr() != g_color[k].data_ptr():
                     g_color[k].copy_(g_img)
                 if g_dep is not None:
                     if g_depth is None:

@@ -318,3 +318,27 @@ def test_fused_reduce_scatter_source(on_host):
         assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max()) + 1e-12, k
         assert float(full[0][rows:].abs().max()) == 0.0 and float(full[1][:rows].abs().max()) == 0.0      # nobody touched foreign rows
         assert float(full[1][P:].abs().max()) == 0.0                                                         # padding rows: zeros
+
+
+def test_loss_gradient_written_in_place(on_host):
+    """A loss_fn with a ``grad_out`` parameter receives its slot of the batch's gradient buffer: same result as the copying path."""
+    import bench
+    from gaussian_renderer import GradientBucket, render_views_backward
+    dgr = on_host
+    scene, cams, gts, bg = _batch_inputs(n=200)
+
+    def run(in_place):
+        pc = bench.BenchGaussians(scene, 3, "cpu")
+        bucket = GradientBucket(pc.parameters())
+        seen = []
+
+        def with_slot(img, d, i, grad_out=None):
+            seen.append(grad_out is not None)
+            return dgr.l1_loss_and_grad(img, gts[i], grad_out=grad_out)
+        plain = lambda img, d, i: dgr.l1_loss_and_grad(img, gts[i])
+        out = render_views_backward(cams, pc, bench.Pipe(), bg, with_slot if in_place else plain, loss_returns_grad=True, overwrite=True)
+        assert seen == ([True, True] if in_place else [])
+        return out["losses"].numpy(), bucket.flat.numpy().copy()
+
+    (l0, g0), (l1, g1) = run(False), run(True)
+    assert np.array_equal(l0, l1) and np.abs(g0 - g1).max() <= 1e-6 * np.abs(g0).max()
