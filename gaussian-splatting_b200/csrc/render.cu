@@ -32,6 +32,26 @@ namespace gsb {
 
 constexpr int RB = 256;  // gaussians staged per round, forward
 
+// One staged gaussian = ONE 48-byte shared-memory record, so that the blend loops form one address per list entry and read the
+// record with two or three 128-bit loads at fixed offsets.  (The ncu source page of the round-2 kernels showed 42 % of the forward
+// loop's executed instructions to be integer / address / predicate work: separate arrays meant one address computation each, the
+// third one -- behind the alpha test -- rebuilt from the CTA's shared-window base every iteration for lack of registers.)
+struct alignas(16) StagedRec {
+    ulonglong2 w0;      // {(x, y), (A', C')} as two f32x2
+    float4 q1;          // {B', opacity, r, g}
+    float b, inv_z;
+    uint32_t row;       // backward: row of the gradient accumulator (view * P + gaussian id)
+    uint32_t pad;
+};
+static_assert(sizeof(StagedRec) == 48, "three 16-byte units");
+
+__device__ __forceinline__ void stage_record(StagedRec &dst, float4 q0, float4 q1, const float4 q2, const uint32_t row) {
+    stage_scale(q0, q1);   // conic pre-scaled for the log2-domain exponent (blend_common.cuh): q0 = {x, y, A', C'}, q1 = {B', o, r, g}
+    dst.w0 = make_ulonglong2(pk(q0.x, q0.y), pk(q0.z, q0.w));
+    dst.q1 = q1;
+    dst.b = q2.x; dst.inv_z = q2.y; dst.row = row; dst.pad = 0u;
+}
+
 // per-view base pointers of a batched launch (blockIdx.y = view)
 struct FwdView {
     const uint2 *ranges;
@@ -70,8 +90,7 @@ __device__ __forceinline__ FwdView fwd_view(const RenderFwdArgs &a) {
 __global__ void __launch_bounds__(256, 6)
 render_fwd_kernel(const RenderFwdArgs a) {
     constexpr int WARPS = 8, NT = 32 * WARPS;
-    __shared__ float4 s0[RB], s1[RB];
-    __shared__ float2 s2[RB];
+    __shared__ StagedRec srec[RB];
     __shared__ uint8_t smask[RB];
     __shared__ uint8_t slist[WARPS][RB];
     const FwdView f = fwd_view(a);
@@ -93,26 +112,26 @@ render_fwd_kernel(const RenderFwdArgs a) {
 
     for (int rd = 0; rd < rounds; ++rd) {
         if (__syncthreads_count(done) == NT) break;
-#pragma unroll
-        for (int k = (int)threadIdx.x; k < RB; k += NT) {
-            const int idx = rd * RB + k;
-            if (idx < todo) {
-                const uint32_t g = f.point_list[range.x + idx];
-                const float4 *rec = f.splat + (size_t)g * SPLAT_F4;
-                float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
-                const float4 q2 = __ldg(rec + 2);
-                smask[k] = (uint8_t)patch_mask(q0.x, q0.y, q0.z, q0.w, q1.x, q2.z, ox, oy);
-                stage_scale(q0, q1);   // conic pre-scaled for the log2-domain exponent (blend_common.cuh)
-                s0[k] = q0; s1[k] = q1; s2[k] = make_float2(q2.x, q2.y);
-            }
+        const int idx = rd * RB + threadIdx.x;
+        if (idx < todo) {
+            const uint32_t g = f.point_list[range.x + idx];
+            const float4 *rec = f.splat + (size_t)g * SPLAT_F4;
+            const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
+            smask[threadIdx.x] = (uint8_t)patch_mask(q0.x, q0.y, q0.z, q0.w, q1.x, q2.z, ox, oy);
+            stage_record(srec[threadIdx.x], q0, q1, q2, 0u);
         }
         __syncthreads();
         const int n = min(RB, todo - rd * RB);
         const int cnt = compact_hits(smask, n, 1u << w, slist[w]);
-        for (int k = 0; !done && k < cnt; ++k) {
+        // The loop bound is per lane: a pixel that is done sets its bound to zero (one move) instead of carrying a flag through
+        // the loop condition; the index of the last contributor is kept as the list position and turned into `last` once per round.
+        int lim = done ? 0 : cnt;
+        int lastj = -1;
+        for (int k = 0; k < lim; ++k) {
             const int j = slist[w][k];
-            const ulonglong2 w0 = reinterpret_cast<const ulonglong2 *>(s0)[j];   // {(x, y), (A', C')} as two f32x2
-            const float4 q1 = s1[j];
+            const StagedRec &r = srec[j];
+            const ulonglong2 w0 = r.w0;
+            const float4 q1 = r.q1;
             // Same roundings as the backward kernel (x - px == x + (-px) in IEEE arithmetic; each packed lane is an ordinary
             // round-to-nearest multiply), so both passes agree bit for bit on alpha -- in 6 issue slots instead of 9.
             const f32x2 d2 = add2((f32x2)w0.x, negp);
@@ -125,14 +144,17 @@ render_fwd_kernel(const RenderFwdArgs a) {
             const float alpha = fminf(ALPHA_MAX, __fmul_rn(q1.y, ex2_approx(power)));
             if (alpha < ALPHA_MIN) continue;
             const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-            if (test_T < T_STOP) { done = true; continue; }
-            const float2 q2 = s2[j];
+            const bool go = !(test_T < T_STOP);
+            lim = go ? lim : 0;                       // the stop test ends this pixel's loop: one select, no flag to carry
+            if (!go) continue;
             const float wgt = __fmul_rn(alpha, T);
-            C0 = __fmaf_rn(q1.z, wgt, C0); C1 = __fmaf_rn(q1.w, wgt, C1); C2 = __fmaf_rn(q2.x, wgt, C2);
-            Dp = __fmaf_rn(q2.y, wgt, Dp);
+            C0 = __fmaf_rn(q1.z, wgt, C0); C1 = __fmaf_rn(q1.w, wgt, C1); C2 = __fmaf_rn(r.b, wgt, C2);
+            Dp = __fmaf_rn(r.inv_z, wgt, Dp);
             T = test_T;
-            last = (uint32_t)(rd * RB + j + 1);
+            lastj = j;
         }
+        done = done || (cnt != 0 && lim == 0);      // bound zeroed by the stop test
+        if (lastj >= 0) last = (uint32_t)(rd * RB + lastj + 1);
     }
     if (inside) {
         const size_t pid = (size_t)py * a.W + px, HW = (size_t)a.W * a.H;
@@ -151,9 +173,7 @@ template <bool DEPTH, int MINB>
 __global__ void __launch_bounds__(64, MINB)
 render_bwd_kernel(const RenderBwdArgs a) {
     constexpr int NT = 64;
-    __shared__ float4 s0[MP_R], s1[MP_R];
-    __shared__ float2 s2[MP_R];
-    __shared__ uint32_t sid[MP_R];
+    __shared__ StagedRec srec[MP_R];
     __shared__ uint32_t s_max;
     __shared__ uint8_t smask[MP_R];
     __shared__ uint8_t slist[2][MP_R];
@@ -164,7 +184,9 @@ render_bwd_kernel(const RenderBwdArgs a) {
     const uint32_t *const n_contrib = a.n_contrib + v * a.sv_image;
     const float *const dL_dcolor = a.dL_dcolor + v * a.sv_color;
     const float *const out_color = a.out_color + v * a.sv_color;
-    float *const dacc = a.dacc + v * a.sv_dacc;
+    // accumulator rows are addressed as (view * P + gaussian) from the batch's base: the per-view offset goes into the staged
+    // record once per 128 entries instead of being rebuilt in the loop (five uniform-pipe instructions per iteration before)
+    const uint32_t row0 = (uint32_t)(v * (a.sv_dacc / DACC_STRIDE));
     const uint32_t want = 0xfu << (4 * (threadIdx.x >> 5));
     const int tile = a.tile_order ? (int)a.tile_order[v * a.sv_ranges + blockIdx.x] : (int)blockIdx.x;
     const int ox = (tile % a.gx) * TILE, oy = (tile / a.gx) * TILE;
@@ -212,18 +234,20 @@ render_bwd_kernel(const RenderBwdArgs a) {
         for (int k = t; k < n; k += NT) {
             const uint32_t g = point_list[range.x + base + k];
             const float4 *rec = splat + (size_t)g * SPLAT_F4;
-            float4 q0 = __ldg(rec), q1 = __ldg(rec + 1);
-            const float4 q2 = __ldg(rec + 2);
+            const float4 q0 = __ldg(rec), q1 = __ldg(rec + 1), q2 = __ldg(rec + 2);
             smask[k] = (uint8_t)patch_mask(q0.x, q0.y, q0.z, q0.w, q1.x, q2.z, (float)ox, (float)oy);
-            stage_scale(q0, q1);
-            s0[k] = q0; s1[k] = q1; s2[k] = make_float2(q2.x, q2.y); sid[k] = g;
+            stage_record(srec[k], q0, q1, q2, row0 + g);
         }
         __syncthreads();
         const int nw = max(0, min(n, my_todo - base));
         const int cnt = compact_hits(smask, nw, want, slist[t >> 5]);
         for (int kk = 0; kk < cnt; ++kk) {
             const int j = (int)slist[t >> 5][kk];
-            const float4 q0 = s0[j], q1 = s1[j];
+            const StagedRec &rec = srec[j];
+            const float4 q1 = rec.q1;
+            float4 q0;                                   // {x, y, A', C'}
+            unpk((f32x2)rec.w0.x, q0.x, q0.y);
+            unpk((f32x2)rec.w0.y, q0.z, q0.w);
             const uint32_t pos = (uint32_t)(base + j + 1);
             // column-packed terms (shared by both rows): dx, A' dx^2, B' dx
             const f32x2 dx2 = pk(q0.x - fx0, q0.x - (fx0 + 1.0f));   // same rounding as the forward kernel
@@ -254,7 +278,7 @@ render_bwd_kernel(const RenderBwdArgs a) {
                 }
             }
             if (!__any_sync(0xffffffffu, any)) continue;
-            const float2 q2 = s2[j];
+            const float2 q2 = make_float2(rec.b, rec.inv_z);
             f32x2 m_x = pk1(0.f), m_y = m_x, m_xx = m_x, m_xy = m_x, m_yy = m_x, g_o = m_x, g_r = m_x, g_g = m_x, g_b = m_x, g_d = m_x;
             const f32x2 cr = pk1(q1.z), cg = pk1(q1.w), cb = pk1(q2.x), cd = pk1(q2.y), op2 = pk1(q1.y);
 #pragma unroll
@@ -285,7 +309,7 @@ render_bwd_kernel(const RenderBwdArgs a) {
                 m_xx = fma2(u, dx2, m_xx); m_xy = fma2(u, dy2, m_xy); m_yy = fma2(vv, dy2, m_yy);
             }
             const int lane = t & 31;
-            float *d = dacc + (size_t)sid[j] * DACC_STRIDE;
+            float *d = a.dacc + (size_t)rec.row * DACC_STRIDE;
             // both shuffle networks are issued before either atomic so that their (independent) chains overlap
             const float ra = reduce8_transposed(hsum(m_x), hsum(m_y), hsum(m_xx), hsum(m_xy), hsum(m_yy), hsum(g_o), hsum(g_r), hsum(g_g));
             float rb;

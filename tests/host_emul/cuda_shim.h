@@ -53,6 +53,7 @@ struct float3 { float x, y, z; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(8) uint2 { unsigned x, y; };
 struct alignas(16) ulonglong2 { unsigned long long x, y; };
+inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
 struct alignas(16) uint4 { unsigned x, y, z, w; };
 struct alignas(8) int2 { int x, y; };
 struct alignas(16) int4 { int x, y, z, w; };
