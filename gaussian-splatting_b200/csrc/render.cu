@@ -140,9 +140,8 @@ render_fwd_kernel(const RenderFwdArgs a) {
             unpk(d2, dx, dy);
             unpk(u2, Axx, Cyy);
             const float power = power2_at(Axx, Cyy, __fmul_rn(q1.x, dx), dy);
-            if (power > 0.0f) continue;
             const float alpha = fminf(ALPHA_MAX, __fmul_rn(q1.y, ex2_approx(power)));
-            if (alpha < ALPHA_MIN) continue;
+            if (!(alpha >= ALPHA_MIN && power <= 0.0f)) continue;      // one branch for both rejections (power > 0 is a rounding rarity)
             const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
             const bool go = !(test_T < T_STOP);
             lim = go ? lim : 0;                       // the stop test ends this pixel's loop: one select, no flag to carry
@@ -165,6 +164,16 @@ render_fwd_kernel(const RenderFwdArgs a) {
         f.out_color[2 * HW + pid] = C2 + T * __ldg(f.bg + 2);
         f.out_invdepth[pid] = Dp;
     }
+}
+
+// *(float *)(base + off) += v (relaxed, device scope, no return value) for the lanes with off >= 0, as ONE predicated instruction
+__device__ __forceinline__ void red_add_if(char *base, const int off, const float v) {
+#ifdef GSB_HOST_EMUL
+    if (off >= 0) atomicAdd(reinterpret_cast<float *>(base + off), v);
+#else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ge.s32 p, %1, 0;\n\t@p red.global.add.f32 [%0], %2;\n\t}"
+                 ::"l"(base + (off < 0 ? 0 : off)), "r"(off), "f"(v) : "memory");
+#endif
 }
 
 // Backward.  Arithmetic per lane is IEEE round-to-nearest; the packed instructions compute exactly what their scalar
@@ -227,6 +236,11 @@ render_bwd_kernel(const RenderBwdArgs a) {
     const int todo = (int)s_max;
     const int my_todo = (int)my_max;
     const f32x2 one2 = pk1(1.0f);
+    const int lane = t & 31;
+    int red_off = (lane & 3) == 0 ? 4 * (lane >> 2) : (lane == 1 ? 32 : (DEPTH && lane == 17 ? 36 : -1));
+#ifndef GSB_HOST_EMUL
+    asm volatile("" : "+r"(red_off));      // opaque from here on: kept in a register instead of being rebuilt from the lane id in the loop
+#endif
 
     for (int base = 0; base < todo; base += MP_R) {
         __syncthreads();
@@ -308,9 +322,7 @@ render_bwd_kernel(const RenderBwdArgs a) {
                 m_x = add2(m_x, u); m_y = add2(m_y, vv);
                 m_xx = fma2(u, dx2, m_xx); m_xy = fma2(u, dy2, m_xy); m_yy = fma2(vv, dy2, m_yy);
             }
-            const int lane = t & 31;
-            float *d = a.dacc + (size_t)rec.row * DACC_STRIDE;
-            // both shuffle networks are issued before either atomic so that their (independent) chains overlap
+            // both shuffle networks are issued before the atomic so that their (independent) chains overlap
             const float ra = reduce8_transposed(hsum(m_x), hsum(m_y), hsum(m_xx), hsum(m_xy), hsum(m_yy), hsum(g_o), hsum(g_r), hsum(g_g));
             float rb;
             if (DEPTH) {
@@ -320,12 +332,10 @@ render_bwd_kernel(const RenderBwdArgs a) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) rb += __shfl_xor_sync(0xffffffffu, rb, o);
             }
-            if ((lane & 3) == 0) atomicAdd(d + (lane >> 2), ra);
-            if (DEPTH) {
-                if ((lane & 15) == 1) atomicAdd(d + 8 + (lane >> 4), rb);
-            } else {
-                if (lane == 1) atomicAdd(d + 8, rb);
-            }
+            // ONE predicated reduction instruction for the ten sums: lanes 0, 4, ..., 28 hold sums 0..7 (ra), lane 1 (and 17 with a
+            // depth gradient) the remaining ones (rb); red_off is the lane's byte offset into the 48-byte accumulator row or -1
+            // (computed once per thread: the loop used to rebuild the lane roles and branch around two atomics every iteration).
+            red_add_if(reinterpret_cast<char *>(a.dacc + (size_t)rec.row * DACC_STRIDE), red_off, red_off >= 32 ? rb : ra);
         }
     }
 }
