@@ -141,16 +141,17 @@ render_fwd_kernel(const RenderFwdArgs a) {
             unpk(u2, Axx, Cyy);
             const float power = power2_at(Axx, Cyy, __fmul_rn(q1.x, dx), dy);
             const float alpha = fminf(ALPHA_MAX, __fmul_rn(q1.y, ex2_approx(power)));
-            if (!(alpha >= ALPHA_MIN && power <= 0.0f)) continue;      // one branch for both rejections (power > 0 is a rounding rarity)
             const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-            const bool go = !(test_T < T_STOP);
-            lim = go ? lim : 0;                       // the stop test ends this pixel's loop: one select, no flag to carry
-            if (!go) continue;
-            const float wgt = __fmul_rn(alpha, T);
+            // No branch in the loop body: 94 % of the warp's iterations have at least one accepting lane (ncu source page), so the
+            // accept block runs anyway; predicating it saves the branch and its reconvergence pair.
+            const bool hit = alpha >= ALPHA_MIN && power <= 0.0f;       // both rejections (power > 0 is a rounding rarity)
+            const bool go = hit && !(test_T < T_STOP);
+            lim = (hit && !go) ? 0 : lim;                                // the stop test ends this pixel's loop
+            const float wgt = go ? __fmul_rn(alpha, T) : 0.0f;
             C0 = __fmaf_rn(q1.z, wgt, C0); C1 = __fmaf_rn(q1.w, wgt, C1); C2 = __fmaf_rn(r.b, wgt, C2);
             Dp = __fmaf_rn(r.inv_z, wgt, Dp);
-            T = test_T;
-            lastj = j;
+            T = go ? test_T : T;
+            lastj = go ? j : lastj;
         }
         done = done || (cnt != 0 && lim == 0);      // bound zeroed by the stop test
         if (lastj >= 0) last = (uint32_t)(rd * RB + lastj + 1);
