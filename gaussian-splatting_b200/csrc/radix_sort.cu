@@ -276,11 +276,15 @@ static int onesweep_sort(uint32_t *keys, uint32_t *vals, uint32_t *keys_alt, uin
                          cudaStream_t stream, int V, size_t sv) {
     OnesweepPasses ps;
     ps.npass = 0;
-    for (int bit = begin_bit; bit < end_bit; bit += RADIX_BITS) {
-        if (ps.npass == OS_MAX_PASSES) { set_error("onesweep: more than %d passes", OS_MAX_PASSES); return GSB_ERR_ARGUMENT; }
-        const int bits = (end_bit - bit) < RADIX_BITS ? (end_bit - bit) : RADIX_BITS;
-        ps.shift[ps.npass] = bit;
-        ps.mask[ps.npass] = (1u << bits) - 1u;
+    // the key bits are split EVENLY over the fewest passes (13 tile bits = 7 + 6, not 8 + 5): a pass with fewer digits writes
+    // longer runs per digit out of every block
+    const int total_bits = end_bit - begin_bit, npass = (total_bits + RADIX_BITS - 1) / RADIX_BITS;
+    if (npass > OS_MAX_PASSES) { set_error("onesweep: more than %d passes", OS_MAX_PASSES); return GSB_ERR_ARGUMENT; }
+    for (int p = 0, bit = begin_bit; p < npass; ++p) {
+        const int bits = total_bits / npass + (p < total_bits % npass ? 1 : 0);
+        ps.shift[p] = bit;
+        ps.mask[p] = (1u << bits) - 1u;
+        bit += bits;
         ++ps.npass;
     }
     const int ipt = sort_ipt(n);

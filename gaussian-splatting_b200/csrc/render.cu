@@ -306,8 +306,13 @@ render_bwd_kernel(const RenderBwdArgs a) {
                 f32x2 g = fma2(dL2[r], cb, fma2(dL1[r], cg, mul2(dL0[r], cr)));
                 if (DEPTH) g = fma2(dLd[r], cd, g);
                 F[r] = fma2(w, g, F[r]);
-                g_r = fma2(w, dL0[r], g_r); g_g = fma2(w, dL1[r], g_g); g_b = fma2(w, dL2[r], g_b);
-                if (DEPTH) g_d = fma2(w, dLd[r], g_d);
+                if (r == 0) {
+                    g_r = mul2(w, dL0[r]); g_g = mul2(w, dL1[r]); g_b = mul2(w, dL2[r]);
+                    if (DEPTH) g_d = mul2(w, dLd[r]);
+                } else {
+                    g_r = fma2(w, dL0[r], g_r); g_g = fma2(w, dL1[r], g_g); g_b = fma2(w, dL2[r], g_b);
+                    if (DEPTH) g_d = fma2(w, dLd[r], g_d);
+                }
                 const f32x2 om = sub2(one2, ai);
                 float om0, om1;
                 unpk(om, om0, om1);
@@ -316,12 +321,16 @@ render_bwd_kernel(const RenderBwdArgs a) {
                 const f32x2 dLda = sub2(mul2(T[r], g), mul2(sub2(S[r], F[r]), rcp));
                 T[r] = mul2(T[r], om);
                 const f32x2 Gd = mul2(Gm, dLda);
-                g_o = add2(g_o, Gd);
                 const f32x2 tt = mul2(op2, Gd);
                 const f32x2 dy2 = pk1(dy[r]);
                 const f32x2 u = mul2(tt, dx2), vv = mul2(tt, dy2);
-                m_x = add2(m_x, u); m_y = add2(m_y, vv);
-                m_xx = fma2(u, dx2, m_xx); m_xy = fma2(u, dy2, m_xy); m_yy = fma2(vv, dy2, m_yy);
+                if (r == 0) {     // the sums START at the first row's terms (0 + x is not folded away: it turns -0 into +0)
+                    g_o = Gd; m_x = u; m_y = vv;
+                    m_xx = mul2(u, dx2); m_xy = mul2(u, dy2); m_yy = mul2(vv, dy2);
+                } else {
+                    g_o = add2(g_o, Gd); m_x = add2(m_x, u); m_y = add2(m_y, vv);
+                    m_xx = fma2(u, dx2, m_xx); m_xy = fma2(u, dy2, m_xy); m_yy = fma2(vv, dy2, m_yy);
+                }
             }
             // both shuffle networks are issued before the atomic so that their (independent) chains overlap
             const float ra = reduce8_transposed(hsum(m_x), hsum(m_y), hsum(m_xx), hsum(m_xy), hsum(m_yy), hsum(g_o), hsum(g_r), hsum(g_g));
