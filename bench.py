@@ -163,6 +163,12 @@ class ClockSampler:
         self.proc = None
         self.stop_flag = False
         self.t_start, self.t_end = 0.0, float("inf")
+        # NVML calls share driver locks with kernel launches and occasionally take tens of ms: a launch thread that has no lead over
+        # the device yet (every timed region starts from a synchronize) passes such a stall on to the device, and through the
+        # collective to every rank.  Inside a timed region the sampler therefore waits until the launch thread has enqueued the
+        # region's work (timed() calls hold() / release()); the samples are still taken under load, while the device drains.
+        self.clear = threading.Event()
+        self.clear.set()
 
     def start(self):
         try:
@@ -175,6 +181,8 @@ class ClockSampler:
 
             def loop():
                 while not self.stop_flag:
+                    if not self.clear.wait(0.05):
+                        continue
                     try:
                         sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
                         try:
@@ -184,7 +192,7 @@ class ClockSampler:
                         self.samples.append((time.time(), float(sm), float(mx), int(r)))
                     except Exception:
                         pass
-                    time.sleep(0.1)
+                    time.sleep(0.02 if self.draining else 0.1)
             self.thread = threading.Thread(target=loop, daemon=True)
             self.thread.start()
             self.kind = "nvml"
@@ -212,6 +220,18 @@ class ClockSampler:
             self.kind = "nvidia-smi"
         except Exception:
             self.kind = "unavailable"
+
+    draining = False
+
+    def hold(self):
+        """the launch thread is about to enqueue a timed region: no NVML calls until release()"""
+        self.draining = False
+        self.clear.clear()
+
+    def release(self):
+        """the region's work is enqueued (the device is still executing it): sample now, every 20 ms"""
+        self.draining = True
+        self.clear.set()
 
     def mark(self, which):
         """start / end of the timed region (wall clock): only samples taken inside it are reported."""
@@ -553,20 +573,26 @@ def main():
                 dist.barrier()
             torch.cuda.synchronize()
             marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+            sampler.hold()
             t0 = time.perf_counter()
             marks[0].record()
             for k in range(steps):
                 step(host_inputs)
                 marks[k + 1].record()
             host_ms = (time.perf_counter() - t0) * 1e3
+            sampler.release()
             torch.cuda.synchronize()
+            sampler.draining = False
             if world > 1:
                 dist.barrier()
         finally:
             gc.enable()
+            sampler.clear.set()
+            sampler.draining = False
         per_step = [marks[k].elapsed_time(marks[k + 1]) for k in range(steps)]
         step_stats[host_inputs] = {"min": round(min(per_step), 3), "median": round(statistics.median(per_step), 3),
-                                   "max": round(max(per_step), 3), "host_enqueue_ms_per_step": round(host_ms / steps, 3)}
+                                   "max": round(max(per_step), 3), "slowest_step": int(max(range(steps), key=per_step.__getitem__)),
+                                   "host_enqueue_ms_per_step": round(host_ms / steps, 3)}
         ms = torch.tensor([marks[0].elapsed_time(marks[steps])], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
