@@ -596,6 +596,14 @@ def main():
         ms = torch.tensor([marks[0].elapsed_time(marks[steps])], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            # every rank's own view of the region (outside the timing): which launch thread fell behind, if any
+            mine = torch.tensor([host_ms / steps, float(step_stats[host_inputs]["slowest_step"]), max(per_step),
+                                 statistics.median(per_step)], device=dev, dtype=torch.float32)
+            every = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine)
+            rows = [[round(float(x), 3) for x in t.tolist()] for t in every]
+            step_stats[host_inputs]["ranks"] = {"host_enqueue_ms_per_step": [r[0] for r in rows], "slowest_step": [int(r[1]) for r in rows],
+                                                "max": [r[2] for r in rows], "median": [r[3] for r in rows]}
         return float(ms.item())
 
     def measured(host_inputs: bool):
