@@ -4,6 +4,7 @@
 
     training_setup :176-211 | update_learning_rate :213-223 | reset_opacity :258-261 | densify_and_prune :452-469
     add_densification_stats :471-473 | oneupSHdegree :146-148 | activations :102-130 | optimizer.step() train.py:178-186
+    per-image exposures :133-140, :173-176, :201-217, :264-274 (plain torch parameters with their own Adam, as in the reference)
 
 What differs, and why.  The reference keeps six ``nn.Parameter`` tensors, lets autograd chain the rasterizer's gradients
 through exp / sigmoid / normalize / cat, runs ``torch.optim.Adam`` group by group, and rebuilds every tensor and both Adam
@@ -123,6 +124,13 @@ class GaussianModel:
         self.lr: Dict[str, float] = {}
         self.betas, self.eps = (0.9, 0.999), 1e-15
         self._xyz_sched = None
+        # per-image exposure (gaussian_model.py:133-140,173-176): ordinary torch parameters next to the flat store -- a [N,3,4]
+        # affine colour transform per training image, applied by render(use_trained_exp=True), with its own Adam
+        self._exposure = None
+        self.exposure_mapping: Dict[str, int] = {}
+        self.pretrained_exposures = None
+        self.exposure_optimizer = None
+        self._exposure_sched = None
 
     # ---- construction ----------------------------------------------------------------------------------------------
     def create_from_tensors(self, xyz, features_dc, features_rest, scaling, rotation, opacity, spatial_lr_scale: float = 1.0):
@@ -145,10 +153,54 @@ class GaussianModel:
         self.max_radii2D = torch.zeros(P, device=dev)
         return self
 
-    def create_from_pcd(self, points: torch.Tensor, colors: torch.Tensor, spatial_lr_scale: float = 1.0):
-        """Initialisation from a point cloud (gaussian_model.py:150-172): colours -> SH DC band (RGB2SH, utils/sh_utils.py:114-115),
+    def create_exposures(self, cam_infos, device=None):
+        """One identity 3x4 exposure per training image (gaussian_model.py:173-176).  ``cam_infos``: objects with an
+        ``image_name`` attribute (the reference's CameraInfo) or the names themselves."""
+        names = [c if isinstance(c, str) else c.image_name for c in cam_infos]
+        dev = device if device is not None else (self.store.device if self.store is not None else "cpu")
+        self.exposure_mapping = {name: idx for idx, name in enumerate(names)}
+        self.pretrained_exposures = None
+        self._exposure = torch.nn.Parameter(torch.eye(3, 4, device=dev)[None].repeat(len(names), 1, 1).requires_grad_(True))
+        return self
+
+    @property
+    def get_exposure(self):
+        return self._exposure
+
+    def get_exposure_from_name(self, image_name):
+        """gaussian_model.py:136-140: the trained exposure of an image, or the one loaded from exposure.json."""
+        if self.pretrained_exposures is None:
+            if self._exposure is None:
+                raise RuntimeError("no exposures: call create_exposures(cam_infos) (or create_from_pcd(..., cam_infos=...)) first")
+            return self._exposure[self.exposure_mapping[image_name]]
+        return self.pretrained_exposures[image_name]
+
+    def load_exposures(self, exposure_file: str, device="cuda") -> bool:
+        """exposure.json as Scene.save writes it (scene/__init__.py:87-94; read at gaussian_model.py:264-274):
+        {image_name: 3x4 nested list}.  Returns False (and keeps training exposures) when the file does not exist."""
+        import json
+        import os
+        if not os.path.exists(exposure_file):
+            self.pretrained_exposures = None
+            return False
+        with open(exposure_file, "r") as f:
+            exposures = json.load(f)
+        self.pretrained_exposures = {name: torch.tensor(exposures[name], dtype=torch.float32, device=device).requires_grad_(False)
+                                     for name in exposures}
+        return True
+
+    def save_exposures(self, exposure_file: str) -> None:
+        """The exposure.json of scene/__init__.py:87-94."""
+        import json
+        table = {name: self.get_exposure_from_name(name).detach().cpu().numpy().tolist() for name in self.exposure_mapping}
+        with open(exposure_file, "w") as f:
+            json.dump(table, f, indent=2)
+
+    def create_from_pcd(self, points: torch.Tensor, colors: torch.Tensor, spatial_lr_scale: float = 1.0, cam_infos=None):
+        """Initialisation from a point cloud (gaussian_model.py:150-176): colours -> SH DC band (RGB2SH, utils/sh_utils.py:114-115),
         higher bands zero, isotropic log-scales from the mean squared distance to the three nearest neighbours (the
-        ``distCUDA2`` call, here gsb_knn_mean_dist2), identity rotations, opacity 0.1.  ``points`` [N,3], ``colors`` [N,3] in [0,1]."""
+        ``distCUDA2`` call, here gsb_knn_mean_dist2), identity rotations, opacity 0.1, and -- with ``cam_infos`` -- one identity
+        exposure per training image.  ``points`` [N,3], ``colors`` [N,3] in [0,1]."""
         pts = points.detach().to(torch.float32).reshape(-1, 3).contiguous()
         N, M = int(pts.shape[0]), self.sh_coeffs
         dc = ((colors.detach().to(pts.device, torch.float32).reshape(N, 3) - 0.5) / 0.28209479177387814).reshape(N, 1, 3)
@@ -157,6 +209,8 @@ class GaussianModel:
         rots = torch.zeros((N, 4), device=pts.device)
         rots[:, 0] = 1
         opac = torch.full((N, 1), math.log(0.1 / 0.9), device=pts.device)          # inverse_sigmoid(0.1)
+        if cam_infos is not None:
+            self.create_exposures(cam_infos, device=pts.device)
         return self.create_from_tensors(pts, dc, torch.zeros((N, M - 1, 3), device=pts.device), scales, rots, opac, spatial_lr_scale)
 
     def _allocate(self, P: int, device):
@@ -256,8 +310,17 @@ class GaussianModel:
         self._skip_next = set()
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
+        if self._exposure is not None:       # gaussian_model.py:201,208-211 (train.py:178-179 steps it)
+            self.exposure_optimizer = torch.optim.Adam([self._exposure])
+            if hasattr(training_args, "exposure_lr_init"):
+                self._exposure_sched = dict(lr_init=g("exposure_lr_init"), lr_final=g("exposure_lr_final"),
+                                            lr_delay_steps=int(g("exposure_lr_delay_steps")), lr_delay_mult=g("exposure_lr_delay_mult"),
+                                            max_steps=int(g("iterations")))
 
     def update_learning_rate(self, iteration: int) -> float:
+        if self.pretrained_exposures is None and self.exposure_optimizer is not None and self._exposure_sched is not None:
+            for param_group in self.exposure_optimizer.param_groups:
+                param_group["lr"] = expon_lr(iteration, **self._exposure_sched)
         self.lr["xyz"] = expon_lr(iteration, **self._xyz_sched)
         return self.lr["xyz"]
 
@@ -372,8 +435,11 @@ class GaussianModel:
         write_gaussian_ply(path, c(self._xyz), c(self._features_dc), c(self._features_rest), c(self._opacity), c(self._scaling),
                            c(self._rotation))
 
-    def load_ply(self, path: str, device="cuda", spatial_lr_scale: Optional[float] = None):
+    def load_ply(self, path: str, device="cuda", spatial_lr_scale: Optional[float] = None, use_train_test_exp: bool = False):
         from .ply import read_gaussian_ply
+        if use_train_test_exp:               # gaussian_model.py:264-274: <model>/exposure.json two levels above the ply
+            import os
+            self.load_exposures(os.path.join(os.path.dirname(path), os.pardir, os.pardir, "exposure.json"), device=device)
         a = {k: torch.from_numpy(v).to(device) for k, v in read_gaussian_ply(path, self.max_sh_degree).items()}
         self.create_from_tensors(a["xyz"], a["features_dc"], a["features_rest"], a["scaling"], a["rotation"], a["opacity"],
                                  self.spatial_lr_scale if spatial_lr_scale is None else spatial_lr_scale)
@@ -406,7 +472,7 @@ class GaussianModel:
     def restore(self, model_args, training_args=None):
         """``restore(model_args, training_args)`` of the reference (gaussian_model.py:78-99): ``model_args`` is the tuple written by
         the reference's or this class's ``capture()`` -- the per-group Adam state (moments and step counts) goes into the flat
-        moments.  The per-image exposure parameters of the reference are not part of this model."""
+        moments.  (As in the reference, the per-image exposures are not part of the tuple: they travel in exposure.json.)"""
         if not isinstance(model_args, (tuple, list)) or len(model_args) != 12:
             raise ValueError("restore: expected the 12-tuple of GaussianModel.capture()")
         (active, xyz, f_dc, f_rest, scaling, rotation, opacity, max_radii2D, grad_accum, denom, opt_dict, spatial) = model_args

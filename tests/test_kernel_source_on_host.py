@@ -195,3 +195,48 @@ def test_checkpoint_contract_of_the_reference(on_host):
     for n in GROUPS:
         assert torch.equal(views_m[n], mom[n]["m"]) and torch.equal(views_v[n], mom[n]["v"]) and m3.group_steps[n] == 2
     assert m3.active_sh_degree == 2 and torch.equal(m3._xyz, p["xyz"])
+
+
+def test_exposure_parameters_follow_the_reference_class(on_host, tmp_path):
+    """Per-image exposures of gaussian_store.GaussianModel (create_exposures / get_exposure_from_name / exposure optimizer and
+    its learning-rate schedule / exposure.json) against a fixture recorded from the reference's OWN scene/gaussian_model.py
+    stepped as train.py:178-179 does (tests/golden/make_golden_exposure.py); the colour transform is the expression of the
+    reference's gaussian_renderer/__init__.py:113-115, which gaussian_renderer.render(use_trained_exp=True) applies."""
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_exposure.npz"))
+    names = [str(n) for n in gold["names"]]
+    lr_init, lr_final, delay_steps, delay_mult, iterations = (float(x) for x in gold["sched"])
+    args = SimpleNamespace(position_lr_init=0.00016, position_lr_final=0.0000016, position_lr_delay_mult=0.01, position_lr_max_steps=30000,
+                           feature_lr=0.0025, opacity_lr=0.025, scaling_lr=0.005, rotation_lr=0.001, percent_dense=0.01,
+                           exposure_lr_init=lr_init, exposure_lr_final=lr_final, exposure_lr_delay_steps=delay_steps,
+                           exposure_lr_delay_mult=delay_mult, iterations=iterations)
+    g = torch.Generator().manual_seed(1)
+    pts, cols = torch.rand(40, 3, generator=g), torch.rand(40, 3, generator=g)
+    m = GaussianModel(1).create_from_pcd(pts, cols, spatial_lr_scale=1.0, cam_infos=[SimpleNamespace(image_name=n) for n in names])
+    assert m.exposure_mapping == {n: i for i, n in enumerate(names)} and m.pretrained_exposures is None
+    assert torch.equal(m.get_exposure, torch.eye(3, 4)[None].repeat(len(names), 1, 1))
+    m.training_setup(args)
+    imgs, tgts = torch.from_numpy(gold["imgs"]), torch.from_numpy(gold["tgts"])
+    for k, it in enumerate(gold["iters"].tolist()):
+        m.update_learning_rate(it)
+        assert abs(m.exposure_optimizer.param_groups[0]["lr"] - float(gold["lrs"][k])) <= 1e-12 * float(gold["lrs"][k]) + 1e-18
+        i = int(gold["order"][k])
+        exposure = m.get_exposure_from_name(names[i])
+        img = torch.matmul(imgs[i].permute(1, 2, 0), exposure[:3, :3]).permute(2, 0, 1) + exposure[:3, 3, None, None]
+        (img - tgts[i]).abs().mean().backward()
+        m.exposure_optimizer.step()
+        m.exposure_optimizer.zero_grad(set_to_none=True)
+        assert torch.allclose(m.get_exposure.detach(), torch.from_numpy(gold["exposures"][k]), rtol=0, atol=1e-7), k
+    # exposure.json: written as Scene.save does, read back as load_ply(use_train_test_exp=True) does (two levels above the ply)
+    ply_dir = tmp_path / "point_cloud" / "iteration_7"
+    ply_dir.mkdir(parents=True)
+    m.save_exposures(str(tmp_path / "exposure.json"))
+    m.save_ply(str(ply_dir / "point_cloud.ply"))
+    m2 = GaussianModel(1).load_ply(str(ply_dir / "point_cloud.ply"), device="cpu", use_train_test_exp=True)
+    assert set(m2.pretrained_exposures) == set(names)
+    for n in names:
+        assert torch.allclose(m2.get_exposure_from_name(n), m.get_exposure_from_name(n).detach(), rtol=0, atol=1e-7)
+        assert not m2.get_exposure_from_name(n).requires_grad
+    m3 = GaussianModel(1).load_ply(str(ply_dir / "point_cloud.ply"), device="cpu")          # without the flag: nothing loaded
+    assert m3.pretrained_exposures is None
+    with pytest.raises(RuntimeError, match="no exposures"):
+        m3.get_exposure_from_name(names[0])
