@@ -1,4 +1,5 @@
-// blend_common.cuh -- helpers shared by the multi-pixel blend kernels (render_mp.cu, render_ps.cu).
+// blend_common.cuh -- helpers of the blend kernels (render.cu): staged-record scaling, the pinned exponent, packed f32x2 arithmetic,
+// the transposed warp reductions of the backward pass.
 #pragma once
 #include "kernels.cuh"
 #include "patch_cull.cuh"
